@@ -1,0 +1,252 @@
+"""One rank of a collectives correctness battery (stub on CPU, P2P/NVLS on GPUs).
+
+Every check compares the kernel against a plain PyTorch fp32/fp64 reference of
+the same op computed from deterministic per-rank inputs (each rank can
+regenerate every other rank's input from its seed).
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from batch_shipyard_b200.ops import coll  # noqa: E402
+
+
+def gen(rank, n, dtype, device, salt=0):
+    g = torch.Generator().manual_seed(1000 + 17 * rank + salt)
+    if dtype in (torch.int32, torch.int64):
+        return torch.randint(-50, 50, (n,), generator=g, dtype=dtype).to(device)
+    return (torch.randn(n, generator=g, dtype=torch.float32) * 2.0).to(dtype).to(device)
+
+
+def ref_sum(world, n, dtype, salt=0):
+    acc = torch.zeros(n, dtype=torch.float64)
+    for r in range(world):
+        acc += gen(r, n, dtype, "cpu", salt).to(torch.float64)
+    return acc
+
+
+def tol(dtype, world):
+    if dtype in (torch.int32, torch.int64):
+        return 0.0, 0.0
+    if dtype == torch.float64:
+        return 1e-12, 1e-12
+    if dtype == torch.float32:
+        return 1e-5 * world, 1e-5
+    return 0.06 * world, 2e-2  # bf16/f16: one rounding of an fp32-accumulated sum
+
+
+def close(a, b, dtype, world, what):
+    atol, rtol = tol(dtype, world)
+    a = a.detach().to("cpu", torch.float64)
+    b = b.detach().to("cpu", torch.float64)
+    if not torch.allclose(a, b, atol=atol, rtol=rtol):
+        err = (a - b).abs().max().item()
+        raise AssertionError(f"{what}: max err {err} (atol {atol}, rtol {rtol})")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rank", type=int, required=True)
+    ap.add_argument("--world", type=int, required=True)
+    ap.add_argument("--session", required=True)
+    ap.add_argument("--device", type=int, default=-1)
+    ap.add_argument("--transport", default="auto")
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    dev_index = None if a.device < 0 else a.device
+    if dev_index is not None:
+        torch.cuda.set_device(dev_index)
+    comm = coll.Communicator(a.rank, a.world, a.session, dev_index, heap_bytes=(512 << 20) if dev_index is not None else (192 << 20),
+                             transport=a.transport)
+    dev = comm.torch_device
+    W, R = a.world, a.rank
+    sync = (lambda: None) if comm.is_stub else (lambda: torch.cuda.synchronize(dev))
+    checks = 0
+
+    def algos_for(nbytes):
+        if comm.is_stub:
+            return ["auto"]
+        out = ["auto"]
+        if nbytes <= 16 << 10:
+            out.append("ll")
+        if nbytes <= 8 << 20:
+            out.append("oneshot")
+        out.append("twoshot_p2p")
+        if comm.has_multicast:
+            out.append("twoshot_nvls")
+        return out
+
+    sizes = [1, 3, 8, 257, 4096, 65536 + 5] if a.quick else [1, 2, 3, 8, 31, 257, 1000, 4096, 65536 + 5, (1 << 20) + 24, 3 << 20]
+    dtypes = [torch.float32, torch.bfloat16, torch.float64, torch.int32] if a.quick else \
+        [torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int32, torch.int64]
+    # ---- all-reduce: plain (non-symmetric) buffers, every algorithm -----------
+    for dtype in dtypes:
+        for n in sizes:
+            x = gen(R, n, dtype, dev)
+            ref = ref_sum(W, n, dtype)
+            for algo in algos_for(n * x.element_size()):
+                if algo == "twoshot_nvls" and dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                    continue
+                out = torch.empty_like(x)
+                comm.all_reduce(x, out, algo=algo)
+                sync()
+                close(out, ref, dtype, W, f"all_reduce {dtype} n={n} algo={algo}")
+                checks += 1
+    # ---- all-reduce on symmetric buffers, in place, fused scale + cast --------
+    for (din, dout) in [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                        (torch.bfloat16, torch.float32), (torch.float32, torch.bfloat16)]:
+        for n in ([4096 + 3, 1 << 20] if a.quick else [8, 4096 + 3, 1 << 20, (5 << 20) + 9]):
+            xs = comm.alloc(n, din)
+            os_ = comm.alloc(n, dout) if din != dout else xs
+            for algo in algos_for(n * xs.element_size()):
+                if algo in ("ll",):
+                    continue
+                xs.copy_(gen(R, n, din, dev, salt=3))
+                sync()
+                comm.barrier(); sync()
+                comm.all_reduce(xs, os_, scale=1.0 / W, algo=algo)
+                sync()
+                ref = ref_sum(W, n, din, salt=3) / W
+                close(os_, ref, dout if dout != torch.float32 else din, W, f"sym all_reduce {din}->{dout} n={n} {algo}")
+                comm.barrier(); sync()
+                checks += 1
+        comm.reset_heap()
+    # ---- max / min -----------------------------------------------------------
+    for op, fn in (("max", torch.maximum), ("min", torch.minimum)):
+        n = 5000
+        x = gen(R, n, torch.float32, dev, salt=5)
+        ref = gen(0, n, torch.float32, "cpu", salt=5)
+        for r in range(1, W):
+            ref = fn(ref, gen(r, n, torch.float32, "cpu", salt=5))
+        out = torch.empty_like(x)
+        comm.all_reduce(x, out, op=op)
+        sync()
+        close(out, ref, torch.float32, 1, f"all_reduce {op}")
+        checks += 1
+    # ---- reduce-scatter / all-gather / all-to-all / broadcast / rooted ops ---
+    for dtype in (torch.float32, torch.bfloat16):
+        for cnt in (64, 1000, 1 << 16):
+            x = gen(R, cnt * W, dtype, dev, salt=7)
+            out = torch.empty(cnt, dtype=dtype, device=dev)
+            comm.reduce_scatter(x, out)
+            sync()
+            close(out, ref_sum(W, cnt * W, dtype, salt=7)[R * cnt:(R + 1) * cnt], dtype, W, f"reduce_scatter {dtype} {cnt}")
+            g_in = gen(R, cnt, dtype, dev, salt=9)
+            g_out = torch.empty(cnt * W, dtype=dtype, device=dev)
+            comm.all_gather(g_in, g_out)
+            sync()
+            ref = torch.cat([gen(r, cnt, dtype, "cpu", salt=9) for r in range(W)])
+            assert torch.equal(g_out.cpu(), ref), f"all_gather {dtype} {cnt}"
+            a_in = gen(R, cnt * W, dtype, dev, salt=11)
+            a_out = torch.empty_like(a_in)
+            comm.all_to_all(a_in, a_out)
+            sync()
+            ref = torch.cat([gen(r, cnt * W, dtype, "cpu", salt=11)[R * cnt:(R + 1) * cnt] for r in range(W)])
+            assert torch.equal(a_out.cpu(), ref), f"all_to_all {dtype} {cnt}"
+            for root in {0, W - 1}:
+                b = gen(R, cnt, dtype, dev, salt=13)
+                comm.broadcast(b, root=root)
+                sync()
+                assert torch.equal(b.cpu(), gen(root, cnt, dtype, "cpu", salt=13)), f"broadcast {dtype} {cnt} root={root}"
+                r_in = gen(R, cnt, dtype, dev, salt=15)
+                r_out = torch.zeros(cnt, dtype=dtype, device=dev)
+                comm.reduce(r_in, r_out, root=root)
+                sync()
+                if R == root:
+                    close(r_out, ref_sum(W, cnt, dtype, salt=15), dtype, W, f"reduce {dtype} root={root}")
+                ga_out = torch.zeros(cnt * W, dtype=dtype, device=dev)
+                comm.gather(g_in, ga_out, root=root)
+                sync()
+                if R == root:
+                    assert torch.equal(ga_out.cpu(), torch.cat([gen(r, cnt, dtype, "cpu", salt=9) for r in range(W)])), "gather"
+                sc_in = gen(root, cnt * W, dtype, dev, salt=17)
+                sc_out = torch.zeros(cnt, dtype=dtype, device=dev)
+                comm.scatter(sc_in, sc_out, root=root)
+                sync()
+                assert torch.equal(sc_out.cpu(), gen(root, cnt * W, dtype, "cpu", salt=17)[R * cnt:(R + 1) * cnt]), "scatter"
+            checks += 6
+    # symmetric-output variants (zero-copy paths incl. NVLS broadcast/all-gather)
+    cnt = 1 << 18
+    so = comm.alloc(cnt * W, torch.float32)
+    si = gen(R, cnt, torch.float32, dev, salt=19)
+    comm.all_gather(si, so); sync()
+    assert torch.equal(so.cpu(), torch.cat([gen(r, cnt, torch.float32, "cpu", salt=19) for r in range(W)])), "sym all_gather"
+    comm.barrier(); sync()
+    a_in = gen(R, cnt * W, torch.float32, dev, salt=21)
+    comm.all_to_all(a_in, so); sync()
+    assert torch.equal(so.cpu(), torch.cat([gen(r, cnt * W, torch.float32, "cpu", salt=21)[R * cnt:(R + 1) * cnt] for r in range(W)])), "sym all_to_all"
+    comm.barrier(); sync()
+    sb = comm.alloc(cnt, torch.float32)
+    sb.copy_(gen(R, cnt, torch.float32, dev, salt=23)); sync(); comm.barrier(); sync()
+    comm.broadcast(sb, root=W - 1); sync()
+    assert torch.equal(sb.cpu(), gen(W - 1, cnt, torch.float32, "cpu", salt=23)), "sym broadcast"
+    checks += 3
+    comm.barrier(); sync()
+    comm.reset_heap()
+    # ---- put / wait signal ---------------------------------------------------
+    if W > 1:
+        ghost = comm.alloc(1024, torch.float32)
+        ghost.zero_(); sync(); comm.barrier(); sync()
+        peer = (R + 1) % W
+        src = gen(R, 1024, torch.float32, dev, salt=25)
+        comm.put_signal(src, comm.heap_offset(ghost), peer, sig=3)
+        comm.wait_signal(3, 1)
+        sync()
+        assert torch.equal(ghost.cpu(), gen((R - 1) % W, 1024, torch.float32, "cpu", salt=25)), "put_signal"
+        checks += 1
+        comm.barrier(); sync()
+        comm.reset_heap()
+    # ---- fused all-reduce + SGD ------------------------------------------------
+    for (dg, dp) in [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)]:
+        n = 8 * 1237 * W
+        grads = comm.alloc(n, dg)
+        params = comm.alloc(n, dp)
+        lo, cnt_s = comm.shard_range(n)
+        w0 = gen(99, n, torch.float32, "cpu", salt=27)
+        master = w0[lo:lo + cnt_s].clone().to(dev)
+        mom = torch.zeros(cnt_s, dtype=torch.float32, device=dev)
+        lr, mu, wd = 0.1, 0.9, 1e-4
+        hyper = torch.tensor([lr, mu, wd, 1.0 / W], dtype=torch.float32, device=dev)
+        params.copy_(w0.to(dp).to(dev))
+        ref_w = w0.clone().to(torch.float64)
+        ref_m = torch.zeros(n, dtype=torch.float64)
+        for step in range(3):
+            grads.copy_(gen(R, n, dg, dev, salt=29 + step)); sync()
+            comm.fused_allreduce_sgd(grads, params, master, mom, hyper, zero_grads=True)
+            sync()
+            g = ref_sum(W, n, dg, salt=29 + step) / W + wd * ref_w
+            ref_m = mu * ref_m + g
+            ref_w = ref_w - lr * ref_m
+            close(params, ref_w, dp if dp != torch.float32 else dg, W, f"fused_sgd {dg}->{dp} step {step} params")
+            close(master, ref_w[lo:lo + cnt_s], torch.float32 if dg == torch.float32 else torch.bfloat16, W, "fused_sgd master")
+            assert float(grads.abs().max()) == 0.0, "fused_sgd must zero the gradient buffer"
+            checks += 1
+        comm.barrier(); sync()
+        comm.reset_heap()
+    # ---- fp8 block-scaled all-reduce -----------------------------------------
+    n = 128 * 41 * W
+    xin = comm.alloc(n, torch.bfloat16)
+    q = comm.alloc(n, torch.uint8)
+    sc = comm.alloc(n // 32, torch.uint8)
+    xin.copy_(gen(R, n, torch.bfloat16, dev, salt=31)); sync(); comm.barrier(); sync()
+    comm.all_reduce_fp8(xin, q, sc, scale=1.0 / W)
+    sync()
+    deq = coll.dequant_mx_fp8(q.cpu(), sc.cpu()).to(torch.float64)
+    ref = ref_sum(W, n, torch.bfloat16, salt=31) / W
+    # e4m3 has 3 mantissa bits; with amax/scale in (224, 448] the worst case is 16/224 of the block max
+    blk_max = ref.abs().view(-1, 32).max(dim=1, keepdim=True).values.expand(-1, 32).reshape(-1)
+    err = (deq - ref).abs()
+    assert bool((err <= blk_max * 0.075 + 1e-6).all()), f"fp8 block-scaled all-reduce: max rel err {(err / (blk_max + 1e-9)).max().item()}"
+    checks += 1
+    comm.barrier(); sync()
+    comm.check_status()
+    launches = comm.launches
+    comm.close()
+    print(f"rank {R}/{W} transport={comm.transport} multicast={comm.has_multicast} checks={checks} launches={launches} OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

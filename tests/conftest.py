@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with `-m gpu` under gpurun)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 GPUs")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        ngpu = 0
+    for item in items:
+        if "gpu" in item.keywords and ngpu == 0:
+            item.add_marker(pytest.mark.skip(reason="no GPU on this box"))
+        if "multigpu" in item.keywords and ngpu < 2:
+            item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))
