@@ -1,0 +1,102 @@
+"""ResNet-50 (v1.5) for the PyTorch-GPU recipe retarget.
+
+The reference's ``recipes/PyTorch-GPU`` only launches a user container running
+stock PyTorch (/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8); the
+north star retargets it to multi-instance ResNet-50.  This is our own
+implementation (not torchvision): NHWC/bf16 end to end, parameters are views
+into ONE flat symmetric buffer so the fused all-reduce + SGD kernel
+(``ops.coll.Communicator.fused_allreduce_sgd``) updates the whole model in a
+single launch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import fused as _fused
+
+
+class ConvBN(nn.Module):
+    """conv (no bias) + train-mode BatchNorm (+ residual add) (+ ReLU)."""
+
+    def __init__(self, cin: int, cout: int, k: int, stride: int = 1, relu: bool = True, zero_gamma: bool = False):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.relu = cin, cout, k, stride, relu
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
+        self.gamma = nn.Parameter(torch.zeros(cout) if zero_gamma else torch.ones(cout))
+        self.beta = nn.Parameter(torch.zeros(cout))
+        self.register_buffer("running_mean", torch.zeros(cout, dtype=torch.float32))
+        self.register_buffer("running_var", torch.ones(cout, dtype=torch.float32))
+        self.momentum, self.eps = 0.1, 1e-5
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = F.conv2d(x, self.weight, None, self.stride, self.k // 2)
+        if y.is_cuda and self.training:
+            # one fused stats + apply(+residual)(+ReLU) pair instead of BN / add / ReLU kernels;
+            # no eager fallback on GPU: a missing extension must fail loudly
+            return _fused.fused_bn_act(y, self.gamma, self.beta, residual, self.running_mean, self.running_var,
+                                       self.relu, self.eps, self.momentum)
+        y = F.batch_norm(y.float(), self.running_mean, self.running_var, self.gamma.float(), self.beta.float(),
+                         self.training, self.momentum, self.eps).to(y.dtype)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if self.relu else y
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin: int, width: int, stride: int):
+        super().__init__()
+        cout = width * self.expansion
+        self.c1 = ConvBN(cin, width, 1)
+        self.c2 = ConvBN(width, width, 3, stride)          # v1.5: stride on the 3x3
+        self.c3 = ConvBN(width, cout, 1, relu=True, zero_gamma=True)
+        self.down = ConvBN(cin, cout, 1, stride, relu=False) if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        idt = x if self.down is None else self.down(x)
+        return self.c3(self.c2(self.c1(x)), residual=idt)
+
+
+class ResNet(nn.Module):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes: int = 1000, width: int = 64):
+        super().__init__()
+        self.stem = ConvBN(3, width, 7, 2)
+        blocks, cin = [], width
+        for i, n in enumerate(layers):
+            w = width * (2 ** i)
+            for j in range(n):
+                blocks.append(Bottleneck(cin, w, (1 if i == 0 else 2) if j == 0 else 1))
+                cin = w * Bottleneck.expansion
+        self.blocks = nn.Sequential(*blocks)
+        self.fc_weight = nn.Parameter(torch.empty(num_classes, cin))
+        self.fc_bias = nn.Parameter(torch.zeros(num_classes))
+        nn.init.kaiming_uniform_(self.fc_weight, a=math.sqrt(5))
+        bound = 1 / math.sqrt(cin)
+        nn.init.uniform_(self.fc_bias, -bound, bound)
+
+    def forward(self, x):
+        x = self.stem(x)
+        x = F.max_pool2d(x, 3, 2, 1)
+        x = self.blocks(x)
+        x = x.mean(dim=(2, 3))
+        return F.linear(x, self.fc_weight, self.fc_bias)
+
+
+def resnet50(num_classes: int = 1000) -> ResNet:
+    return ResNet((3, 4, 6, 3), num_classes)
+
+
+def resnet_tiny(num_classes: int = 10) -> ResNet:
+    """Two-block variant for smoke tests."""
+    return ResNet((1, 1, 1, 1), num_classes, width=16)
+
+
+def param_count(m: nn.Module) -> int:
+    return sum(p.numel() for p in m.parameters())

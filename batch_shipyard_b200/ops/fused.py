@@ -1,0 +1,148 @@
+"""ctypes binding for ``libshipyard_ops`` (fused elementwise / normalisation kernels)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_LIB = None
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_native", "libshipyard_ops.so")
+
+
+def load() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            from .._build import ensure_built
+            ensure_built(["ops"])
+        if not os.path.exists(p):
+            raise RuntimeError(f"{p} missing: run `python native/build.py ops` (no Python fallback on GPU)")
+        lib = C.CDLL(p)
+        lib.sy_ops_launch_count.restype = C.c_ulonglong
+        lib.sy_ops_u8_to_bf16_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float),
+                                               C.POINTER(C.c_float), C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def launch_count() -> int:
+    return int(load().sy_ops_launch_count())
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def u8_to_bf16_norm(src_u8: torch.Tensor, dst_bf16: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 NHWC (C=3) -> normalised bf16 NHWC, one pass, on ``dst``'s current stream."""
+    assert src_u8.dtype == torch.uint8 and dst_bf16.dtype == torch.bfloat16
+    assert src_u8.numel() == dst_bf16.numel() and src_u8.is_cuda and dst_bf16.is_cuda
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    rc = load().sy_ops_u8_to_bf16_norm(C.c_void_p(src_u8.data_ptr()), C.c_void_p(dst_bf16.data_ptr()),
+                                       src_u8.numel(), m, s, _stream(dst_bf16))
+    if rc != 0:
+        raise RuntimeError(f"u8_to_bf16_norm launch failed: cuda error {rc}")
+    return dst_bf16
+
+
+# ---------------------------------------------------------------------------
+# fused train-mode BatchNorm (+ residual) (+ ReLU), NHWC bf16
+# ---------------------------------------------------------------------------
+def _bind_bn(lib):
+    if getattr(lib, "_bn_bound", False):
+        return
+    vp, fp = C.c_void_p, C.c_void_p
+    lib.sy_ops_bn_fwd.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, C.c_float,
+                                  C.c_int, vp]
+    lib.sy_ops_bn_apply_only.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float,
+                                         C.c_float, C.c_int, vp]
+    lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, vp]
+    lib._bn_bound = True
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _is_nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def bn_shape_supported(c: int) -> bool:
+    g = c // 8
+    return c % 8 == 0 and 1 <= g <= 256 and (g & (g - 1)) == 0
+
+
+class _FusedBNAct(torch.autograd.Function):
+    """y = act(BN_train(x) [+ residual]) with saved (x, y, mean, invstd) for the fused backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats):
+        lib = load(); _bind_bn(lib)
+        assert x.is_cuda and x.dtype == torch.bfloat16 and _is_nhwc(x), "fused BN wants NHWC bf16"
+        n, c, h, w = x.shape
+        m = n * h * w
+        out = torch.empty_like(x)                       # preserves channels_last strides
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        if residual is not None:
+            assert residual.shape == x.shape and _is_nhwc(residual) and residual.dtype == x.dtype
+        if stats is None:
+            ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            rc = lib.sy_ops_bn_fwd(_ptr(x), _ptr(residual), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                   _ptr(running_var), _ptr(save_mean), _ptr(save_invstd), _ptr(ws), m, c, eps,
+                                   momentum, 1 if relu else 0, _stream(x))
+        else:
+            rc = lib.sy_ops_bn_apply_only(_ptr(x), _ptr(residual), _ptr(out), _ptr(gamma), _ptr(beta),
+                                          _ptr(running_mean), _ptr(running_var), _ptr(save_mean), _ptr(save_invstd),
+                                          _ptr(stats), m, c, eps, momentum, 1 if relu else 0, _stream(x))
+        if rc != 0:
+            raise RuntimeError(f"fused BN forward failed (rc={rc}, C={c})")
+        ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
+        ctx.relu, ctx.has_res = bool(relu), residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load(); _bind_bn(lib)
+        x, out, mean, invstd, gamma = ctx.saved_tensors
+        n, c, h, w = x.shape
+        m = n * h * w
+        if not _is_nhwc(dout):
+            dout = dout.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
+        dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
+        ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+        rc = lib.sy_ops_bn_bwd(_ptr(dout), _ptr(out), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
+                               _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
+                               _stream(x))
+        if rc != 0:
+            raise RuntimeError(f"fused BN backward failed (rc={rc})")
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+def fused_bn_act(x, gamma, beta, residual=None, running_mean=None, running_var=None, relu=True, eps=1e-5,
+                 momentum=0.1, stats=None):
+    """Train-mode BN + optional residual + optional ReLU in two passes (NHWC bf16, CUDA only)."""
+    return _FusedBNAct.apply(x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats)
+
+
+def bn_act_reference(x, gamma, beta, residual=None, relu=True, eps=1e-5):
+    """Plain PyTorch fp32 reference of the same op (used by the numerics tests and the CPU path)."""
+    xf = x.float()
+    mean = xf.mean(dim=(0, 2, 3), keepdim=True)
+    var = xf.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+    y = (xf - mean) * torch.rsqrt(var + eps) * gamma.float().view(1, -1, 1, 1) + beta.float().view(1, -1, 1, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return torch.relu(y) if relu else y

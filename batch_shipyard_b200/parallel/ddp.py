@@ -1,0 +1,250 @@
+"""Fused data-parallel trainer: one CUDA graph per step, one collective kernel per step.
+
+Design (B200-first, replaces what DDP + NCCL + a separate optimizer do in the
+baseline recipe):
+
+* every parameter and every gradient is a view into ONE flat bf16 buffer that
+  lives in the communicator's symmetric heap, so there is nothing to bucket or
+  copy before communication;
+* after backward a single kernel does reduce-scatter (multimem.ld_reduce through
+  NVSwitch) -> 1/N scale -> SGD-momentum update of the fp32 master shard this
+  rank owns -> bf16 all-gather of the new parameters (multimem.st) -> zeroing of
+  the local gradient buffer (ZeRO-1 style optimizer-state sharding for free);
+* forward + backward + that kernel are captured in one CUDA graph, so a step
+  is a single launch from the host;
+* the end-to-end path stages uint8 NHWC batches from pinned host memory with a
+  double-buffered copy stream and converts them on the GPU.
+
+Reference counterpart: the launcher only wires ``mpirun``/ssh for user
+containers (/root/reference/convoy/batch.py:4362-4486); gradient exchange is
+whatever the container's framework does.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import coll as _coll
+from ..ops import fused as _fused
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class FlatLayout:
+    total: int
+    offsets: dict  # name -> (offset, numel, shape, channels_last)
+
+
+class FlatParameters:
+    """Re-homes a module's parameters/gradients into flat symmetric buffers."""
+
+    def __init__(self, model: nn.Module, comm: _coll.Communicator, dtype=torch.bfloat16):
+        self.model, self.comm, self.dtype = model, comm, dtype
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        off, lay = 0, {}
+        for n, p in named:
+            lay[n] = (off, p.numel(), tuple(p.shape), p.dim() == 4)
+            off = _round_up(off + p.numel(), 8)
+        total = _round_up(off, 8 * max(1, comm.world))
+        self.layout = FlatLayout(total, lay)
+        dev = comm.torch_device
+        # fp32 image of the initial weights (identical on every rank: same seed)
+        init = torch.zeros(total, dtype=torch.float32, device=dev)
+        for n, p in named:
+            o, cnt, shape, cl = lay[n]
+            src = p.detach().to(dev, torch.float32)
+            if cl:
+                src = src.permute(0, 2, 3, 1).contiguous()
+            init[o:o + cnt].copy_(src.reshape(-1))
+        self.params = comm.alloc(total, dtype)
+        self.grads = comm.alloc(total, dtype)
+        self.params.copy_(init.to(dtype))
+        self.grads.zero_()
+        lo, cnt = comm.shard_range(total)
+        self.shard = (lo, cnt)
+        self.master = init[lo:lo + cnt].clone()
+        self.momentum = torch.zeros(cnt, dtype=torch.float32, device=dev)
+        del init
+        for n, p in named:
+            o, cnt_p, shape, cl = lay[n]
+            pv, gv = self.params[o:o + cnt_p], self.grads[o:o + cnt_p]
+            if cl:
+                co, ci, kh, kw = shape
+                pv = pv.view(co, kh, kw, ci).permute(0, 3, 1, 2)   # NHWC storage, NCHW logical
+                gv = gv.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                pv, gv = pv.view(shape), gv.view(shape)
+            p.data = pv
+            p.grad = gv
+        for b in model.buffers():
+            b.data = b.data.to(dev)
+
+    def checksum(self) -> float:
+        return float(self.params.float().sum())
+
+
+class FusedDataParallelTrainer:
+    """Owns the model replica, the flat buffers and the captured training step."""
+
+    def __init__(self, model: nn.Module, comm: _coll.Communicator, batch_shape, num_classes: int,
+                 lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4,
+                 loss_fn: Optional[Callable] = None, use_graph: bool = True, channels_last: bool = True):
+        self.comm, self.model = comm, model
+        self.dev = comm.torch_device
+        self.is_cuda = self.dev.type == "cuda"
+        self.flat = FlatParameters(model, comm, torch.bfloat16 if self.is_cuda else torch.float32)
+        self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / comm.world], dtype=torch.float32, device=self.dev)
+        self.loss_fn = loss_fn or (lambda logits, y: F.cross_entropy(logits.float(), y))
+        n, c, h, w = batch_shape
+        self.batch_shape = batch_shape
+        act_dtype = torch.bfloat16 if self.is_cuda else torch.float32
+        # NHWC storage viewed as NCHW (= torch channels_last)
+        self._x_store = torch.zeros((n, h, w, c), dtype=act_dtype, device=self.dev)
+        self.static_x = self._x_store.permute(0, 3, 1, 2) if channels_last else self._x_store.permute(0, 3, 1, 2).contiguous()
+        self.static_y = torch.zeros((n,), dtype=torch.int64, device=self.dev)
+        self.static_loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.graph = None
+        self.use_graph = use_graph and self.is_cuda
+        self.kernels_per_step = 0          # OUR kernels inside one step (graph replays included)
+        self.steps_done = 0
+        self._stager = None
+        model.train()
+
+    # -- one optimisation step on the static buffers ---------------------------
+    def _step_body(self) -> None:
+        logits = self.model(self.static_x)
+        loss = self.loss_fn(logits, self.static_y)
+        loss.backward()
+        self.comm.fused_allreduce_sgd(self.flat.grads, self.flat.params, self.flat.master, self.flat.momentum,
+                                      self.hyper, zero_grads=True)
+        self.static_loss.copy_(loss.detach())
+
+    def _count_own_launches(self) -> int:
+        return self.comm.launches + _fused.launch_count() + _extra_launches()
+
+    def prepare(self, warmup: int = 3) -> None:
+        """Eager warm-up (also lets cuDNN pick algorithms), then capture the step."""
+        if not self.use_graph:
+            before = self._count_own_launches()
+            self._step_body()
+            self.kernels_per_step = self._count_own_launches() - before
+            for _ in range(max(0, warmup - 1)):
+                self._step_body()
+            return
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._step_body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = self._count_own_launches()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        self.kernels_per_step = self._count_own_launches() - before
+        torch.cuda.synchronize(self.dev)
+
+    def step(self) -> torch.Tensor:
+        """Run one step on whatever is in static_x/static_y; returns the loss tensor (device)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.steps_done += 1
+        return self.static_loss
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0:1].fill_(lr)
+
+    # -- end-to-end input path -------------------------------------------------
+    def make_stager(self, depth: int = 2) -> "InputStager":
+        self._stager = InputStager(self, depth)
+        return self._stager
+
+
+class InputStager:
+    """Pinned uint8 NHWC host batches -> device, double-buffered on a copy stream,
+    converted to normalised bf16 by our kernel right before the step."""
+
+    def __init__(self, tr: FusedDataParallelTrainer, depth: int = 2):
+        self.tr, self.depth = tr, depth
+        n, c, h, w = tr.batch_shape
+        dev = tr.dev
+        pin = tr.is_cuda
+        self.host_x = [torch.empty((n, h, w, c), dtype=torch.uint8, pin_memory=pin) for _ in range(depth)]
+        self.host_y = [torch.empty((n,), dtype=torch.int64, pin_memory=pin) for _ in range(depth)]
+        self.dev_x = [torch.empty((n, h, w, c), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.dev_y = [torch.empty((n,), dtype=torch.int64, device=dev) for _ in range(depth)]
+        self.host_loss = [torch.zeros((), dtype=torch.float32, pin_memory=pin) for _ in range(depth)]
+        self.h2d_bytes = self.host_x[0].numel() + self.host_y[0].numel() * 8
+        self.d2h_bytes = 4
+        if tr.is_cuda:
+            self.copy_stream = torch.cuda.Stream(dev)
+            self.copied = [torch.cuda.Event() for _ in range(depth)]
+            self.consumed = [torch.cuda.Event() for _ in range(depth)]
+            self.loss_ready = [torch.cuda.Event() for _ in range(depth)]
+        self._issued = [False] * depth
+
+    def fill_synthetic(self, seed: int = 0) -> None:
+        g = torch.Generator().manual_seed(seed)
+        for hx, hy in zip(self.host_x, self.host_y):
+            hx.copy_(torch.randint(0, 256, hx.shape, dtype=torch.uint8, generator=g))
+            hy.copy_(torch.randint(0, 1000, hy.shape, dtype=torch.int64, generator=g) % 1000)
+
+    def prefetch(self, slot: int) -> None:
+        tr = self.tr
+        if not tr.is_cuda:
+            self.dev_x[slot].copy_(self.host_x[slot]); self.dev_y[slot].copy_(self.host_y[slot])
+            return
+        with torch.cuda.stream(self.copy_stream):
+            if self._issued[slot]:
+                self.copy_stream.wait_event(self.consumed[slot])   # the step that read this slot is done with it
+            self.dev_x[slot].copy_(self.host_x[slot], non_blocking=True)
+            self.dev_y[slot].copy_(self.host_y[slot], non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+        self._issued[slot] = True
+
+    def run_step(self, slot: int) -> None:
+        """Consume a prefetched slot: convert, train one step, start the loss read-back."""
+        tr = self.tr
+        if tr.is_cuda:
+            cur = torch.cuda.current_stream(tr.dev)
+            cur.wait_event(self.copied[slot])
+            _fused.u8_to_bf16_norm(self.dev_x[slot], tr._x_store)
+            tr.static_y.copy_(self.dev_y[slot], non_blocking=True)
+            self.consumed[slot].record(cur)
+            tr.step()
+            self.host_loss[slot].copy_(tr.static_loss, non_blocking=True)
+            self.loss_ready[slot].record(cur)
+        else:
+            x = self.dev_x[slot].to(torch.float32) / 255.0
+            tr._x_store.copy_(x)
+            tr.static_y.copy_(self.dev_y[slot])
+            tr.step()
+            self.host_loss[slot].copy_(tr.static_loss)
+
+    def read_loss(self, slot: int) -> float:
+        if self.tr.is_cuda:
+            self.loss_ready[slot].synchronize()
+        return float(self.host_loss[slot])
+
+
+_EXTRA_COUNTERS: list = []
+
+
+def register_launch_counter(fn: Callable[[], int]) -> None:
+    """Other native op libraries (GEMM, ...) register their launch counters here."""
+    _EXTRA_COUNTERS.append(fn)
+
+
+def _extra_launches() -> int:
+    return sum(int(f()) for f in _EXTRA_COUNTERS)

@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""Headline benchmark: PyTorch-GPU recipe retarget, ResNet-50 training images/sec.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N>1 under
+torchrun, one rank per GPU).  Prints ONE JSON line on rank 0.
+
+* ``value``      device-timed throughput of the captured training step (forward +
+                 backward + fused all-reduce/SGD/all-gather kernel), CUDA events,
+                 barrier + synchronize on both sides, max over ranks.
+* ``e2e``        the same metric through the public API with, every step, the H2D
+                 copy of that step's uint8 batch from pinned host memory and the
+                 D2H read of the loss.
+* ``--impl reference``  the unmodified reference cannot be installed offline
+                 (no setup.py/pyproject; imports azure.* at module load) -> prints
+                 ``{"impl": "reference", "unavailable": ...}``.
+* ``--impl nccl-baseline``  the bar BASELINE.md defines: torchvision resnet50 +
+                 DDP/NCCL + SGD, bf16 autocast, channels_last (not our code path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="shipyard", choices=["shipyard", "reference", "nccl-baseline"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SHIPYARD_BENCH_BATCH", "256")), help="per-GPU batch")
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def max_over_ranks(x: float, world: int, dev) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn_step, steps: int, world: int, dev) -> float:
+    """ms per step: barrier+sync, CUDA events around exactly `steps` steps, max over ranks."""
+    import torch
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn_step(i)
+    e1.record()
+    e1.synchronize()
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    return max_over_ranks(ms, world, dev) / steps
+
+
+def run_shipyard(args, rank, world, local):
+    import torch
+    from batch_shipyard_b200.models.resnet import resnet50, resnet_tiny
+    from batch_shipyard_b200.ops.coll import Communicator
+    from batch_shipyard_b200.parallel.ddp import FusedDataParallelTrainer
+
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    torch.backends.cudnn.benchmark = True
+    comm = Communicator(rank, world, session=f"bench-{os.environ.get('MASTER_PORT', '0')}-{os.getppid() if world > 1 else os.getpid()}",
+                        device=local, heap_bytes=1 << 30)
+    model = resnet50() if args.model == "resnet50" else resnet_tiny(1000)
+    B = args.batch
+    tr = FusedDataParallelTrainer(model, comm, (B, 3, 224, 224), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4,
+                                  use_graph=not args.no_graph)
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    tr._x_store.copy_(torch.randn(tr._x_store.shape, generator=g).to(torch.bfloat16))
+    tr.static_y.copy_(torch.randint(0, 1000, (B,), generator=g))
+    tr.prepare(warmup=max(3, args.warmup))
+    # --- device-timed captured step ------------------------------------------
+    for _ in range(args.warmup):
+        tr.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: tr.step(), args.steps, world, dev)
+    clocks = sampler.stop() if rank == 0 else {}
+    comm.check_status()
+    loss_dev = float(tr.static_loss)
+    # --- end-to-end through the public API: pinned uint8 -> H2D -> convert -> step -> loss D2H
+    e2e = None
+    if not args.no_e2e:
+        st = tr.make_stager(depth=2)
+        st.fill_synthetic(seed=11 + rank)
+        for i in range(max(3, args.warmup)):
+            st.prefetch(i % 2); st.run_step(i % 2); st.read_loss(i % 2)
+        losses = []
+
+        def e2e_step(i):
+            slot = i % 2
+            if i == 0:
+                st.prefetch(slot)
+            st.run_step(slot)
+            if i + 1 < args.steps:
+                st.prefetch((i + 1) % 2)      # next batch's H2D overlaps this step's compute
+            if i > 0:
+                losses.append(st.read_loss((i - 1) % 2))   # D2H read of the previous step's loss
+
+        ms_e2e = timed(e2e_step, args.steps, world, dev)
+        losses.append(st.read_loss((args.steps - 1) % 2))
+        e2e = {"value": round(B * world / (ms_e2e / 1e3), 2), "unit": "images/sec", "ms_per_step": round(ms_e2e, 3),
+               "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
+               "last_loss": round(losses[-1], 4)}
+    comm.check_status()
+    own = tr.kernels_per_step
+    out = {
+        "metric": "resnet50_train_images_per_sec", "value": round(B * world / (ms / 1e3), 2), "unit": "images/sec",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "impl": "shipyard",
+        "config": {"model": args.model, "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
+                   "seq_len": None, "parallelism": f"dp{world}", "optimizer": "sgd-momentum (fp32 master, sharded)",
+                   "l2_policy": "per-step working set (activations) >> 126 MB L2; no explicit flush",
+                   "cuda_graph": not args.no_graph, "collective_transport": comm.transport,
+                   "nvls_multicast": comm.has_multicast},
+        "clocks": clocks, "e2e": e2e,
+        "gpu_launches": own * args.steps + (0 if args.no_e2e else 0),
+        "own_kernels_per_step": own, "loss": round(loss_dev, 4),
+    }
+    base = _baseline_number(world)
+    if base:
+        out["vs_baseline"] = round(out["value"] / base, 4)
+    comm.close()
+    return out
+
+
+def _baseline_number(world: int):
+    """BASELINE.md publishes nothing for the reference; once this repo has measured the plain
+    NCCL/cuDNN arm the number is recorded in bench/baseline_measured.json."""
+    p = os.path.join(ROOT, "bench", "baseline_measured.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("resnet50_images_per_sec", {}).get(str(world))
+    except Exception:
+        return None
+
+
+def run_nccl_baseline(args, rank, world, local):
+    """Plain PyTorch arm: torchvision resnet50, DDP over NCCL, SGD, bf16 autocast, channels_last."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    torch.backends.cudnn.benchmark = True
+    model = torchvision.models.resnet50(weights=None).to(dev).to(memory_format=torch.channels_last)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    B = args.batch
+    x = torch.randn(B, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (B,), device=dev)
+    hx = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory()
+    hy = torch.randint(0, 1000, (B,), dtype=torch.int64).pin_memory()
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+
+    def step(xx, yy):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(model(xx), yy)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step(x, y)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: step(x, y), args.steps, world, dev)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    def e2e_step(i):
+        dx = hx.to(dev, non_blocking=True); dy = hy.to(dev, non_blocking=True)
+        xx = ((dx.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous(memory_format=torch.channels_last)
+        float(step(xx, dy))
+
+    for i in range(3):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps, world, dev)
+    return {"metric": "resnet50_train_images_per_sec", "value": round(B * world / (ms / 1e3), 2), "unit": "images/sec",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "impl": "nccl-baseline",
+            "config": {"model": "torchvision.resnet50", "global_batch": B * world, "per_gpu_batch": B,
+                       "parallelism": f"ddp{world}", "autocast": "bf16", "memory_format": "channels_last"},
+            "clocks": clocks,
+            "e2e": {"value": round(B * world / (ms_e2e / 1e3), 2), "unit": "images/sec",
+                    "h2d_bytes_per_step": hx.numel() + hy.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": 0}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "Azure/batch-shipyard has no setup.py/pyproject (pip cannot install it), imports azure.batch at "
+                          "module load (SDK absent, no network) and contains no training/collective code to time"}))
+        return 0
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device visible"}))
+        return 0
+    rank, world, local = dist_setup(args)
+    out = run_shipyard(args, rank, world, local) if args.impl == "shipyard" else run_nccl_baseline(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

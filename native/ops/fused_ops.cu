@@ -1,0 +1,309 @@
+// Fused elementwise / normalisation kernels for the recipe workloads (sm_100a).
+// All are HBM-bandwidth bound: 16-byte vector accesses, one pass over the data,
+// statistics accumulated in fp32.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DEVI __device__ __forceinline__
+struct alignas(16) V16 { uint32_t x, y, z, w; };
+
+#include <atomic>
+// counted across threads: autograd runs backward kernels from its own worker thread
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" unsigned long long sy_ops_launch_count() { return g_launches.load(); }
+#define COUNT_LAUNCH() do { g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
+#define RET_LAST() do { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : (int)e; } while (0)
+
+DEVI float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+DEVI float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+DEVI uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------
+// uint8 NHWC image batch -> normalised bf16 NHWC (the step-input path: the
+// staged uint8 batch is converted on the GPU, so H2D moves 1 byte per value)
+// 16 input bytes (16 values) per thread -> 32 output bytes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_u8_to_bf16_norm(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n,
+                  float m0, float m1, float m2, float s0, float s1, float s2) {
+  const float mean[3] = {m0, m1, m2}, istd[3] = {s0, s1, s2};
+  const size_t nv = n / 16;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+    const V16 raw = reinterpret_cast<const V16*>(in)[v];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[8];
+    int c = (int)((v * 16) % 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t word = w[i / 2];
+      const float a = (float)((word >> ((i % 2) * 16)) & 0xff);
+      const float b = (float)((word >> ((i % 2) * 16 + 8)) & 0xff);
+      const int c0 = c, c1 = c + 1 >= 3 ? c - 2 : c + 1;
+      o[i] = pack_bf2((a * (1.f / 255.f) - mean[c0]) * istd[c0], (b * (1.f / 255.f) - mean[c1]) * istd[c1]);
+      c = c1 + 1 >= 3 ? c1 - 2 : c1 + 1;
+    }
+    reinterpret_cast<V16*>(out)[2 * v] = V16{o[0], o[1], o[2], o[3]};
+    reinterpret_cast<V16*>(out)[2 * v + 1] = V16{o[4], o[5], o[6], o[7]};
+  }
+  // tail (n % 16)
+  for (size_t i = nv * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    out[i] = __float2bfloat16_rn(((float)in[i] * (1.f / 255.f) - mean[c]) * istd[c]);
+  }
+}
+
+extern "C" int sy_ops_u8_to_bf16_norm(const void* in, void* out, size_t n, const float* mean3, const float* std3,
+                                      void* stream) {
+  size_t nv = n / 16 + 1;
+  int blocks = (int)((nv + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_u8_to_bf16_norm<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, (__nv_bfloat16*)out, n, mean3[0],
+                                                              mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+
+// ===========================================================================
+// Fused train-mode BatchNorm (+ residual add) (+ ReLU) on NHWC bf16 activations.
+// x is the conv output viewed as [M, C] (M = N*H*W, C contiguous, C % 8 == 0,
+// C/8 a power of two <= 256).  Thread t owns channel group t % (C/8) (8 channels,
+// one 16-byte vector) and walks rows, so every access is a coalesced 16B vector
+// and the per-channel parameters sit in registers.
+//   fwd : stats (1 read)            -> apply (1-2 reads, 1 write)
+//   bwd : reduce (3 reads)          -> apply (3 reads, 1-2 writes)
+// versus separate BN / add / ReLU kernels this removes 2-4 full passes per layer.
+// ===========================================================================
+DEVI void unpack8(const V16& v, float* f) {
+  f[0] = bf_lo(v.x); f[1] = bf_hi(v.x); f[2] = bf_lo(v.y); f[3] = bf_hi(v.y);
+  f[4] = bf_lo(v.z); f[5] = bf_hi(v.z); f[6] = bf_lo(v.w); f[7] = bf_hi(v.w);
+}
+DEVI V16 pack8(const float* f) {
+  return V16{pack_bf2(f[0], f[1]), pack_bf2(f[2], f[3]), pack_bf2(f[4], f[5]), pack_bf2(f[6], f[7])};
+}
+DEVI V16 ldg16(const void* p) {
+  V16 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+DEVI void stg16(void* p, const V16& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// block-level reduction of per-thread 8-channel partials, then one atomicAdd per channel
+template <int NACC>
+DEVI void block_reduce_atomic(float (&acc)[NACC][8], float* __restrict__ out, int C, int G) {
+  __shared__ float sh[NACC][256][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh[a][threadIdx.x][i] = acc[a][i];
+  __syncthreads();
+  // thread t < G*8 handles (channel group t/8, lane t%8)... use all 256 threads: (a, cg, i)
+  const int items = NACC * G * 8;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int a = it / (G * 8), cg = (it / 8) % G, i = it % 8;
+    float s = 0.f;
+    for (int t = cg; t < (int)blockDim.x; t += G) s += sh[a][t][i];
+    atomicAdd(out + (size_t)a * C + cg * 8 + i, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long M, int C) {
+  const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
+  float acc[2][8] = {};
+  const long stride = (long)gridDim.x * rpi;
+  long r = (long)blockIdx.x * rpi + rl;
+  for (; r + stride < M; r += 2 * stride) {
+    V16 a = ldg16(x + r * C + cg * 8), b = ldg16(x + (r + stride) * C + cg * 8);
+    float fa[8], fb[8]; unpack8(a, fa); unpack8(b, fb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[0][i] += fa[i] + fb[i]; acc[1][i] += fa[i] * fa[i] + fb[i] * fb[i]; }
+  }
+  for (; r < M; r += stride) {
+    V16 a = ldg16(x + r * C + cg * 8);
+    float fa[8]; unpack8(a, fa);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[0][i] += fa[i]; acc[1][i] += fa[i] * fa[i]; }
+  }
+  block_reduce_atomic<2>(acc, sums, C, G);
+}
+
+// out = act(gamma * (x - mean) * invstd + beta [+ res]); also finalises mean/invstd and running stats
+__global__ void __launch_bounds__(256)
+k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+               __nv_bfloat16* __restrict__ out, const float* __restrict__ sums,
+               const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+               float* __restrict__ running_mean, float* __restrict__ running_var,
+               float* __restrict__ save_mean, float* __restrict__ save_invstd,
+               long M, int C, float eps, float momentum, int relu) {
+  const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
+  float sc[8], sh[8];
+  const float invM = 1.f / (float)M;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    const float mean = sums[c] * invM;
+    float var = sums[C + c] * invM - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float istd = rsqrtf(var + eps);
+    const float g = __bfloat162float(gamma[c]), b = __bfloat162float(beta[c]);
+    sc[i] = g * istd; sh[i] = b - mean * g * istd;
+    if (blockIdx.x == 0 && rl == 0) {
+      save_mean[c] = mean; save_invstd[c] = istd;
+      if (running_mean) {
+        const float unb = M > 1 ? var * (float)M / (float)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+      }
+    }
+  }
+  const long stride = (long)gridDim.x * rpi;
+  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
+    const size_t off = (size_t)r * C + cg * 8;
+    float f[8]; unpack8(ldg16(x + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+    if (res) {
+      float q[8]; unpack8(ldg16(res + off), q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += q[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    stg16(out + off, pack8(f));
+  }
+}
+
+// s1[c] = sum dz, s2[c] = sum dz * xhat, dz = relu ? dout * (out > 0) : dout
+__global__ void __launch_bounds__(256)
+k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                const float* __restrict__ invstd, float* __restrict__ sums, long M, int C, int relu) {
+  const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
+  float mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
+  float acc[2][8] = {};
+  const long stride = (long)gridDim.x * rpi;
+  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
+    const size_t off = (size_t)r * C + cg * 8;
+    float d[8], xv[8];
+    unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
+    if (relu) {
+      float o[8]; unpack8(ldg16(out + off), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[0][i] += d[i]; acc[1][i] += d[i] * (xv[i] - mu[i]) * is[i]; }
+  }
+  block_reduce_atomic<2>(acc, sums, C, G);
+}
+
+// dx = gamma*invstd*(dz - s1/M - xhat*s2/M); dres = dz; block 0 writes dgamma/dbeta (bf16)
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+               const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+               const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ gamma,
+               const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
+               __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dgamma,
+               __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu) {
+  const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
+  float mu[8], is[8], k0[8], k1[8], k2[8];
+  const float invM = 1.f / (float)M;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    mu[i] = mean[c]; is[i] = invstd[c];
+    const float g = __bfloat162float(gamma[c]), s1 = sums[c], s2 = sums[C + c];
+    k0[i] = g * is[i];                 // dz coefficient
+    k1[i] = -g * is[i] * s1 * invM;    // constant term
+    k2[i] = -g * is[i] * s2 * invM;    // xhat coefficient
+    if (blockIdx.x == 0 && rl == 0) { dgamma[c] = __float2bfloat16_rn(s2); dbeta[c] = __float2bfloat16_rn(s1); }
+  }
+  const long stride = (long)gridDim.x * rpi;
+  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
+    const size_t off = (size_t)r * C + cg * 8;
+    float d[8], xv[8];
+    unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
+    if (relu) {
+      float o[8]; unpack8(ldg16(out + off), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+    if (dres) stg16(dres + off, pack8(d));
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fmaf(d[i], k0[i], fmaf((xv[i] - mu[i]) * is[i], k2[i], k1[i]));
+    stg16(dx + off, pack8(g));
+  }
+}
+
+static inline int bn_grid(long M, int C) {
+  const int rpi = 256 / (C / 8);
+  long b = (M + rpi - 1) / rpi;
+  b = (b + 3) / 4;                    // >= 4 rows per thread
+  if (b > 148 * 6) b = 148 * 6;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static inline bool bn_shape_ok(int C) {
+  if (C % 8) return false;
+  int G = C / 8;
+  return G >= 1 && G <= 256 && (G & (G - 1)) == 0;
+}
+
+// ws: float[2*C] scratch (zeroed here).  Returns 0 or a cuda error / -1 for bad shape.
+extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const void* gamma, const void* beta,
+                             float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                             float* ws, long M, int C, float eps, float momentum, int relu, void* stream) {
+  if (!bn_shape_ok(C)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
+  const int g = bn_grid(M, C);
+  k_bn_stats<<<g, 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, C);
+  COUNT_LAUNCH();
+  k_bn_apply_fwd<<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, ws,
+                                   (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, running_mean, running_var,
+                                   save_mean, save_invstd, M, C, eps, momentum, relu);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+
+// variant used when the producing GEMM already accumulated the statistics in its epilogue
+extern "C" int sy_ops_bn_apply_only(const void* x, const void* res, void* out, const void* gamma, const void* beta,
+                                    float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                                    const float* sums, long M, int C, float eps, float momentum, int relu, void* stream) {
+  if (!bn_shape_ok(C)) return -1;
+  const int g = bn_grid(M, C);
+  k_bn_apply_fwd<<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out,
+                                                      sums, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, running_mean,
+                                                      running_var, save_mean, save_invstd, M, C, eps, momentum, relu);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+
+extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
+                             const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
+                             int relu, void* stream) {
+  if (!bn_shape_ok(C)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
+  const int g = bn_grid(M, C);
+  k_bn_bwd_reduce<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
+                                    ws, M, C, relu);
+  COUNT_LAUNCH();
+  k_bn_bwd_apply<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
+                                   (const __nv_bfloat16*)gamma, ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
