@@ -36,7 +36,7 @@ class ConvBN(nn.Module):
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         y = F.conv2d(x, self.weight, None, self.stride, self.k // 2)
-        if y.is_cuda and self.training:
+        if y.is_cuda and self.training and y.dtype == torch.bfloat16:
             # one fused stats + apply(+residual)(+ReLU) pair instead of BN / add / ReLU kernels;
             # no eager fallback on GPU: a missing extension must fail loudly
             return _fused.fused_bn_act(y, self.gamma, self.beta, residual, self.running_mean, self.running_var,
