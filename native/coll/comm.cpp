@@ -41,10 +41,11 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->rank = rank; c->world = world; c->device = device; c->session = session;
   c->dev.rank = rank; c->dev.world = world;
   c->timeout_ms = (long)env_sz("SHIPYARD_COLL_TIMEOUT_MS", 20000);
-  c->max_blocks = (long)env_sz("SHIPYARD_COLL_MAX_BLOCKS", 64);
+  c->max_blocks = (long)env_sz("SHIPYARD_COLL_MAX_BLOCKS", 128);
   c->threads = (long)env_sz("SHIPYARD_COLL_THREADS", 512);
   c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 4096);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
+  c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);
   if (heap_bytes == 0) heap_bytes = env_sz("SHIPYARD_COLL_HEAP", transport == SY_TRANSPORT_STUB ? (256ul << 20) : (1ul << 30));
   size_t min_heap = SY_USER_OFF + (16ul << 20);
   if (heap_bytes < min_heap) heap_bytes = min_heap;
@@ -115,6 +116,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "oneshot_max_bytes")) c->oneshot_max_bytes = v > (long)SY_OS_SLOT ? (long)SY_OS_SLOT : v;
   else if (!strcmp(k, "nvls_min_bytes")) c->nvls_min_bytes = v;
   else if (!strcmp(k, "timeout_ms")) c->timeout_ms = v;
+  else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
   else return SY_ERR_ARG;
   return SY_OK;
 }
@@ -125,6 +127,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "oneshot_max_bytes")) return c->oneshot_max_bytes;
   if (!strcmp(k, "nvls_min_bytes")) return c->nvls_min_bytes;
   if (!strcmp(k, "timeout_ms")) return c->timeout_ms;
+  if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
   return -1;
 }
 
@@ -248,7 +251,7 @@ extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
-  rc = k_allgather(c, in, t.off, count, dt, c->has_mc && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
+  rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
   if (rc) return rc;
   if (t.staged) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes * c->world, cudaMemcpyDeviceToDevice, s));
   return SY_OK;
@@ -262,7 +265,7 @@ extern "C" int sy_broadcast(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   OutStage t; int rc = out_target(c, out, bytes, &t); if (rc) return rc;
-  rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && bytes >= (size_t)c->nvls_min_bytes, stream);
+  rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && c->nvls_copy && bytes >= (size_t)c->nvls_min_bytes, stream);
   if (rc) return rc;
   if (t.staged) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes, cudaMemcpyDeviceToDevice, s));
   return SY_OK;

@@ -56,9 +56,10 @@ struct sy_comm {
   uint64_t launches = 0;
   uint32_t* status_host = nullptr;
   // tuning
-  long max_blocks = 64, threads = 512;
+  long max_blocks = 128, threads = 512;
   long ll_max_bytes = 4096, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;
   long timeout_ms = 20000;
+  long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
   // VMM handles (opaque to other TUs)
   void* impl = nullptr;
   // stub transport state

@@ -263,6 +263,46 @@ DEVI void shard_of(size_t units, int world, int r, size_t& begin, size_t& n) {
 // ---------------------------------------------------------------------------
 // reduce one unit (EPU elements at unit index u) across all ranks over P2P
 // ---------------------------------------------------------------------------
+// NW: compile-time upper bound on the world size (2, 4 or 8) so the register file only
+// holds NW in-flight vectors per unit and small worlds can unroll over more units.
+template <int DT_IN, int DT_OUT, int OP, int NW>
+DEVI void p2p_load_unit(const CommDev& c, size_t in_off, size_t u, V16 (&v)[NW][Unit<DT_IN, DT_OUT>::IN_V]) {
+  using U = Unit<DT_IN, DT_OUT>;
+#pragma unroll
+  for (int r = 0; r < NW; ++r) {
+    if (r < c.world) {
+      const char* src = c.heap[r] + in_off + u * (size_t)(U::IN_V * 16);
+#pragma unroll
+      for (int k = 0; k < U::IN_V; ++k) v[r][k] = ld16(src + k * 16);
+    }
+  }
+}
+template <int DT_IN, int DT_OUT, int OP, int NW>
+DEVI void p2p_finish_unit(const CommDev& c, V16 (&v)[NW][Unit<DT_IN, DT_OUT>::IN_V], float scale,
+                          uint32_t (&outw)[Unit<DT_IN, DT_OUT>::OUT_V * 4]) {
+  using U = Unit<DT_IN, DT_OUT>;
+  using acc_t = typename U::acc_t;
+  acc_t acc[U::EPU];
+  Codec<DT_IN, U::EPU>::unpack(reinterpret_cast<const uint32_t*>(v[0]), acc);
+#pragma unroll
+  for (int r = 1; r < NW; ++r) {
+    if (r < c.world) {
+      acc_t a[U::EPU];
+      Codec<DT_IN, U::EPU>::unpack(reinterpret_cast<const uint32_t*>(v[r]), a);
+#pragma unroll
+      for (int i = 0; i < U::EPU; ++i) acc[i] = op_apply<OP>(acc[i], a[i]);
+    }
+  }
+  typename U::oacc_t o[U::EPU];
+#pragma unroll
+  for (int i = 0; i < U::EPU; ++i) {
+    if (DT_IN == SY_F32 || DT_IN == SY_BF16 || DT_IN == SY_F16) o[i] = (typename U::oacc_t)((float)acc[i] * scale);
+    else if (DT_IN == SY_F64) o[i] = (typename U::oacc_t)((double)acc[i] * (double)scale);
+    else o[i] = (typename U::oacc_t)acc[i];
+  }
+  Codec<DT_OUT, U::EPU>::pack(o, outw);
+}
+
 template <int DT_IN, int DT_OUT, int OP>
 DEVI void p2p_reduce_unit(const CommDev& c, size_t in_off, size_t u, float scale,
                           uint32_t (&outw)[Unit<DT_IN, DT_OUT>::OUT_V * 4]) {
@@ -316,7 +356,7 @@ DEVI typename Acc<DT_OUT>::t p2p_reduce_elem(const CommDev& c, size_t in_off, si
 // fused scale + cast.  in/out are symmetric-heap offsets (in-place allowed).
 // mode 0: all-reduce; mode 1: reduce-scatter into local `rs_out` (count = per-rank count)
 // ---------------------------------------------------------------------------
-template <int DT_IN, int DT_OUT, int OP>
+template <int DT_IN, int DT_OUT, int OP, int NW, int UNR>
 __global__ void __launch_bounds__(512)
 k_twoshot_p2p(const __grid_constant__ CommDev c, size_t in_off, size_t out_off, size_t count,
               float scale, int mode, void* rs_out) {
@@ -335,23 +375,32 @@ k_twoshot_p2p(const __grid_constant__ CommDev c, size_t in_off, size_t out_off, 
   const size_t ufirst = (ebeg + U::EPU - 1) / U::EPU, ulast = eend / U::EPU;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   if (ulast > ufirst) {
-    for (size_t u = ufirst + tid; u < ulast; u += nth) {
-      uint32_t w[U::OUT_V * 4];
-      p2p_reduce_unit<DT_IN, DT_OUT, OP>(c, in_off, u, scale, w);
-      if (mode == 0) {
+    // UNR units per thread per iteration: UNR x world 16B loads in flight before the first use
+    for (size_t ub = ufirst + tid; ub < ulast; ub += (size_t)UNR * nth) {
+      V16 v[UNR][NW][U::IN_V];
 #pragma unroll
-        for (int p = 0; p < SY_MAXR; ++p)
-          if (p < c.world) {
-            int q = c.rank + p; if (q >= c.world) q -= c.world;
-            char* dst = c.heap[q] + out_off + u * (size_t)(U::OUT_V * 16);
+      for (int j = 0; j < UNR; ++j)
+        if (ub + (size_t)j * nth < ulast) p2p_load_unit<DT_IN, DT_OUT, OP, NW>(c, in_off, ub + (size_t)j * nth, v[j]);
 #pragma unroll
-            for (int k = 0; k < U::OUT_V; ++k) st16(dst + k * 16, *reinterpret_cast<V16*>(&w[4 * k]));
-          }
-      } else {
-        char* dst = (char*)rs_out + (u * U::EPU - ebeg) * U::SO;
-        // rs_out is 16B aligned only if ebeg*SO is; caller guarantees via scalar path otherwise
+      for (int j = 0; j < UNR; ++j) {
+        const size_t u = ub + (size_t)j * nth;
+        if (u >= ulast) break;
+        uint32_t w[U::OUT_V * 4];
+        p2p_finish_unit<DT_IN, DT_OUT, OP, NW>(c, v[j], scale, w);
+        if (mode == 0) {
 #pragma unroll
-        for (int k = 0; k < U::OUT_V; ++k) st16(dst + k * 16, *reinterpret_cast<V16*>(&w[4 * k]));
+          for (int p = 0; p < NW; ++p)
+            if (p < c.world) {
+              int q = c.rank + p; if (q >= c.world) q -= c.world;
+              char* dst = c.heap[q] + out_off + u * (size_t)(U::OUT_V * 16);
+#pragma unroll
+              for (int k = 0; k < U::OUT_V; ++k) st16(dst + k * 16, *reinterpret_cast<V16*>(&w[4 * k]));
+            }
+        } else {
+          char* dst = (char*)rs_out + (u * U::EPU - ebeg) * U::SO;
+#pragma unroll
+          for (int k = 0; k < U::OUT_V; ++k) st16(dst + k * 16, *reinterpret_cast<V16*>(&w[4 * k]));
+        }
       }
     }
   }
@@ -401,7 +450,7 @@ DEVI void nvls_reduce_unit(const CommDev& c, size_t in_off, size_t u, float scal
   Codec<DT_OUT, U::EPU>::pack(a, outw);
 }
 
-template <int DT_IN, int DT_OUT>
+template <int DT_IN, int DT_OUT, int UNR>
 __global__ void __launch_bounds__(512)
 k_twoshot_nvls(const __grid_constant__ CommDev c, size_t in_off, size_t out_off, size_t count,
                float scale, int mode, void* rs_out) {
@@ -418,33 +467,37 @@ k_twoshot_nvls(const __grid_constant__ CommDev c, size_t in_off, size_t out_off,
   const size_t ufirst = (ebeg + U::EPU - 1) / U::EPU, ulast = eend / U::EPU;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   if (ulast > ufirst) {
-    // 2x unrolled: two units in flight per thread hides the switch round trip
-    size_t u = ufirst + tid;
-    for (; u + nth < ulast; u += 2 * nth) {
-      uint32_t w0[U::OUT_V * 4], w1[U::OUT_V * 4];
-      nvls_reduce_unit<DT_IN, DT_OUT>(c, in_off, u, scale, w0);
-      nvls_reduce_unit<DT_IN, DT_OUT>(c, in_off, u + nth, scale, w1);
-      if (mode == 0) {
+    // UNR multimem.ld_reduce in flight per thread hide the switch round trip
+    for (size_t ub = ufirst + tid; ub < ulast; ub += (size_t)UNR * nth) {
+      V16 raw[UNR][U::IN_V];
 #pragma unroll
-        for (int k = 0; k < U::OUT_V; ++k) {
-          mc_st16(c.mc + out_off + u * (size_t)(U::OUT_V * 16) + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
-          mc_st16(c.mc + out_off + (u + nth) * (size_t)(U::OUT_V * 16) + k * 16, *reinterpret_cast<V16*>(&w1[4 * k]));
-        }
-      } else {
+      for (int j = 0; j < UNR; ++j) {
+        const size_t u = ub + (size_t)j * nth;
+        if (u < ulast) {
 #pragma unroll
-        for (int k = 0; k < U::OUT_V; ++k) {
-          st16((char*)rs_out + (u * U::EPU - ebeg) * U::SO + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
-          st16((char*)rs_out + ((u + nth) * U::EPU - ebeg) * U::SO + k * 16, *reinterpret_cast<V16*>(&w1[4 * k]));
+          for (int k = 0; k < U::IN_V; ++k) raw[j][k] = mc_ld_reduce<DT_IN>(c.mc + in_off + u * (size_t)(U::IN_V * 16) + k * 16);
         }
       }
-    }
-    for (; u < ulast; u += nth) {
-      uint32_t w0[U::OUT_V * 4];
-      nvls_reduce_unit<DT_IN, DT_OUT>(c, in_off, u, scale, w0);
 #pragma unroll
-      for (int k = 0; k < U::OUT_V; ++k) {
-        if (mode == 0) mc_st16(c.mc + out_off + u * (size_t)(U::OUT_V * 16) + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
-        else st16((char*)rs_out + (u * U::EPU - ebeg) * U::SO + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
+      for (int j = 0; j < UNR; ++j) {
+        const size_t u = ub + (size_t)j * nth;
+        if (u >= ulast) break;
+        uint32_t w0[U::OUT_V * 4];
+        if (DT_IN == DT_OUT && scale == 1.0f) {
+#pragma unroll
+          for (int k = 0; k < U::IN_V * 4; ++k) w0[k] = reinterpret_cast<uint32_t*>(raw[j])[k];
+        } else {
+          float a[U::EPU];
+          Codec<DT_IN, U::EPU>::unpack(reinterpret_cast<const uint32_t*>(raw[j]), a);
+#pragma unroll
+          for (int i = 0; i < U::EPU; ++i) a[i] *= scale;
+          Codec<DT_OUT, U::EPU>::pack(a, w0);
+        }
+#pragma unroll
+        for (int k = 0; k < U::OUT_V; ++k) {
+          if (mode == 0) mc_st16(c.mc + out_off + u * (size_t)(U::OUT_V * 16) + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
+          else st16((char*)rs_out + (u * U::EPU - ebeg) * U::SO + k * 16, *reinterpret_cast<V16*>(&w0[4 * k]));
+        }
       }
     }
   }
@@ -641,10 +694,10 @@ DEVI void copy_bytes_block(char* dst, const char* src, size_t bytes, size_t tid,
   const bool al = ((((uintptr_t)dst) | ((uintptr_t)src) | bytes) & 15) == 0;
   if (al) {
     size_t n = bytes / 16, i = tid;
-    for (; i + nth < n; i += 2 * nth) {   // two 16B in flight
-      V16 a = ld16(src + i * 16), b = ld16(src + (i + nth) * 16);
-      if (mc) { mc_st16(dst + i * 16, a); mc_st16(dst + (i + nth) * 16, b); }
-      else { st16(dst + i * 16, a); st16(dst + (i + nth) * 16, b); }
+    for (; i + 3 * nth < n; i += 4 * nth) {   // four 16B loads in flight per thread
+      V16 a = ld16(src + i * 16), b = ld16(src + (i + nth) * 16), cc = ld16(src + (i + 2 * nth) * 16), d = ld16(src + (i + 3 * nth) * 16);
+      if (mc) { mc_st16(dst + i * 16, a); mc_st16(dst + (i + nth) * 16, b); mc_st16(dst + (i + 2 * nth) * 16, cc); mc_st16(dst + (i + 3 * nth) * 16, d); }
+      else { st16(dst + i * 16, a); st16(dst + (i + nth) * 16, b); st16(dst + (i + 2 * nth) * 16, cc); st16(dst + (i + 3 * nth) * 16, d); }
     }
     for (; i < n; i += nth) { V16 a = ld16(src + i * 16); if (mc) mc_st16(dst + i * 16, a); else st16(dst + i * 16, a); }
   } else if (!mc && ((((uintptr_t)dst) | ((uintptr_t)src) | bytes) & 3) == 0) {
@@ -1046,8 +1099,16 @@ static int launch_ar_op(sy_comm* c, const void* in, void* out, size_t in_off, si
     OPSWITCH((k_oneshot<DT_IN, DT_OUT, OP><<<g, th, 0, s>>>(d, in, out, count, scale)));
   } else if (algo == SY_ALGO_TWOSHOT_P2P) {
     size_t units = count / U::EPU / (size_t)c->world + 1;
-    int g = grid_for(c, units, th);
-    OPSWITCH((k_twoshot_p2p<DT_IN, DT_OUT, OP><<<g, th, 0, s>>>(d, in_off, out_off, count, scale, 0, nullptr)));
+    if (op == SY_SUM && c->world <= 2) {
+      int g = grid_for(c, units, th, 4);
+      k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM, 2, 4><<<g, th, 0, s>>>(d, in_off, out_off, count, scale, 0, nullptr);
+    } else if (op == SY_SUM && c->world <= 4) {
+      int g = grid_for(c, units, th, 2);
+      k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM, 4, 2><<<g, th, 0, s>>>(d, in_off, out_off, count, scale, 0, nullptr);
+    } else {
+      int g = grid_for(c, units, th);
+      OPSWITCH((k_twoshot_p2p<DT_IN, DT_OUT, OP, SY_MAXR, 1><<<g, th, 0, s>>>(d, in_off, out_off, count, scale, 0, nullptr)));
+    }
   } else return SY_ERR_ARG;
 #undef OPSWITCH
   LAUNCH_CHECK(c);
@@ -1058,8 +1119,8 @@ template <int DT_IN, int DT_OUT>
 static int launch_ar_nvls(sy_comm* c, size_t in_off, size_t out_off, size_t count, float scale, cudaStream_t s) {
   using U = Unit<DT_IN, DT_OUT>;
   size_t units = count / U::EPU / (size_t)c->world + 1;
-  int g = grid_for(c, units, (int)c->threads, 2);
-  k_twoshot_nvls<DT_IN, DT_OUT><<<g, (int)c->threads, 0, s>>>(devof(c), in_off, out_off, count, scale, 0, nullptr);
+  int g = grid_for(c, units, (int)c->threads, 4);
+  k_twoshot_nvls<DT_IN, DT_OUT, 4><<<g, (int)c->threads, 0, s>>>(devof(c), in_off, out_off, count, scale, 0, nullptr);
   LAUNCH_CHECK(c);
   return SY_OK;
 }
@@ -1104,13 +1165,17 @@ static int launch_rs(sy_comm* c, size_t in_off, void* out, size_t count, float s
   if (!kNvlsType) nvls = false;
   if (nvls) {
     if constexpr (kNvlsType)
-      k_twoshot_nvls<DT_IN, DT_OUT><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out);
+      k_twoshot_nvls<DT_IN, DT_OUT, 4><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out);
+  } else if (vec_ok && op == SY_SUM && c->world <= 2) {
+    k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM, 2, 4><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out);
+  } else if (vec_ok && op == SY_SUM && c->world <= 4) {
+    k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM, 4, 2><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out);
   } else if (vec_ok) {
     switch (op) {
-      case SY_SUM: k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
-      case SY_MAX: k_twoshot_p2p<DT_IN, DT_OUT, SY_MAX><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
-      case SY_MIN: k_twoshot_p2p<DT_IN, DT_OUT, SY_MIN><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
-      default: k_twoshot_p2p<DT_IN, DT_OUT, SY_PROD><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
+      case SY_SUM: k_twoshot_p2p<DT_IN, DT_OUT, SY_SUM, SY_MAXR, 1><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
+      case SY_MAX: k_twoshot_p2p<DT_IN, DT_OUT, SY_MAX, SY_MAXR, 1><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
+      case SY_MIN: k_twoshot_p2p<DT_IN, DT_OUT, SY_MIN, SY_MAXR, 1><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
+      default: k_twoshot_p2p<DT_IN, DT_OUT, SY_PROD, SY_MAXR, 1><<<g, (int)c->threads, 0, s>>>(d, in_off, 0, count, scale, 1, out); break;
     }
   } else {
     return SY_ERR_UNSUPPORTED;  // caller falls back to the staged element path
@@ -1138,8 +1203,8 @@ int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_
 
 int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt, bool nvls, void* stream) {
   size_t bytes = count * sy_dtype_size(dt);
-  int g = grid_for(c, bytes / 16 + 1, (int)c->threads, 2);
-  if (!nvls && g < c->world && bytes >= (64u << 10)) g = c->world;
+  int g = grid_for(c, bytes / 16 + 1, (int)c->threads, 4);
+  if (!nvls) { g = g / c->world * c->world; if (g < c->world) g = bytes >= (64u << 10) ? c->world : 1; }
   k_allgather_k<<<g, (int)c->threads, 0, (cudaStream_t)stream>>>(devof(c), in, out_off, bytes, nvls ? 1 : 0);
   LAUNCH_CHECK(c);
   return SY_OK;

@@ -73,7 +73,7 @@ int sy_is_symmetric(sy_comm* c, const void* p);
 
 // ---- tuning ---------------------------------------------------------------
 // knob names: "max_blocks", "threads", "ll_max_bytes", "oneshot_max_bytes",
-// "nvls_min_bytes", "timeout_ms"
+// "nvls_min_bytes", "timeout_ms", "nvls_copy"
 int sy_set_tuning(sy_comm* c, const char* knob, long value);
 long sy_get_tuning(sy_comm* c, const char* knob);
 
