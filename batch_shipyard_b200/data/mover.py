@@ -1,0 +1,128 @@
+"""Task-side data mover (the blobxfer / task_file_mover stand-in).
+
+Runs inside a task's system prologue / epilogue:
+  fetch      copy one resource file (file:// URL or path) into the working dir
+  ingress    storage "account" (a local directory) -> task directory, include/exclude filters
+  egress     task directory -> storage location, only when the condition matches
+             $SHIPYARD_TASK_RESULT (tasksuccess | taskfailure | taskcompletion)
+  taskfiles  copy another task's files (``input_data.azure_batch``)
+Reference: /root/reference/scripts/shipyard_blobxfer.sh:7-71 (spec parsing, conditional
+egress), /root/reference/cargo/task_file_mover.py:87-141, /root/reference/convoy/data.py:115-489.
+"""
+from __future__ import annotations
+
+import argparse
+import fnmatch
+import os
+import shutil
+import sys
+import time
+import urllib.parse
+from typing import Iterable, Optional
+
+
+def _match(rel: str, include: Iterable[str], exclude: Iterable[str]) -> bool:
+    include, exclude = list(include or []), list(exclude or [])
+    if include and not any(fnmatch.fnmatch(rel, p) for p in include):
+        return False
+    return not any(fnmatch.fnmatch(rel, p) for p in exclude)
+
+
+def copy_tree(src: str, dst: str, include=(), exclude=()) -> tuple[int, int]:
+    """Copy files under `src` (or the single file `src`) to `dst`; returns (files, bytes)."""
+    n = nb = 0
+    if os.path.isfile(src):
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy2(src, os.path.join(dst, os.path.basename(src)))
+        return 1, os.path.getsize(src)
+    for d, _, fs in os.walk(src):
+        for fn in fs:
+            p = os.path.join(d, fn)
+            rel = os.path.relpath(p, src).replace(os.sep, "/")
+            if not _match(rel, include, exclude):
+                continue
+            out = os.path.join(dst, rel)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            shutil.copy2(p, out)
+            n += 1; nb += os.path.getsize(p)
+    return n, nb
+
+
+def storage_root(state_dir: str, link: str) -> str:
+    """Directory backing a storage account link: credentials.storage.<link>.local_path if recorded
+    at pool creation, else <state>/storage/<link>."""
+    from ..state.store import Store
+    st = Store(state_dir)
+    ent = st.try_get("storagelink", link, "")
+    if ent and ent.get("local_path"):
+        return ent["local_path"]
+    return os.path.join(state_dir, "storage", link)
+
+
+def _log(name: str, msg: str) -> None:
+    try:
+        with open(os.path.join(os.environ.get("AZ_BATCH_TASK_DIR", "."), f"blobxfer-{name}.log"), "a") as f:
+            f.write(f"{time.strftime('%Y-%m-%dT%H:%M:%S')} {msg}\n")
+    except OSError:
+        pass
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="shipyard-mover")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    f = sub.add_parser("fetch"); f.add_argument("--url", required=True); f.add_argument("--dest", required=True); f.add_argument("--mode")
+    for name in ("ingress", "egress"):
+        p = sub.add_parser(name)
+        p.add_argument("--state-dir", required=True); p.add_argument("--link", required=True)
+        p.add_argument("--remote", required=True); p.add_argument("--local", required=True)
+        p.add_argument("--include", action="append", default=[]); p.add_argument("--exclude", action="append", default=[])
+        if name == "egress":
+            p.add_argument("--condition", default="tasksuccess", choices=["tasksuccess", "taskfailure", "taskcompletion"])
+    t = sub.add_parser("taskfiles")
+    t.add_argument("--state-dir", required=True); t.add_argument("--job", required=True); t.add_argument("--task", required=True)
+    t.add_argument("--dest", required=True)
+    t.add_argument("--include", action="append", default=[]); t.add_argument("--exclude", action="append", default=[])
+    a = ap.parse_args(argv)
+    if a.cmd == "fetch":
+        u = urllib.parse.urlparse(a.url)
+        if u.scheme in ("", "file"):
+            src = u.path if u.scheme == "file" else a.url
+        else:
+            print(f"mover: cannot fetch '{a.url}': no network on a local pool (use file:// or a path)", file=sys.stderr)
+            return 1
+        os.makedirs(os.path.dirname(os.path.abspath(a.dest)) or ".", exist_ok=True)
+        shutil.copy2(src, a.dest)
+        if a.mode:
+            os.chmod(a.dest, int(str(a.mode), 8))
+        return 0
+    if a.cmd == "ingress":
+        src = os.path.join(storage_root(a.state_dir, a.link), a.remote.strip("/"))
+        if not os.path.exists(src):
+            print(f"mover: ingress source {src} does not exist", file=sys.stderr)
+            return 1
+        n, nb = copy_tree(src, a.local, a.include, a.exclude)
+        _log("download", f"ingress {a.link}:{a.remote} -> {a.local}: {n} files, {nb} bytes")
+        return 0
+    if a.cmd == "egress":
+        result = os.environ.get("SHIPYARD_TASK_RESULT", "success")
+        want = {"tasksuccess": result == "success", "taskfailure": result != "success", "taskcompletion": True}[a.condition]
+        if not want:
+            _log("upload", f"egress skipped: condition {a.condition} not met (result={result})")
+            return 0
+        dst = os.path.join(storage_root(a.state_dir, a.link), a.remote.strip("/"))
+        n, nb = copy_tree(a.local, dst, a.include, a.exclude + ["*.spec", ".shipyard.envlist", ".heartbeat"])
+        _log("upload", f"egress {a.local} -> {a.link}:{a.remote}: {n} files, {nb} bytes")
+        return 0
+    if a.cmd == "taskfiles":
+        from ..backend.local import LocalBackend
+        b = LocalBackend(state_dir=a.state_dir)
+        job = b.get_job(a.job)
+        src = b.task_dir(job["pool_id"], a.job, a.task)
+        n, nb = copy_tree(src, a.dest, a.include, a.exclude)
+        _log("download", f"taskfiles {a.job}/{a.task} -> {a.dest}: {n} files, {nb} bytes")
+        return 0
+    return 2
+
+
+if __name__ == "__main__":
+    sys.exit(main())

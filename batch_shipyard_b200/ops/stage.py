@@ -1,0 +1,131 @@
+"""ctypes binding for ``libshipyard_stage`` (pinned arena + async H2D mover).
+
+``Stager(device=None)`` is the host-only mode used on CPU boxes; with a device index the
+arena is cudaHostAlloc'd and copies run on per-worker CUDA copy streams.  Used by the
+image/artefact pre-loader (cascade equivalent), ``shipyard data ingress`` and the recipes'
+input pipelines.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_native", "libshipyard_stage.so")
+
+
+def load() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            from .._build import ensure_built
+            ensure_built(["stage"])
+        lib = C.CDLL(p)
+        vp, sz, i, lg, db = C.c_void_p, C.c_size_t, C.c_int, C.c_long, C.c_double
+        lib.sy_stage_last_error.restype = C.c_char_p
+        lib.sy_stage_create.argtypes = [C.POINTER(vp), i, sz, i, i]
+        lib.sy_stage_destroy.argtypes = [vp]
+        lib.sy_stage_submit_file.argtypes = [vp, C.c_char_p, vp, sz, sz]; lib.sy_stage_submit_file.restype = lg
+        lib.sy_stage_submit_host.argtypes = [vp, vp, sz, vp]; lib.sy_stage_submit_host.restype = lg
+        lib.sy_stage_wait.argtypes = [vp, lg, db]
+        lib.sy_stage_stream_wait.argtypes = [vp, lg, vp]
+        lib.sy_stage_ptr.argtypes = [vp, lg]; lib.sy_stage_ptr.restype = vp
+        lib.sy_stage_query.argtypes = [vp, lg, C.POINTER(C.c_ulonglong), C.POINTER(db)]
+        lib.sy_stage_release.argtypes = [vp, lg]
+        lib.sy_stage_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(db)]
+        _LIB = lib
+    return _LIB
+
+
+class StageError(RuntimeError):
+    pass
+
+
+@dataclass
+class TicketInfo:
+    state: str
+    bytes: int
+    done_bytes: int
+    queue_seconds: float
+    transfer_seconds: float
+
+
+_STATES = {0: "queued", 1: "running", 2: "done", 3: "failed"}
+
+
+class Stager:
+    def __init__(self, device: Optional[int] = None, arena_bytes: int = 256 << 20, concurrency: int = 4,
+                 chunks_per_worker: int = 2):
+        self.lib = load()
+        self.device = -1 if device is None else int(device)
+        h = C.c_void_p()
+        rc = self.lib.sy_stage_create(C.byref(h), self.device, int(arena_bytes), int(concurrency), int(chunks_per_worker))
+        if rc != 0:
+            raise StageError(f"stage create failed ({rc}): {self.lib.sy_stage_last_error().decode()}")
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.sy_stage_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit_file(self, path: str, dptr: int = 0, offset: int = 0, nbytes: int = 0) -> int:
+        t = self.lib.sy_stage_submit_file(self._h, path.encode(), C.c_void_p(dptr), offset, nbytes)
+        if t < 0:
+            raise StageError(self.lib.sy_stage_last_error().decode())
+        return int(t)
+
+    def submit_host(self, host_ptr: int, nbytes: int, dptr: int = 0) -> int:
+        t = self.lib.sy_stage_submit_host(self._h, C.c_void_p(host_ptr), nbytes, C.c_void_p(dptr))
+        if t < 0:
+            raise StageError(self.lib.sy_stage_last_error().decode())
+        return int(t)
+
+    def wait(self, ticket: int, timeout: float = -1.0) -> bool:
+        rc = self.lib.sy_stage_wait(self._h, ticket, float(timeout))
+        if rc == 1:
+            return False
+        if rc != 0:
+            raise StageError(f"ticket {ticket}: {self.lib.sy_stage_last_error().decode()}")
+        return True
+
+    def stream_wait(self, ticket: int, cuda_stream: int) -> None:
+        rc = self.lib.sy_stage_stream_wait(self._h, ticket, C.c_void_p(cuda_stream))
+        if rc != 0:
+            raise StageError(f"ticket {ticket}: {self.lib.sy_stage_last_error().decode()}")
+
+    def ptr(self, ticket: int) -> int:
+        return int(self.lib.sy_stage_ptr(self._h, ticket) or 0)
+
+    def query(self, ticket: int) -> TicketInfo:
+        out = (C.c_ulonglong * 3)(); secs = (C.c_double * 2)()
+        if self.lib.sy_stage_query(self._h, ticket, out, secs) != 0:
+            raise StageError(f"unknown ticket {ticket}")
+        return TicketInfo(_STATES[int(out[0])], int(out[1]), int(out[2]), float(secs[0]), float(secs[1]))
+
+    def read_host(self, ticket: int) -> bytes:
+        """Host-only mode: the staged bytes."""
+        assert self.device < 0
+        info = self.query(ticket)
+        return C.string_at(self.ptr(ticket), info.bytes)
+
+    def release(self, ticket: int) -> None:
+        self.lib.sy_stage_release(self._h, ticket)
+
+    def stats(self) -> dict:
+        out = (C.c_ulonglong * 4)(); busy = C.c_double()
+        self.lib.sy_stage_stats(self._h, out, C.byref(busy))
+        return {"bytes_staged": int(out[0]), "memcpy_calls": int(out[1]), "arena_bytes": int(out[2]),
+                "chunk_bytes": int(out[3]), "busy_seconds": float(busy.value)}
