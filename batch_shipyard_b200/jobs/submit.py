@@ -176,7 +176,10 @@ def add_jobs(b: LocalBackend, config: dict, recreate: bool = False, tail: Option
             elif tid in existing_ids or tid in reserved:
                 raise JobSubmissionError(f"task id {tid} already exists in job {jid}")
             reserved.add(tid)
-            rec = B.build_task(config, pool, jobspec, t, tid, counts, gpu_count=gpu_count, dry_run=dry_run).to_dict()
+            try:
+                rec = B.build_task(config, pool, jobspec, t, tid, counts, gpu_count=gpu_count, dry_run=dry_run).to_dict()
+            except ValueError as e:
+                raise JobSubmissionError(str(e)) from e
             if scratch is not None and auto_scratch.setup == "dependency":
                 rec["depends_on"] = list(rec["depends_on"]) + [scratch["id"]]
             if scratch is not None:

@@ -79,8 +79,10 @@ class Store:
         os.makedirs(os.path.join(self.root, "blobs"), exist_ok=True)
         self.db_path = os.path.join(self.root, "state.db")
         self._local = threading.local()
-        with self._tx() as c:
-            c.executescript(_SCHEMA)
+        c = self._conn()
+        for stmt in _SCHEMA.split(";"):
+            if stmt.strip():
+                c.execute(stmt)
 
     # -- connection handling ---------------------------------------------------
     def _conn(self) -> sqlite3.Connection:

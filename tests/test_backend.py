@@ -1,0 +1,289 @@
+"""Local backend + node agent + native runner: the integration layer of the test pyramid."""
+import json
+import os
+import time
+
+import pytest
+
+from _helpers import make, read, run, up
+from batch_shipyard_b200.backend.agent import NodeAgent
+from batch_shipyard_b200.backend.local import BackendError
+from batch_shipyard_b200.jobs import submit
+from batch_shipyard_b200.pool import provision
+
+
+def test_pool_lifecycle_and_markers(tmp_path):
+    cfg, b = make(tmp_path)
+    pool = up(cfg, b)
+    assert pool["allocation_state"] == "steady" and pool["_summary"]["ready"] == 2
+    nodes = b.list_nodes("testpool")
+    assert [n["id"] for n in nodes] == ["cpu-0", "cpu-1"] and all(n["state"] == "idle" for n in nodes)
+    assert os.path.exists(os.path.join(b.node_startup_dir("testpool"), "cpu-0", provision.NODEPREP_FINISHED))
+    ev = [(e["source"], e["event"]) for e in b.store.events("testpool")]
+    assert ("nodeprep", "start") in ev and ("nodeprep", "end") in ev and ("cascade", "start") in ev and ("cascade", "gr-done") in ev
+    assert [e["event"] for e in b.store.events("testpool") if e["source"] == "cascade"].count("pull-end") == 1
+    with pytest.raises(provision.PoolCreationError):
+        up(cfg, b)
+    up(cfg, b, recreate=True)
+    b.resize_pool("testpool", 4, 0)
+    provision.bring_up_nodes(b, "testpool")
+    assert b.node_counts("testpool")["dedicated"]["idle"] == 4
+    b.resize_pool("testpool", 1, 0)
+    assert b.node_counts("testpool")["dedicated"]["total"] == 1
+    stats = b.pool_stats("testpool")
+    assert stats["total_nodes"] == 1 and stats["task_slots"] == 1
+    b.delete_pool("testpool")
+    assert not b.pool_exists("testpool")
+
+
+def test_start_task_failure_reboot_and_unusable_recovery(tmp_path):
+    cfg, b = make(tmp_path, pool={"reboot_on_start_task_failed": True, "attempt_recovery_on_unusable": True})
+    calls = {}
+
+    def hook(node, attempt):
+        calls[node["id"]] = calls.get(node["id"], 0) + 1
+        if node["id"] == "cpu-0" and attempt < 2:
+            return "start task exited 1"
+        if node["id"] == "cpu-1" and attempt == 0 and calls[node["id"]] == 1:
+            return "unusable: device fell off the bus"
+        return None
+    pool = up(cfg, b, fault_hook=hook)
+    s = pool["_summary"]
+    assert s["rebooted"] == 2 and s["recovered"] == 1
+    provision.bring_up_nodes(b, "testpool")
+    states = {n["id"]: n["state"] for n in b.list_nodes("testpool")}
+    assert states["cpu-0"] == "idle" and list(states.values()).count("idle") == 2
+    # without reboot permission the node stays start_task_failed
+    cfg2, b2 = make(tmp_path / "b")
+    pool2 = up(cfg2, b2, fault_hook=lambda n, a: "boom" if n["id"] == "cpu-1" else None)
+    assert pool2["_summary"]["start_task_failed"] == 1
+    assert b2.list_nodes("testpool", start_task_failed=True)[0]["id"] == "cpu-1"
+
+
+def test_cross_field_rules(tmp_path):
+    cfg, _ = make(tmp_path, pool={"vm_count": {"dedicated": 1, "low_priority": 1}})
+    with pytest.raises(ValueError):
+        provision.adjust_settings_for_pool_creation(cfg)
+    cfg, _ = make(tmp_path, pool={"per_job_auto_scratch": True, "inter_node_communication_enabled": False})
+    with pytest.raises(ValueError):
+        provision.adjust_settings_for_pool_creation(cfg)
+    cfg, _ = make(tmp_path, pool={"transfer_files_on_pool_creation": True})
+    warns = provision.adjust_settings_for_pool_creation(cfg)
+    assert cfg["pool_specification"]["block_until_all_global_resources_loaded"] is False and warns
+    assert "-b" not in provision.nodeprep_flags(cfg) and "-c" in provision.nodeprep_flags(cfg)
+
+
+def test_runner_contract_env_and_exit_code(tmp_path):
+    tasks = [{"id": "ok", "docker_image": "busybox", "environment_variables": {"FOO": "bar"},
+              "command": 'echo "$AZ_BATCH_JOB_ID/$AZ_BATCH_TASK_ID $FOO $AZ_BATCH_POOL_ID"; test -d "$AZ_BATCH_TASK_WORKING_DIR" && test "$PWD" = "$AZ_BATCH_TASK_WORKING_DIR" && test -d "$AZ_BATCH_NODE_SHARED_DIR"'},
+             {"id": "bad", "docker_image": "busybox", "command": "echo oops >&2; exit 7"}]
+    cfg, b = make(tmp_path, tasks=tasks)
+    up(cfg, b); run(cfg, b)
+    assert read(b, "job1", "ok").strip() == "job1/ok bar testpool"
+    t = b.get_task("job1", "ok")
+    assert t["state"] == "completed" and t["result"] == "success" and t["exit_code"] == 0 and len(t["node_ids"]) == 1
+    bad = b.get_task("job1", "bad")
+    assert bad["result"] == "failure" and bad["exit_code"] == 7 and "oops" in read(b, "job1", "bad", "stderr.txt")
+    envlist = read(b, "job1", "ok", ".shipyard.envlist")
+    assert "FOO=bar" in envlist and "\nHOME=" not in "\n" + envlist and "\nPATH=" not in "\n" + envlist
+    res = json.loads(read(b, "job1", "bad", "result.json"))
+    assert res["exit_code"] == 7 and res["result"] == "fail"
+    assert b.count_tasks("job1") == {"active": 0, "running": 0, "completed": 2, "succeeded": 1, "failed": 1}
+    assert all(n["state"] == "idle" and not n["running_tasks"] for n in b.list_nodes("testpool"))
+
+
+def test_dependencies_merge_task_and_ids(tmp_path):
+    tasks = [{"docker_image": "busybox", "task_factory": {"repeat": 3}, "command": "echo part >> $AZ_BATCH_NODE_SHARED_DIR/parts"},
+             {"id": "after", "docker_image": "busybox", "depends_on": ["task-00000", "task-00001"], "command": "wc -l < $AZ_BATCH_NODE_SHARED_DIR/parts"}]
+    cfg, b = make(tmp_path, tasks=tasks, job={"merge_task": {"docker_image": "busybox", "command": "echo merged"}})
+    up(cfg, b)
+    out = run(cfg, b)
+    assert out["job1"]["task_ids"] == ["task-00000", "task-00001", "task-00002", "after", "merge-task-00000"]
+    m = b.get_task("job1", "merge-task-00000")
+    assert m["result"] == "success" and sorted(m["depends_on"]) == ["after", "task-00000", "task-00001", "task-00002"]
+    assert m["start_time"] >= max(b.get_task("job1", t)["end_time"] for t in m["depends_on"])
+    assert int(read(b, "job1", "after").strip()) >= 2
+    # appending to the existing job continues the generic id sequence
+    with pytest.raises(submit.JobSubmissionError):
+        submit.add_jobs(b, cfg)                       # explicit id "after" would collide
+    cfg["job_specifications"][0]["tasks"].pop()
+    out2 = submit.add_jobs(b, cfg)
+    assert out2["job1"]["task_ids"][0] == "task-00003" and out2["job1"]["task_ids"][-1] == "merge-task-00001"
+
+
+def test_dependency_failure_blocks_or_satisfies(tmp_path):
+    def tasks(action):
+        return [{"id": "a", "docker_image": "busybox", "command": "exit 3", "exit_conditions": {"default": {"exit_options": {"dependency_action": action}}}},
+                {"id": "b", "docker_image": "busybox", "depends_on": ["a"], "command": "echo ran"}]
+    cfg, b = make(tmp_path, tasks=tasks("block")); up(cfg, b); run(cfg, b, max_seconds=5)
+    assert b.get_task("job1", "b")["state"] == "active"
+    cfg, b = make(tmp_path / "s", tasks=tasks("satisfy")); up(cfg, b); run(cfg, b)
+    assert b.get_task("job1", "b")["result"] == "success"
+    cfg, b = make(tmp_path / "r", tasks=[{"id": "0", "docker_image": "busybox", "command": "true"}, {"id": "1", "docker_image": "busybox", "command": "true"},
+                                         {"id": "r", "docker_image": "busybox", "depends_on_range": [0, 1], "command": "echo range"}])
+    up(cfg, b); run(cfg, b)
+    assert b.get_task("job1", "r")["result"] == "success"
+
+
+def test_retries_exit_action_and_auto_complete(tmp_path):
+    flaky = 'f=$AZ_BATCH_NODE_SHARED_DIR/flaky; n=$(cat $f 2>/dev/null || echo 0); echo $((n+1)) > $f; test $n -ge 2'
+    cfg, b = make(tmp_path, tasks=[{"id": "flaky", "docker_image": "busybox", "max_task_retries": 3, "command": flaky}], job={"auto_complete": True})
+    up(cfg, b); run(cfg, b)
+    t = b.get_task("job1", "flaky")
+    assert t["result"] == "success" and t["retry_count"] == 2
+    assert b.get_job("job1")["state"] == "completed" and b.get_job("job1")["terminate_reason"] == "AllTasksComplete"
+    tasks = [{"id": "boom", "docker_image": "busybox", "command": "exit 1", "exit_conditions": {"default": {"exit_options": {"job_action": "terminate"}}}},
+             {"id": "later", "docker_image": "busybox", "depends_on": ["boom"], "command": "echo never"}]
+    cfg, b = make(tmp_path / "t", tasks=tasks); up(cfg, b); run(cfg, b)
+    assert b.get_job("job1")["state"] == "completed" and "boom" in b.get_job("job1")["terminate_reason"]
+    assert b.get_task("job1", "later")["result"] == "failure"
+
+
+def test_job_preparation_release_and_input_output_data(tmp_path):
+    store = tmp_path / "acct"
+    (store / "in" / "d").mkdir(parents=True)
+    (store / "in" / "a.dat").write_text("A"); (store / "in" / "d" / "b.dat").write_text("B"); (store / "in" / "skip.tmp").write_text("x")
+    tasks = [{"id": "t", "docker_image": "busybox",
+              "input_data": {"azure_storage": [{"storage_account_settings": "acct", "remote_path": "in", "local_path": "$AZ_BATCH_TASK_WORKING_DIR/inp", "exclude": ["*.tmp"]}]},
+              "output_data": {"azure_storage": [{"storage_account_settings": "acct", "remote_path": "out/ok", "local_path": "$AZ_BATCH_TASK_WORKING_DIR/res", "condition": "tasksuccess"},
+                                                {"storage_account_settings": "acct", "remote_path": "out/fail", "local_path": "$AZ_BATCH_TASK_WORKING_DIR/res", "condition": "taskfailure"}]},
+              "command": "mkdir res; cat inp/a.dat inp/d/b.dat > res/joined; test ! -e inp/skip.tmp; cat $AZ_BATCH_NODE_SHARED_DIR/prep"}]
+    cfg, b = make(tmp_path, tasks=tasks, job={"auto_complete": True, "job_preparation": {"command": "echo prepared > $AZ_BATCH_NODE_SHARED_DIR/prep"},
+                                               "job_release": {"command": "echo released > $AZ_BATCH_NODE_SHARED_DIR/rel"}},
+                  extra={"credentials": {"storage": {"acct": {"local_path": str(store)}}}})
+    up(cfg, b); run(cfg, b)
+    assert b.get_task("job1", "t")["result"] == "success", read(b, "job1", "t", "stderr.txt")
+    assert read(b, "job1", "t").strip() == "prepared"
+    assert (store / "out" / "ok" / "joined").read_text() == "AB" and not (store / "out" / "fail").exists()
+    assert open(os.path.join(b.node_shared_dir("testpool"), "rel")).read().strip() == "released"
+    assert b.get_job("job1")["state"] == "completed"
+
+
+def test_multi_instance_rank_env_and_failure_propagation(tmp_path):
+    mi = {"num_instances": "pool_current_dedicated", "coordination_command": "echo coord >> $AZ_BATCH_NODE_SHARED_DIR/coord",
+          "pre_execution_command": "echo pre > $AZ_BATCH_NODE_SHARED_DIR/pre", "mpi": {"runtime": "openmpi", "processes_per_node": 2}}
+    tasks = [{"id": "mi", "docker_image": "busybox", "multi_instance": mi,
+              "command": 'echo "rank $RANK/$WORLD_SIZE ompi $OMPI_COMM_WORLD_RANK master $AZ_BATCH_IS_CURRENT_NODE_MASTER hosts $AZ_BATCH_HOST_LIST" > $AZ_BATCH_TASK_DIR/r$RANK.txt'}]
+    cfg, b = make(tmp_path, tasks=tasks); up(cfg, b); run(cfg, b)
+    t = b.get_task("job1", "mi")
+    assert t["result"] == "success" and sorted(t["node_ids"]) == ["cpu-0", "cpu-1"]
+    assert t["mpi_command"].startswith("mpirun --oversubscribe -host $AZ_BATCH_HOST_LIST -np 4 --map-by ppr:2:node")
+    got = sorted(read(b, "job1", "mi", f"r{r}.txt").strip() for r in range(4))
+    assert got[0] == "rank 0/4 ompi 0 master true hosts 127.0.0.1,127.0.0.1" and got[3].startswith("rank 3/4 ompi 3 master false")
+    assert open(os.path.join(b.node_shared_dir("testpool"), "coord")).read().count("coord") == 2
+    # a dying rank fails the whole task and the survivors are reaped (no hang)
+    tasks = [{"id": "die", "docker_image": "busybox", "multi_instance": {"num_instances": 2, "mpi": {"runtime": "mpich", "processes_per_node": 1}},
+              "command": 'if [ "$RANK" = "1" ]; then exit 9; else sleep 60; fi'}]
+    cfg, b = make(tmp_path / "d", tasks=tasks); up(cfg, b)
+    t0 = time.time(); run(cfg, b)
+    d = b.get_task("job1", "die")
+    assert d["result"] == "failure" and d["exit_code"] == 9 and time.time() - t0 < 30
+    assert d["failure_info"]["rank_exit_codes"][1] == 9
+    # a task needing more instances than the pool has is never placed
+    cfg, b = make(tmp_path / "n", tasks=[{"id": "big", "docker_image": "busybox", "multi_instance": {"num_instances": 3}, "command": "true"}])
+    up(cfg, b); run(cfg, b, max_seconds=3)
+    assert b.get_task("job1", "big")["state"] == "active" and "needs 3 instances" in b.get_task("job1", "big")["scheduling_note"]
+
+
+def test_wall_time_terminate_and_fault_injection(tmp_path, monkeypatch):
+    cfg, b = make(tmp_path, tasks=[{"id": "slow", "docker_image": "busybox", "max_wall_time": "00:00:01", "command": "sleep 30"}])
+    up(cfg, b); t0 = time.time(); run(cfg, b)
+    t = b.get_task("job1", "slow")
+    assert t["result"] == "failure" and t["exit_code"] == 124 and time.time() - t0 < 20 and "wall time" in t["failure_info"]["message"]
+    cfg, b = make(tmp_path / "k", tasks=[{"id": "victim", "docker_image": "busybox", "command": "sleep 30"}])
+    up(cfg, b); submit.add_jobs(b, cfg)
+    agent = NodeAgent(b, "testpool", poll=0.02)
+    assert agent.acquire()
+    agent.tick()
+    assert b.get_task("job1", "victim")["state"] == "running"
+    b.terminate_task("job1", "victim")
+    for _ in range(400):
+        agent.tick()
+        if b.get_task("job1", "victim")["state"] == "completed":
+            break
+        time.sleep(0.02)
+    v = b.get_task("job1", "victim")
+    assert v["state"] == "completed" and v["result"] == "failure" and "terminated" in v["failure_info"]["message"]
+    agent.release()
+    monkeypatch.setenv("SHIPYARD_FAULT_INJECT", "kill_rank:0:after_ms:100")
+    cfg, b = make(tmp_path / "f", tasks=[{"id": "inj", "docker_image": "busybox", "multi_instance": {"num_instances": 2, "mpi": {"runtime": "openmpi", "processes_per_node": 1}}, "command": "sleep 20"}])
+    up(cfg, b); t0 = time.time(); run(cfg, b)
+    assert b.get_task("job1", "inj")["exit_code"] == 137 and time.time() - t0 < 15
+
+
+def test_disable_enable_migrate_and_priority(tmp_path):
+    cfg, b = make(tmp_path, tasks=[{"id": "t", "docker_image": "busybox", "command": "echo $AZ_BATCH_POOL_ID"}])
+    up(cfg, b)
+    cfg2, _ = make(tmp_path, pool={"id": "other", "vm_count": {"dedicated": 1, "low_priority": 0}})
+    up(cfg2, b)
+    submit.add_jobs(b, cfg)
+    b.disable_job("job1", "requeue")
+    NodeAgent(b, "testpool", poll=0.02).run(until_idle=True, max_seconds=2)
+    assert b.get_task("job1", "t")["state"] == "active"
+    with pytest.raises(BackendError):
+        b.migrate_job("nope", "other")
+    b.migrate_job("job1", "other"); b.enable_job("job1")
+    NodeAgent(b, "other", poll=0.02).run(until_idle=True, max_seconds=30)
+    assert read(b, "job1", "t").strip() == "other"
+    st = b.job_stats()
+    assert st["jobs"] == 1 and st["succeeded"] == 1
+
+
+def test_recurrence_job_schedule(tmp_path):
+    cfg, b = make(tmp_path, tasks=[{"docker_image": "busybox", "command": "date +%s%N >> $AZ_BATCH_NODE_SHARED_DIR/ticks"}],
+                  job={"auto_complete": True, "recurrence": {"schedule": {"recurrence_interval": "00:01:00"}}})
+    up(cfg, b)
+    out = submit.add_jobs(b, cfg)
+    assert out["job1"]["kind"] == "job_schedule" and out["job1"]["tasks_per_recurrence"] == 1
+    b.store.merge("jobschedule", "job1", "", {"recurrence_interval_s": 0.3})      # speed the clock up for the test
+    NodeAgent(b, "testpool", poll=0.02).run(until_idle=False, max_seconds=2.0)
+    s = b.get_job_schedule("job1")
+    assert s["runs"] >= 3
+    ticks = open(os.path.join(b.node_shared_dir("testpool"), "ticks")).read().split()
+    assert len(ticks) >= 3 and b.job_exists("job1:job-1")
+    b.terminate_job_schedule("job1")
+    assert b.get_job_schedule("job1")["state"] == "completed"
+
+
+def test_agent_crash_recovery_and_lease(tmp_path):
+    cfg, b = make(tmp_path, tasks=[{"id": "t", "docker_image": "busybox", "command": "echo again"}])
+    up(cfg, b); submit.add_jobs(b, cfg)
+    # simulate an agent that died right after marking the task running
+    b.update_task("job1", "t", state="running", pid=2 ** 22 + 12345, node_ids=["cpu-0"])
+    b.store.mutate("node", "testpool", "cpu-0", lambda n: (n["running_tasks"].append(["job1", "t"]), n.update(state="running")) and None)
+    a1 = NodeAgent(b, "testpool", poll=0.02)
+    assert a1.acquire()
+    with pytest.raises(BackendError):
+        NodeAgent(b, "testpool").run()           # lease is held
+    a1.release()
+    NodeAgent(b, "testpool", poll=0.02).run(until_idle=True, max_seconds=30)
+    t = b.get_task("job1", "t")
+    assert t["result"] == "success" and t["requeue_count"] == 1
+
+
+def test_auto_scratch_and_missing_image_policy(tmp_path):
+    cfg, b = make(tmp_path, pool={"per_job_auto_scratch": True},
+                  tasks=[{"id": "w", "docker_image": "busybox", "command": "touch $SHIPYARD_AUTO_SCRATCH/x && ls $SHIPYARD_AUTO_SCRATCH"}],
+                  job={"auto_scratch": {"setup": "dependency", "num_instances": "pool_current_dedicated"}, "auto_complete": True})
+    up(cfg, b); out = run(cfg, b)
+    assert out["job1"]["task_ids"][0] == "batch-shipyard-autoscratch"
+    assert b.get_task("job1", "w")["result"] == "success" and read(b, "job1", "w").strip() == "x"
+    assert "batch-shipyard-autoscratch" in b.get_task("job1", "w")["depends_on"]
+    assert not os.path.exists(os.path.join(b.node_shared_dir("testpool"), "auto_scratch", "job1"))   # job release cleaned it
+    cfg, b = make(tmp_path / "m", tasks=[{"docker_image": "notlisted", "command": "true"}]); up(cfg, b)
+    with pytest.raises(submit.JobSubmissionError):
+        submit.add_jobs(b, cfg)
+    cfg["job_specifications"][0]["allow_run_on_missing_image"] = True
+    submit.add_jobs(b, cfg)
+
+
+def test_max_tasks_per_node_and_fill(tmp_path):
+    cfg, b = make(tmp_path, pool={"vm_count": {"dedicated": 2, "low_priority": 0}, "max_tasks_per_node": 2, "node_fill_type": "pack"},
+                  tasks=[{"docker_image": "busybox", "task_factory": {"repeat": 2}, "command": "sleep 0.4; echo $AZ_BATCH_NODE_ID"}])
+    up(cfg, b); run(cfg, b)
+    nodes = {read(b, "job1", t["id"]).strip() for t in b.list_tasks("job1")}
+    assert nodes == {"cpu-0"}                                  # packed onto one node
+    cfg, b = make(tmp_path / "s", pool={"max_tasks_per_node": 2, "node_fill_type": "spread"},
+                  tasks=[{"docker_image": "busybox", "task_factory": {"repeat": 2}, "command": "sleep 0.4; echo $AZ_BATCH_NODE_ID"}])
+    up(cfg, b); run(cfg, b)
+    assert {read(b, "job1", t["id"]).strip() for t in b.list_tasks("job1")} == {"cpu-0", "cpu-1"}
