@@ -1,0 +1,169 @@
+"""Federation constraints / best fit / daemon, and the CLI surface."""
+import json
+import os
+
+import pytest
+from click.testing import CliRunner
+
+from _helpers import make, read, up
+from batch_shipyard_b200 import cli
+from batch_shipyard_b200.backend.agent import NodeAgent
+from batch_shipyard_b200.fed import client as FCl
+from batch_shipyard_b200.fed import constraints as FC
+from batch_shipyard_b200.fed.daemon import FederationProcessor
+from batch_shipyard_b200.fed.scheduler import select_pool
+from batch_shipyard_b200.jobs import submit
+
+
+def view(**kw):
+    d = dict(id="p", valid=True, location="local", vm_size="b200x8", native=False, windows=False, autoscale_enabled=False,
+             target_low_priority=0, max_tasks_per_node=1, inter_node_communication=True, cores_per_node=8, memory_mb_per_node=65536.0,
+             registries=[], idle_dedicated=2, schedulable_dedicated=2)
+    d.update(kw)
+    return FC.PoolView(**d)
+
+
+def cons(fc=None, tasks=None, **job):
+    return FC.parse_constraints(dict({"federation_constraints": fc or {}}, **job), tasks or [{"id": "t"}])
+
+
+def test_hard_constraint_truth_table():
+    ok = view()
+    assert FC.first_failed_hard_constraint(ok, cons()) is None
+    cases = [
+        ({"pool": {"location": "eastus"}}, view(), "location"),
+        ({"pool": {"native": True}}, view(), "native"),
+        ({"pool": {"windows": True}}, view(), "windows"),
+        ({"pool": {"autoscale": {"allow": False}}}, view(autoscale_enabled=True), "autoscale_allow"),
+        ({"pool": {"autoscale": {"allow": True, "exclusive": True}}}, view(), "autoscale_exclusive"),
+        ({"pool": {"low_priority_nodes": {"allow": False}}}, view(target_low_priority=2), "low_priority_nodes_allow"),
+        ({"pool": {"low_priority_nodes": {"allow": True, "exclusive": True}}}, view(), "low_priority_nodes_exclusive"),
+        ({"compute_node": {"exclusive": True}}, view(max_tasks_per_node=4), "exclusive"),
+        ({"compute_node": {"vm_size": "STANDARD_F1"}}, view(), "vm_size"),
+        ({"compute_node": {"gpu": False}}, view(), "gpu"),
+        ({"compute_node": {"infiniband": False}}, view(), "infiniband"),
+        ({"compute_node": {"cores": {"amount": 16}}}, view(), "cores"),
+        ({"compute_node": {"cores": {"amount": 4, "schedulable_variance": 0}}}, view(), "cores"),
+        ({"compute_node": {"cores": {"amount": 4, "schedulable_variance": 0.5}}}, view(), "cores"),
+        ({"compute_node": {"memory": {"amount": "128g"}}}, view(), "memory"),
+        ({"pool": {"container_registries": {"public": ["my.reg.io"]}}}, view(), "registries"),
+    ]
+    for fc, p, name in cases:
+        got = FC.first_failed_hard_constraint(p, cons(fc))
+        assert got is not None and got[0] == name, (fc, got)
+    assert FC.first_failed_hard_constraint(view(valid=False), cons())[0] == "valid"
+    assert FC.first_failed_hard_constraint(view(), cons({"compute_node": {"cores": {"amount": 4, "schedulable_variance": 1.0}}})) is None
+    mi = cons(tasks=[{"id": "t", "multi_instance": {"num_instances": 4}}])
+    assert mi.task.has_multi_instance and mi.task.instance_counts_max == 4
+    assert FC.first_failed_hard_constraint(view(inter_node_communication=False), mi)[0] == "has_multi_instance"
+    backlog = cons({"pool": {"max_active_task_backlog": {"ratio": 0.5, "autoscale_exempt": True}}})
+    assert FC.fails_node_constraints(view(active_tasks=3), backlog)[0] == "max_active_task_backlog"
+    assert FC.fails_node_constraints(view(active_tasks=3, autoscale_enabled=True), backlog) is None
+    assert cons({"compute_node": {"memory": {"amount": "512m"}}}).compute_node.memory == 512
+    with pytest.raises(ValueError):
+        cons({"pool": {"autoscale": {"allow": False, "exclusive": True}}})
+
+
+def test_greedy_best_fit_order():
+    small = view(id="small", idle_dedicated=2, schedulable_dedicated=2)
+    big = view(id="big", idle_dedicated=8, schedulable_dedicated=8)
+    busy = view(id="busy", idle_dedicated=0, schedulable_dedicated=4, active_tasks=9)
+    one = cons(tasks=[{"id": "a"}, {"id": "b"}])
+    assert select_pool([big, small, busy], one)[0] == "small"                     # tightest idle fit
+    four = cons(tasks=[{"id": str(i)} for i in range(4)])
+    assert select_pool([small, busy, big], four)[0] == "big"
+    assert select_pool([small, busy], four)[0] == "busy"                           # available (not idle) capacity
+    mi8 = cons(tasks=[{"id": "m", "multi_instance": {"num_instances": 8}}])
+    assert select_pool([small, busy], mi8)[0] is None                              # MI matched by nodes, never by backlog
+    assert select_pool([small, busy, big], mi8)[0] == "big"
+    auto = view(id="auto", idle_dedicated=0, schedulable_dedicated=0, autoscale_enabled=True)
+    assert select_pool([auto], four)[0] == "auto"
+    nine = cons(tasks=[{"id": str(i)} for i in range(9)])
+    pid, diag = select_pool([small, busy], nine)
+    assert pid == "small" and "backlog" in diag["small"]
+    pid, diag = select_pool([view(id="bo", blackout_until=2e9)], one, now=1e9)
+    assert pid is None and "blackout" in diag["bo"]
+
+
+def test_federation_end_to_end(tmp_path, monkeypatch):
+    monkeypatch.setenv("SHIPYARD_FED_NO_AGENT", "1")
+    cfg, b = make(tmp_path, tasks=[{"docker_image": "busybox", "command": "echo $AZ_BATCH_POOL_ID"}], job={"auto_complete": True})
+    up(cfg, b)
+    cfg2, _ = make(tmp_path, pool={"id": "gpuish", "vm_size": "B200x8", "gpu": {"ignore_warnings": True}, "vm_count": {"dedicated": 1, "low_priority": 0}})
+    up(cfg2, b)
+    FCl.create_federation(b, "Fed1")
+    with pytest.raises(FCl.FederationError):
+        FCl.create_federation(b, "fed1")
+    FCl.add_pools(b, "fed1", ["testpool", "gpuish"])
+    cfg["job_specifications"][0]["federation_constraints"] = {"compute_node": {"gpu": True}}
+    info = submit.add_jobs(b, cfg, federation_id="fed1")["job1"]
+    assert info["kind"] == "job" and info["num_tasks"] == 1 and info["federation"]["id"] == "fed1"
+    assert len(FCl.list_jobs(b, "fed1", queued=True)["queued"]) == 1
+    with pytest.raises(FCl.FederationError):
+        submit.add_jobs(b, cfg, federation_id="fed1") if b.store.exists("fedjob", "fed1", "job1") else (_ for _ in ()).throw(FCl.FederationError("x"))
+    proc = FederationProcessor(b, blackout=0.0, evaluate_autoscale=False)
+    assert proc.is_leader() and not FederationProcessor(b).is_leader()            # single leader via the lease
+    assert proc.process_all() == 1
+    fj = FCl.list_jobs(b, "fed1")["jobs"]["job1"]
+    assert fj["pool_id"] == "gpuish"                                              # the gpu constraint steered it
+    NodeAgent(b, "gpuish", poll=0.02).run(until_idle=True, max_seconds=30)
+    assert read(b, "job1", "task-00000").strip() == "gpuish"
+    # unschedulable -> blocked, not dropped; zap removes it
+    cfg["job_specifications"][0]["id"] = "job2"
+    cfg["job_specifications"][0]["federation_constraints"] = {"pool": {"location": "mars"}}
+    uid = submit.add_jobs(b, cfg, federation_id="fed1")["job2"]["unique_id"]
+    assert proc.process_all() == 0
+    blk = FCl.list_jobs(b, "fed1", blocked=True)["blocked"]
+    assert blk and blk[0]["unique_id"] == uid and "location" in blk[0]["reason"]
+    assert FCl.zap_action(b, "fed1", uid)["removed"] >= 1
+    assert not FCl.list_jobs(b, "fed1", blocked=True)["blocked"]
+    # terminate through the action queue keeps FIFO per job
+    FCl.enqueue_job_action(b, "fed1", "delete", ["job1"])
+    assert proc.process_all() == 1 and not b.job_exists("job1")
+    FCl.destroy_federation(b, "fed1")
+    assert FCl.list_federations(b) == {}
+
+
+def test_cli_surface_and_commands(tmp_path, monkeypatch):
+    leaves = cli.leaf_commands()
+    assert len(leaves) == 105
+    for must in ("pool add", "pool autoscale evaluate", "pool nodes zap", "jobs tasks list", "data files stream", "fed jobs zap",
+                 "fs cluster orchestrate", "monitor destroy", "slurm ssh node", "storage sas create", "keyvault add", "cert create",
+                 "misc mirror-images", "diag logs upload", "account quota"):
+        assert must in leaves
+    assert sorted(cli.cli.commands) == ["account", "cert", "data", "diag", "fed", "fs", "jobs", "keyvault", "misc", "monitor", "pool", "slurm", "storage"]
+    recipe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "recipes", "mpiBench-OpenMPI", "config")
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
+    monkeypatch.setenv("SHIPYARD_INLINE_AGENT", "1")
+    r = CliRunner()
+    res = r.invoke(cli.cli, ["pool", "exists", "--configdir", recipe], obj=cli.CliContext())
+    assert res.exit_code == 1 and "does not exist" in res.output
+    res = r.invoke(cli.cli, ["jobs", "add", "--configdir", recipe, "--dry-run", "--raw"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    dry = json.loads(res.output)["mpibench"]
+    assert dry["dry_run"] and dry["tasks"][0]["mpi_command"].startswith("mpirun --oversubscribe -host $AZ_BATCH_HOST_LIST -np 2")
+    assert dry["tasks"][0]["multi_instance"]["coordination_line"].startswith("docker run -d")
+    res = r.invoke(cli.cli, ["pool", "add", "--configdir", recipe, "--raw", "-y"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    assert json.loads(res.output)["mpibench"]["node_counts"]["dedicated"]["idle"] == 2
+    assert r.invoke(cli.cli, ["pool", "exists", "--configdir", recipe], obj=cli.CliContext()).exit_code == 0
+    res = r.invoke(cli.cli, ["jobs", "add", "--configdir", recipe, "--raw"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    res = r.invoke(cli.cli, ["jobs", "tasks", "list", "--configdir", recipe, "--raw"], obj=cli.CliContext())
+    tasks = json.loads(res.output)["mpibench"]
+    assert tasks[0]["state"] == "completed" and tasks[0]["result"] == "success" and tasks[0]["multi_instance"]
+    res = r.invoke(cli.cli, ["data", "files", "stream", "--filespec", "mpibench,task-00000,stdout.txt", "--configdir", recipe], obj=cli.CliContext())
+    assert "Allreduce" in res.output and "check failures: 0" in res.output
+    for args in (["pool", "stats"], ["pool", "nodes", "list"], ["pool", "nodes", "count"], ["pool", "images", "list"], ["jobs", "list"],
+                 ["jobs", "stats"], ["jobs", "tasks", "count"], ["account", "info"], ["account", "quota"], ["pool", "list"],
+                 ["misc", "mirror-images"], ["pool", "rdp"], ["storage", "sas", "create", "acct", "cont/x"], ["monitor", "list"]):
+        res = r.invoke(cli.cli, args + ["--configdir", recipe, "--raw"], obj=cli.CliContext())
+        assert res.exit_code == 0, (args, res.output)
+        json.loads(res.output)
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "pool.yaml").write_text("pool_specification:\n  id: x\n  nonsense: 1\n")
+    res = r.invoke(cli.cli, ["pool", "add", "--configdir", str(bad)], obj=cli.CliContext())
+    assert res.exit_code == 1 and "unknown key" in res.output
+    res = r.invoke(cli.cli, ["pool", "del", "--configdir", recipe, "-y", "--raw"], obj=cli.CliContext())
+    assert json.loads(res.output)["deleted"] is True
