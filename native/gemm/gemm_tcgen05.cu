@@ -1,0 +1,388 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a (hand-written PTX, no CUTLASS dependency).
+//
+//   C[M,N] (bf16) = A[M,K] (bf16, K contiguous) x B[N,K]^T (bf16, K contiguous)  (+ bias[N])
+//   optional fused epilogue: per-column sum / sum-of-squares of the bf16-rounded output
+//   accumulated into stats[2*N] (fp32) — the train-mode BatchNorm statistics of a 1x1
+//   convolution come for free with the GEMM instead of costing another pass over C.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of 128xBK (A) and BNxBK (B) tiles, 128B swizzle,
+//                           STAGES-deep mbarrier ring
+//   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//                           from shared-memory descriptors into a TMEM accumulator; tcgen05.commit frees
+//                           the smem stage / publishes the accumulator
+//   warp 2   TMEM allocator (2 x BN columns = two accumulator stages, so the epilogue of tile i overlaps
+//                           the main loop of tile i+1)
+//   warps 4-7 epilogue    : tcgen05.ld (32 lanes x 32 columns per warp-instruction) -> bias -> bf16 ->
+//                           128B-swizzled staging tile in smem -> TMA store; column statistics are read back
+//                           from the staging tile (conflict-free) and kept in registers across the CTA's
+//                           tiles of one N-block, flushed with 4 atomics per thread.
+// Out-of-bounds rows/columns are handled by TMA (zero fill on load, clipping on store).
+//
+// K10: the `peer` epilogue mode adds the tile into every rank's output over NVLink
+// (multimem.red through the switch = GEMM + all-reduce in one kernel) — see gemm_epilogue.cuh notes below.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // one 128-byte swizzle row of bf16
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiChunk = 64;    // columns per epilogue step (one 128B row of bf16)
+
+#define DEVI __device__ __forceinline__
+
+DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+DEVI void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVI void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVI void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+DEVI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DEVI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMA ---------------------------------------------------------------------------------------
+DEVI void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+DEVI void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+DEVI void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+DEVI void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> DEVI void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+DEVI void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- tcgen05 ------------------------------------------------------------------------------------
+template <int NCOLS> DEVI void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> DEVI void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+DEVI void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DEVI void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DEVI void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+DEVI void umma_commit(uint64_t* bar) {   // arrives on `bar` once every MMA issued so far has completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVI void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {   // 32 lanes x 32 consecutive fp32 columns
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+DEVI void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
+DEVI uint64_t make_kmajor_sw128_desc(const void* smem_tile) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);   // start address      bits [0,14)
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                                  // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                                  // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN> DEVI constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+DEVI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+DEVI uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+DEVI bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCBytes = BM * kEpiChunk * 2;          // 16 KB staging tile (x2 buffers)
+  static constexpr int kStages = ((200 * 1024 - 2 * kCBytes) / kStageBytes) > 6 ? 6 : ((200 * 1024 - 2 * kCBytes) / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // two accumulator stages (power of two: BN in {64,128,256})
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool kStats, bool kBias>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
+                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint8_t* smem_c = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C::kCBytes);
+  uint64_t* full_bar = bars;                        // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + C::kStages;          // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * C::kStages;      // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2; // [2]        epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_c); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t / num_m, m_blk = t % num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advancing K inside the 128B swizzle atom = +32 bytes on the start address (encoded >>4)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                     // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+    const int ew = warp - 4, et = threadIdx.x - 128;      // 0..127
+    const int row = ew * 32 + lane;                       // row of the 128-row tile owned by this thread
+    const bool issuer = et == 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    int buf = 0;
+    // statistics: thread (wcol = et % 32, rgrp = et / 32) owns word-column wcol (2 bf16 columns) of rows rgrp*32..+31
+    constexpr int kChunks = BN / kEpiChunk;
+    float st[kChunks][4];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) { st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f; }
+    int cur_n = -1;
+    auto flush_stats = [&](int n_blk) {
+      if (!kStats || n_blk < 0) return;
+      const int wcol = et & 31;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = n_blk * BN + c * kEpiChunk + 2 * wcol;
+        if (col < N) { atomicAdd(&stats[col], st[c][0]); atomicAdd(&stats[N + col], st[c][2]); }
+        if (col + 1 < N) { atomicAdd(&stats[col + 1], st[c][1]); atomicAdd(&stats[N + col + 1], st[c][3]); }
+        st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f;
+      }
+    };
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_blk = t / num_m, m_blk = t % num_m;
+      if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t v[2][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * kEpiChunk);
+        tmem_ld32(taddr, v[0]);
+        tmem_ld32(taddr + 32, v[1]);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {           // accumulator fully read: hand it back to the MMA warp early
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        // staging buffer `buf` must no longer be read by the TMA store issued two chunks ago
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, kEpiThreads);
+        uint8_t* cbuf = smem_c + buf * C::kCBytes;
+        const int n0 = n_blk * BN + c * kEpiChunk;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {     // 8 x 16-byte chunks = 64 bf16 columns of this thread's row
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
+          if (kBias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int col = n0 + q * 8 + i; f[i] += col < N ? __bfloat162float(bias[col]) : 0.f; }
+          }
+          uint4 w = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          // 128B swizzle: 16-byte chunk index XOR (row % 8) — matches the TMA store's SWIZZLE_128B and is bank-conflict free
+          *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m_blk * BM); tma_store_commit(); }
+        if (kStats) {
+          const int wcol = et & 31, rgrp = et >> 5;
+          const int q = wcol >> 2, wi = wcol & 3;
+          const int rows_valid = M - m_blk * BM;          // OOB rows hold zeros from the zero-filled A tile (no bias with stats)
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = rgrp * 32; r < rgrp * 32 + 32; ++r) {
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(cbuf + r * 128 + ((q ^ (r & 7)) << 4) + wi * 4);
+            const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
+            if (r < rows_valid) { s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); }
+          }
+          st[c][0] += s0; st[c][1] += s1; st[c][2] += q0; st[c][3] += q1;
+        }
+        buf ^= 1;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    flush_stats(cur_n);
+    if (issuer) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::atomic<unsigned long long> g_launches{0};
+thread_local char g_err[256];
+
+bool load_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+  g_encode = (EncodeTiledFn)fn;
+  return true;
+}
+
+// 2D bf16 tensor map: dims {inner, outer}, row pitch `ld` elements, box {box_inner, box_outer}, 128B swizzle
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+  return true;
+}
+
+template <int BN>
+int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, const void* bias, float* stats,
+           int max_ctas, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb, tc;
+  if (!make_map(&ta, A, K, M, lda, BK, BM) || !make_map(&tb, B, K, N, ldb, BK, BN) || !make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = tiles < sms ? tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  if (stats && bias) { snprintf(g_err, sizeof g_err, "stats and bias cannot be combined"); return 2; }
+  if (stats) return go(gemm_bf16_tn_kernel<BN, true, false>);
+  if (bias) return go(gemm_bf16_tn_kernel<BN, false, true>);
+  return go(gemm_bf16_tn_kernel<BN, false, false>);
+}
+
+}  // namespace
+
+extern "C" const char* sy_gemm_last_error() { return g_err; }
+extern "C" unsigned long long sy_gemm_launch_count() { return g_launches.load(); }
+
+// C[M,N] = A[M,K] * B[N,K]^T (+bias) ; bf16 in/out, fp32 accumulate in TMEM.  lda/ldb/ldc in elements.
+// stats (optional): float[2*N], caller-zeroed: per-column sum and sum of squares of the bf16 output.
+// Requirements: pointers 16B aligned, lda/ldb/ldc multiples of 8, K >= 1.
+extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                               const void* bias, float* stats, int block_n, int max_ctas, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda | ldb | ldc) & 7 || ((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) {
+    snprintf(g_err, sizeof g_err, "alignment: pointers must be 16B aligned and leading dimensions multiples of 8");
+    return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_n <= 0) block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  switch (block_n) {
+    case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+    case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+    case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
