@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops import fused as _fused
+from ..ops import gemm as _gemm
 
 
 class ConvBN(nn.Module):
@@ -33,14 +34,25 @@ class ConvBN(nn.Module):
         self.register_buffer("running_mean", torch.zeros(cout, dtype=torch.float32))
         self.register_buffer("running_var", torch.ones(cout, dtype=torch.float32))
         self.momentum, self.eps = 0.1, 1e-5
+        import os as _os
+        self.use_tc_gemm = not _os.environ.get("SHIPYARD_NO_TC_GEMM")
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        y = F.conv2d(x, self.weight, None, self.stride, self.k // 2)
-        if y.is_cuda and self.training and y.dtype == torch.bfloat16:
+        fast = x.is_cuda and self.training and x.dtype == torch.bfloat16
+        stats = None
+        if fast and self.k == 1 and self.stride == 1 and self.use_tc_gemm and self.cin % 8 == 0:
+            # 1x1 convolution == GEMM over NHWC pixels: tcgen05 kernel, BN statistics from its epilogue
+            y, stats = _gemm.conv1x1_nhwc(x, self.weight, want_stats=self.cin >= 256)   # short-K layers: the separate stats pass is as cheap
+        elif self.k == 7 and x.shape[1] == 16:
+            # space-to-depth stem: the 7x7/s2/p3 conv as a dense 4x4/s1 conv over the 16-channel s2d input
+            y = F.conv2d(x, _fused.stem_weight_s2d(self.weight).contiguous(memory_format=torch.channels_last))
+        else:
+            y = F.conv2d(x, self.weight, None, self.stride, self.k // 2)
+        if fast:
             # one fused stats + apply(+residual)(+ReLU) pair instead of BN / add / ReLU kernels;
             # no eager fallback on GPU: a missing extension must fail loudly
             return _fused.fused_bn_act(y, self.gamma, self.beta, residual, self.running_mean, self.running_var,
-                                       self.relu, self.eps, self.momentum)
+                                       self.relu, self.eps, self.momentum, stats=stats)
         y = F.batch_norm(y.float(), self.running_mean, self.running_var, self.gamma.float(), self.beta.float(),
                          self.training, self.momentum, self.eps).to(y.dtype)
         if residual is not None:
@@ -80,12 +92,18 @@ class ResNet(nn.Module):
         nn.init.kaiming_uniform_(self.fc_weight, a=math.sqrt(5))
         bound = 1 / math.sqrt(cin)
         nn.init.uniform_(self.fc_bias, -bound, bound)
+        import os as _os
+        self.use_tc_gemm = not _os.environ.get("SHIPYARD_NO_TC_GEMM")
+        self.s2d_stem = True      # CUDA trainers feed the stem a space-to-depth input (see ops.fused.u8_to_s2d_norm)
 
     def forward(self, x):
         x = self.stem(x)
-        x = F.max_pool2d(x, 3, 2, 1)
+        fast = x.is_cuda and x.dtype == torch.bfloat16 and self.training
+        x = _fused.maxpool3x3s2(x) if (fast and x.shape[1] % 8 == 0) else F.max_pool2d(x, 3, 2, 1)
         x = self.blocks(x)
         x = x.mean(dim=(2, 3))
+        if fast and self.use_tc_gemm:
+            return _gemm.linear(x, self.fc_weight, self.fc_bias)          # FC on the tcgen05 kernel (bias fused)
         return F.linear(x, self.fc_weight, self.fc_bias)
 
 
@@ -96,6 +114,12 @@ def resnet50(num_classes: int = 1000) -> ResNet:
 def resnet_tiny(num_classes: int = 10) -> ResNet:
     """Two-block variant for smoke tests."""
     return ResNet((1, 1, 1, 1), num_classes, width=16)
+
+
+def set_tc_gemm(m: nn.Module, flag: bool) -> None:
+    for mod in m.modules():
+        if hasattr(mod, "use_tc_gemm"):
+            mod.use_tc_gemm = flag
 
 
 def param_count(m: nn.Module) -> int:

@@ -64,7 +64,10 @@ def _bind_bn(lib):
                                   C.c_int, vp]
     lib.sy_ops_bn_apply_only.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float,
                                          C.c_float, C.c_int, vp]
-    lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, vp]
+    lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp]
+    lib.sy_ops_maxpool3x3s2_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.sy_ops_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.sy_ops_u8_to_s2d_norm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
     lib._bn_bound = True
 
 
@@ -108,6 +111,7 @@ class _FusedBNAct(torch.autograd.Function):
             raise RuntimeError(f"fused BN forward failed (rc={rc}, C={c})")
         ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
         ctx.relu, ctx.has_res = bool(relu), residual is not None
+        ctx.beta_ref = beta if isinstance(beta, torch.nn.Parameter) else None
         return out
 
     @staticmethod
@@ -120,14 +124,24 @@ class _FusedBNAct(torch.autograd.Function):
             dout = dout.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
-        dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
+        # write dgamma/dbeta straight into the parameters' .grad views when they exist (flat gradient buffer):
+        # saves two AccumulateGrad add-kernels per layer
+        beta = ctx.beta_ref
+        direct = (isinstance(gamma, torch.nn.Parameter) and gamma.grad is not None and beta is not None and beta.grad is not None
+                  and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        if direct:
+            dgamma, dbeta = gamma.grad, beta.grad
+        else:
+            dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
+            dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
         ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
         rc = lib.sy_ops_bn_bwd(_ptr(dout), _ptr(out), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
                                _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
-                               _stream(x))
+                               1 if direct else 0, _stream(x))
         if rc != 0:
             raise RuntimeError(f"fused BN backward failed (rc={rc})")
+        if direct:
+            return dx, None, None, dres, None, None, None, None, None, None
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
@@ -146,3 +160,70 @@ def bn_act_reference(x, gamma, beta, residual=None, relu=True, eps=1e-5):
     if residual is not None:
         y = y + residual.float()
     return torch.relu(y) if relu else y
+
+
+# ---------------------------------------------------------------------------
+# max-pool 3x3/s2/p1 (NHWC bf16) with saved arg-max codes
+# ---------------------------------------------------------------------------
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = load(); _bind_bn(lib)
+        assert x.is_cuda and x.dtype == torch.bfloat16 and _is_nhwc(x) and x.shape[1] % 8 == 0
+        n, c, h, w = x.shape
+        oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)
+        idx = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+        rc = lib.sy_ops_maxpool3x3s2_fwd(_ptr(x), _ptr(y), _ptr(idx), n, h, w, c, _stream(x))
+        if rc != 0:
+            raise RuntimeError(f"maxpool forward failed ({rc})")
+        ctx.save_for_backward(idx)
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = load()
+        (idx,) = ctx.saved_tensors
+        n, c, h, w = ctx.shape
+        if not _is_nhwc(dy):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)
+        rc = lib.sy_ops_maxpool3x3s2_bwd(_ptr(dy), _ptr(idx), _ptr(dx), n, h, w, c, _stream(dy))
+        if rc != 0:
+            raise RuntimeError(f"maxpool backward failed ({rc})")
+        return dx
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    return _MaxPool3x3s2.apply(x)
+
+
+def u8_to_s2d_norm(src_u8: torch.Tensor, dst: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 NHWC [N,H,W,3] -> normalised, zero-bordered space-to-depth bf16 [N,H/2+3,W/2+3,16] (stem input)."""
+    lib = load(); _bind_bn(lib)
+    n, h, w, c = src_u8.shape
+    assert c == 3 and src_u8.dtype == torch.uint8 and dst.dtype == torch.bfloat16 and dst.is_contiguous()
+    assert tuple(dst.shape) == (n, h // 2 + 3, w // 2 + 3, 16), dst.shape
+    m = (C.c_float * 3)(*mean); s = (C.c_float * 3)(*std)
+    rc = lib.sy_ops_u8_to_s2d_norm(_ptr(src_u8), _ptr(dst), n, h, w, m, s, _stream(dst))
+    if rc != 0:
+        raise RuntimeError(f"u8_to_s2d_norm failed ({rc})")
+    return dst
+
+
+def s2d_reference(x_nchw: torch.Tensor) -> torch.Tensor:
+    """PyTorch reference of the stem input transform: [N,3,H,W] float -> [N,16,H/2+3,W/2+3] (zero border/channels)."""
+    n, c, h, w = x_nchw.shape
+    t = x_nchw.view(n, c, h // 2, 2, w // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 12, h // 2, w // 2)   # (p,q,c)
+    out = x_nchw.new_zeros((n, 16, h // 2 + 3, w // 2 + 3))
+    out[:, :12, 2:2 + h // 2, 2:2 + w // 2] = t
+    return out
+
+
+def stem_weight_s2d(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,3,7,7] stride-2 pad-3 kernel -> equivalent [Cout,16,4,4] stride-1 kernel over the s2d input."""
+    co = w.shape[0]
+    w8 = torch.nn.functional.pad(w, (1, 0, 1, 0))                       # ky' = ky + 1 (zero row/col first)
+    w2 = w8.reshape(co, 3, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(co, 12, 4, 4)   # channel = (p*2+q)*3 + c
+    return torch.nn.functional.pad(w2, (0, 0, 0, 0, 0, 4))

@@ -106,8 +106,13 @@ class FusedDataParallelTrainer:
         n, c, h, w = batch_shape
         self.batch_shape = batch_shape
         act_dtype = torch.bfloat16 if self.is_cuda else torch.float32
-        # NHWC storage viewed as NCHW (= torch channels_last)
-        self._x_store = torch.zeros((n, h, w, c), dtype=act_dtype, device=self.dev)
+        # NHWC storage viewed as NCHW (= torch channels_last).  On CUDA the stem takes a zero-bordered
+        # space-to-depth input [N, H/2+3, W/2+3, 16] so its 7x7/s2 conv runs as a dense 4x4 conv.
+        self.s2d = bool(self.is_cuda and getattr(model, "s2d_stem", False) and c == 3 and h % 2 == 0 and w % 2 == 0)
+        if self.s2d:
+            self._x_store = torch.zeros((n, h // 2 + 3, w // 2 + 3, 16), dtype=act_dtype, device=self.dev)
+        else:
+            self._x_store = torch.zeros((n, h, w, c), dtype=act_dtype, device=self.dev)
         self.static_x = self._x_store.permute(0, 3, 1, 2) if channels_last else self._x_store.permute(0, 3, 1, 2).contiguous()
         self.static_y = torch.zeros((n,), dtype=torch.int64, device=self.dev)
         self.static_loss = torch.zeros((), dtype=torch.float32, device=self.dev)
@@ -161,6 +166,16 @@ class FusedDataParallelTrainer:
             self._step_body()
         self.steps_done += 1
         return self.static_loss
+
+    def load_images_u8(self, images_u8: torch.Tensor, labels: torch.Tensor) -> None:
+        """Fill the static step inputs from a device uint8 NHWC batch (used by benches / tests)."""
+        if self.s2d:
+            _fused.u8_to_s2d_norm(images_u8, self._x_store)
+        elif self.is_cuda:
+            _fused.u8_to_bf16_norm(images_u8, self._x_store)
+        else:
+            self._x_store.copy_(images_u8.to(torch.float32) / 255.0)
+        self.static_y.copy_(labels)
 
     def set_lr(self, lr: float) -> None:
         self.hyper[0:1].fill_(lr)
@@ -219,7 +234,10 @@ class InputStager:
         if tr.is_cuda:
             cur = torch.cuda.current_stream(tr.dev)
             cur.wait_event(self.copied[slot])
-            _fused.u8_to_bf16_norm(self.dev_x[slot], tr._x_store)
+            if tr.s2d:
+                _fused.u8_to_s2d_norm(self.dev_x[slot], tr._x_store)
+            else:
+                _fused.u8_to_bf16_norm(self.dev_x[slot], tr._x_store)
             tr.static_y.copy_(self.dev_y[slot], non_blocking=True)
             self.consumed[slot].record(cur)
             tr.step()

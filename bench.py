@@ -153,8 +153,8 @@ def run_shipyard(args, rank, world, local):
     tr = FusedDataParallelTrainer(model, comm, (B, 3, 224, 224), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4,
                                   use_graph=not args.no_graph)
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
-    tr._x_store.copy_(torch.randn(tr._x_store.shape, generator=g).to(torch.bfloat16))
-    tr.static_y.copy_(torch.randint(0, 1000, (B,), generator=g))
+    tr.load_images_u8(torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=g).to(dev),
+                      torch.randint(0, 1000, (B,), generator=g).to(dev))
     tr.prepare(warmup=max(3, args.warmup))
     # --- device-timed captured step ------------------------------------------
     for _ in range(args.warmup):

@@ -46,6 +46,7 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 4096);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
   c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);
+  c->nvls_min_world = (long)env_sz("SHIPYARD_COLL_NVLS_MIN_WORLD", 4);
   if (heap_bytes == 0) heap_bytes = env_sz("SHIPYARD_COLL_HEAP", transport == SY_TRANSPORT_STUB ? (256ul << 20) : (1ul << 30));
   size_t min_heap = SY_USER_OFF + (16ul << 20);
   if (heap_bytes < min_heap) heap_bytes = min_heap;
@@ -117,6 +118,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "nvls_min_bytes")) c->nvls_min_bytes = v;
   else if (!strcmp(k, "timeout_ms")) c->timeout_ms = v;
   else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
+  else if (!strcmp(k, "nvls_min_world")) c->nvls_min_world = v;
   else return SY_ERR_ARG;
   return SY_OK;
 }
@@ -128,6 +130,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "nvls_min_bytes")) return c->nvls_min_bytes;
   if (!strcmp(k, "timeout_ms")) return c->timeout_ms;
   if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
+  if (!strcmp(k, "nvls_min_world")) return c->nvls_min_world;
   return -1;
 }
 
@@ -168,7 +171,7 @@ extern "C" int sy_allreduce(sy_comm* c, const void* in, void* out, size_t count,
   if (algo == SY_ALGO_AUTO) {
     if (bytes <= (size_t)c->ll_max_bytes) algo = SY_ALGO_LL;
     else if (bytes <= (size_t)c->oneshot_max_bytes) algo = SY_ALGO_ONESHOT;
-    else algo = (c->has_mc && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out)) ? SY_ALGO_TWOSHOT_NVLS : SY_ALGO_TWOSHOT_P2P;
+    else algo = (c->has_mc && c->world >= c->nvls_min_world && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out)) ? SY_ALGO_TWOSHOT_NVLS : SY_ALGO_TWOSHOT_P2P;
   }
   if (algo == SY_ALGO_TWOSHOT_NVLS && !(c->has_mc && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out))) {
     sy_set_error("allreduce: NVLS path unavailable for this call"); return SY_ERR_UNSUPPORTED;
@@ -221,7 +224,7 @@ extern "C" int sy_reduce_scatter(sy_comm* c, const void* in, void* out, size_t c
     CUDA_TRY(cudaMemcpyAsync(stage_half(c, 0), in, total, cudaMemcpyDeviceToDevice, s));
     in_off = stage_half_off(c, 0);
   }
-  bool nvls = c->has_mc && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out) && total >= (size_t)c->nvls_min_bytes;
+  bool nvls = c->has_mc && c->world >= c->nvls_min_world && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out) && total >= (size_t)c->nvls_min_bytes;
   int rc = k_reduce_scatter(c, in_off, out, count, dt_in, dt_out, scale, op, nvls, stream);
   if (rc == SY_ERR_UNSUPPORTED) {
     // unaligned shard: all-reduce the whole thing into staging, then copy my shard out
@@ -251,7 +254,7 @@ extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
-  rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
+  rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
   if (rc) return rc;
   if (t.staged) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes * c->world, cudaMemcpyDeviceToDevice, s));
   return SY_OK;
@@ -265,7 +268,7 @@ extern "C" int sy_broadcast(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   OutStage t; int rc = out_target(c, out, bytes, &t); if (rc) return rc;
-  rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && c->nvls_copy && bytes >= (size_t)c->nvls_min_bytes, stream);
+  rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)c->nvls_min_bytes, stream);
   if (rc) return rc;
   if (t.staged) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes, cudaMemcpyDeviceToDevice, s));
   return SY_OK;

@@ -59,6 +59,7 @@ struct sy_comm {
   long max_blocks = 128, threads = 512;
   long ll_max_bytes = 4096, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;
   long timeout_ms = 20000;
+  long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
   long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
   // VMM handles (opaque to other TUs)
   void* impl = nullptr;

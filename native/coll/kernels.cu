@@ -1304,7 +1304,7 @@ int k_fused_sgd(sy_comm* c, size_t g_off, int dt_grad, size_t p_off, int dt_para
   if (count % 8) { sy_set_error("fused_sgd: count must be a multiple of 8"); return SY_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   CommDev d = devof(c);
-  const bool nvls = c->has_mc && c->world > 1 && !getenv("SHIPYARD_COLL_NO_NVLS");
+  const bool nvls = c->has_mc && c->world >= c->nvls_min_world && !getenv("SHIPYARD_COLL_NO_NVLS");
   int g = grid_for(c, count / 8 / (size_t)c->world + 1, (int)c->threads);
   // zeroing the whole local gradient buffer wants a wide grid too
   if (zero_grads) { int gz = grid_for(c, count * sy_dtype_size(dt_grad) / 16 + 1, (int)c->threads, 4); if (gz > g) g = gz; }
@@ -1331,7 +1331,7 @@ int k_allreduce_fp8(sy_comm* c, size_t in_off, int dt_in, void* out_q, void* out
   if (count % 128) { sy_set_error("allreduce_fp8: count must be a multiple of 128"); return SY_ERR_ARG; }
   char* base = c->dev.heap[c->rank];
   size_t q_off = (char*)out_q - base, s_off = (char*)out_scales - base;
-  const bool nvls = c->has_mc && c->world > 1 && !getenv("SHIPYARD_COLL_NO_NVLS");
+  const bool nvls = c->has_mc && c->world >= c->nvls_min_world && !getenv("SHIPYARD_COLL_NO_NVLS");
   int g = grid_for(c, count / 32 / (size_t)c->world + 1, 256);
   CommDev d = devof(c);
   cudaStream_t s = (cudaStream_t)stream;

@@ -215,7 +215,7 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
                const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ gamma,
                const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
                __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dgamma,
-               __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu) {
+               __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu, int accum) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float mu[8], is[8], k0[8], k1[8], k2[8];
   const float invM = 1.f / (float)M;
@@ -227,7 +227,11 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
     k0[i] = g * is[i];                 // dz coefficient
     k1[i] = -g * is[i] * s1 * invM;    // constant term
     k2[i] = -g * is[i] * s2 * invM;    // xhat coefficient
-    if (blockIdx.x == 0 && rl == 0) { dgamma[c] = __float2bfloat16_rn(s2); dbeta[c] = __float2bfloat16_rn(s1); }
+    if (blockIdx.x == 0 && rl == 0) {
+      // accum: add straight into the parameter's .grad view (no separate AccumulateGrad kernel)
+      dgamma[c] = __float2bfloat16_rn(s2 + (accum ? __bfloat162float(dgamma[c]) : 0.f));
+      dbeta[c] = __float2bfloat16_rn(s1 + (accum ? __bfloat162float(dbeta[c]) : 0.f));
+    }
   }
   const long stride = (long)gridDim.x * rpi;
   for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
@@ -293,7 +297,7 @@ extern "C" int sy_ops_bn_apply_only(const void* x, const void* res, void* out, c
 
 extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
                              const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
-                             int relu, void* stream) {
+                             int relu, int accum, void* stream) {
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
@@ -303,7 +307,141 @@ extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, c
   COUNT_LAUNCH();
   k_bn_bwd_apply<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
                                    (const __nv_bfloat16*)gamma, ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
-                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu);
+                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+
+// ===========================================================================
+// 3x3 / stride 2 / pad 1 max-pool on NHWC bf16 with saved arg-max codes.
+// fwd: one thread per (output pixel, 8-channel group): 9 x 16B loads, 16B store + 8 index bytes.
+// bwd: one thread per (input pixel, 8-channel group): gathers from the <= 4 windows that cover
+//      it (no atomics, every dx element written exactly once).
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+k_maxpool_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+              int N, int H, int W, int C, int OH, int OW) {
+  const int G = C / 8;
+  const long total = (long)N * OH * OW * G;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G); long p = t / G;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH); const int n = (int)(p / OH);
+    float best[8]; uint32_t code[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; code[i] = 0; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        float f[8]; unpack8(ldg16(x + (((long)n * H + iy) * W + ix) * C + g * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (f[i] > best[i]) { best[i] = f[i]; code[i] = ky * 3 + kx; }
+      }
+    }
+    const long o = (((long)n * OH + oy) * OW + ox) * C + g * 8;
+    stg16(y + o, pack8(best));
+    uint2 c2 = make_uint2(code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24), code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24));
+    *reinterpret_cast<uint2*>(idx + o) = c2;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
+              int N, int H, int W, int C, int OH, int OW) {
+  const int G = C / 8;
+  const long total = (long)N * H * W * G;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G); long p = t / G;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H); const int n = (int)(p / H);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int oy0 = iy / 2, oy1 = (iy + 1) / 2;     // windows with 2*oy-1 <= iy <= 2*oy+1
+    const int ox0 = ix / 2, ox1 = (ix + 1) / 2;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      if (oy >= OH) continue;
+      const int ky = iy - (2 * oy - 1);
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        if (ox >= OW) continue;
+        const int kx = ix - (2 * ox - 1);
+        const uint32_t want = (uint32_t)(ky * 3 + kx);
+        const long o = (((long)n * OH + oy) * OW + ox) * C + g * 8;
+        const uint2 c2 = *reinterpret_cast<const uint2*>(idx + o);
+        float d[8]; unpack8(ldg16(dy + o), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t c = ((i < 4 ? c2.x : c2.y) >> (8 * (i & 3))) & 0xff;
+          if (c == want) acc[i] += d[i];
+        }
+      }
+    }
+    stg16(dx + (((long)n * H + iy) * W + ix) * C + g * 8, pack8(acc));
+  }
+}
+
+extern "C" int sy_ops_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
+  if (C % 8) return -1;
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  long total = (long)N * OH * OW * (C / 8);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_maxpool_fwd<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, N, H, W, C, OH, OW);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+extern "C" int sy_ops_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
+  if (C % 8) return -1;
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  long total = (long)N * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_maxpool_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, OH, OW);
+  COUNT_LAUNCH();
+  RET_LAST();
+}
+
+// ===========================================================================
+// Stem input transform: uint8 NHWC [N,H,W,3] -> normalised bf16 space-to-depth [N, H/2+3, W/2+3, 16]
+// with a zero border (2 before, 1 after) so that the 7x7/stride-2/pad-3 stem convolution becomes a
+// dense 4x4/stride-1/pad-0 convolution over 16 channels (12 used): channel (p*2+q)*3+c of cell (Y,X)
+// holds pixel (2(Y-2)+p, 2(X-2)+q, c).  One thread writes one 32-byte cell.
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+k_u8_to_s2d(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+            float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int OH = H / 2 + 3, OW = W / 2 + 3;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {s0, s1, s2};
+  const long total = (long)N * OH * OW;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(t % OW); long p = t / OW;
+    const int Y = (int)(p % OH); const int n = (int)(p / OH);
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    const int y0 = 2 * (Y - 2), x0 = 2 * (X - 2);
+    if (Y >= 2 && X >= 2 && y0 + 1 < H && x0 + 1 < W) {
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const uint8_t* src = in + (((long)n * H + y0 + pp) * W + x0) * 3;   // 6 consecutive bytes: (q=0,c=0..2),(q=1,c=0..2)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) f[pp * 6 + j] = ((float)src[j] * (1.f / 255.f) - mean[j % 3]) * istd[j % 3];
+      }
+    }
+    stg16(out + t * 16, pack8(f));
+    stg16(out + t * 16 + 8, pack8(f + 8));
+  }
+}
+
+extern "C" int sy_ops_u8_to_s2d_norm(const void* in, void* out, int N, int H, int W, const float* mean3, const float* std3, void* stream) {
+  if ((H | W) & 1) return -1;
+  long total = (long)N * (H / 2 + 3) * (W / 2 + 3);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_u8_to_s2d<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, (__nv_bfloat16*)out, N, H, W, mean3[0], mean3[1], mean3[2],
+                                                       1.f / std3[0], 1.f / std3[1], 1.f / std3[2]);
   COUNT_LAUNCH();
   RET_LAST();
 }

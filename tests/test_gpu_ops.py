@@ -46,6 +46,36 @@ def test_fused_bn_fwd_bwd(c, hw, relu, res):
     torch.testing.assert_close(rv, 0.9 + 0.1 * xf.var(dim=(0, 2, 3), unbiased=True), atol=2e-2, rtol=2e-2)
 
 
+def test_maxpool_matches_torch():
+    from batch_shipyard_b200.ops import fused
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(3, 64, 23, 30, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = fused.maxpool3x3s2(x)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y.float(), yr)
+    g = torch.randn_like(y)
+    y.backward(g); yr.backward(g.float())
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=2e-2, rtol=2e-2)
+
+
+def test_s2d_stem_equivalence():
+    from batch_shipyard_b200.ops import fused
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (2, 32, 48, 3), dtype=torch.uint8, device="cuda")
+    s2d = torch.empty(2, 19, 27, 16, dtype=torch.bfloat16, device="cuda")
+    fused.u8_to_s2d_norm(img, s2d)
+    mean = torch.tensor(fused.IMAGENET_MEAN, device="cuda"); std = torch.tensor(fused.IMAGENET_STD, device="cuda")
+    xn = ((img.float() / 255.0 - mean) / std).permute(0, 3, 1, 2)
+    torch.testing.assert_close(s2d.permute(0, 3, 1, 2).float(), fused.s2d_reference(xn), atol=2e-2, rtol=1e-2)
+    w = torch.randn(8, 3, 7, 7, device="cuda") * 0.1
+    ref = F.conv2d(xn, w, stride=2, padding=3)
+    out = F.conv2d(s2d.permute(0, 3, 1, 2).float(), fused.stem_weight_s2d(w))
+    torch.testing.assert_close(out, ref, atol=5e-2, rtol=2e-2)
+
+
 def test_trainer_matches_reference_sgd():
     """Two steps of the fused trainer (tiny ResNet) track a plain fp32 PyTorch SGD run."""
     import copy
@@ -60,10 +90,13 @@ def test_trainer_matches_reference_sgd():
     tr = FusedDataParallelTrainer(model, comm, (16, 3, 64, 64), 10, lr=0.05, momentum=0.9, weight_decay=1e-4, use_graph=False)
     x = torch.randn(16, 3, 64, 64, device="cuda")
     y = torch.randint(0, 10, (16,), device="cuda")
-    tr._x_store.copy_(x.permute(0, 2, 3, 1).to(torch.bfloat16)); tr.static_y.copy_(y)
+    img = torch.randint(0, 256, (16, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    tr.load_images_u8(img, y)
     opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     ref.train()
-    xr = x.to(torch.bfloat16).float()
+    from batch_shipyard_b200.ops import fused
+    mean = torch.tensor(fused.IMAGENET_MEAN, device="cuda"); std = torch.tensor(fused.IMAGENET_STD, device="cuda")
+    xr = ((img.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
     for _ in range(2):
         loss = float(tr.step())
         opt.zero_grad(); lr = F.cross_entropy(ref(xr), y); lr.backward(); opt.step()
