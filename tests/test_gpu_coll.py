@@ -23,3 +23,21 @@ def test_multi_gpu_collectives(transport):
     world = min(_ngpu(), 8)
     ok, outs = run_ranks("_coll_worker.py", world, extra=["--transport", transport], gpu=True, timeout=600)
     assert ok, "\n".join(o[-3000:] for o in outs)
+
+
+@pytest.mark.multigpu
+def test_nccl_preload_shim_under_torch_distributed():
+    """LD_PRELOAD the shim under a torchrun NCCL job: results stay correct and the collectives ran on our kernels."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "batch_shipyard_b200", "_native", "libshipyard_preload.so")
+    assert os.path.exists(shim), "libshipyard_preload.so is not built"
+    world = min(_ngpu(), 8)
+    env = dict(os.environ, LD_PRELOAD=shim, SHIPYARD_PRELOAD_STATS="1", SHIPYARD_COLL_SESSION="preloadtest")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "tests", "_preload_worker.py")], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert p.stdout.count("ok=True") == world
