@@ -34,6 +34,8 @@ def load() -> C.CDLL:
         lib.sy_gemm_launch_count.restype = C.c_ulonglong
         lib.sy_gemm_bf16_tn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_tn_allreduce.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -141,3 +143,27 @@ class _Conv1x1NHWC(torch.autograd.Function):
 
 def conv1x1_nhwc(x: torch.Tensor, w: torch.Tensor, want_stats: bool = False):
     return _Conv1x1NHWC.apply(x, w, want_stats)
+
+
+def gemm_tn_allreduce(comm, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Tensor, block_n: int = 0) -> torch.Tensor:
+    """K10: ``out_sym += a @ b.T`` summed over all ranks, ONE kernel (tcgen05 GEMM whose epilogue issues
+    multimem.red into the NVLS multicast mapping of ``out_sym``; ends with a cross-GPU flag barrier).
+    ``out_sym``: fp32 [M, N] from ``comm.alloc`` and zero on every rank before the call; a/b: this rank's K-shard."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out_sym.dtype == torch.float32
+    m, k = a.shape
+    n = b.shape[0]
+    assert tuple(out_sym.shape) == (m, n) and out_sym.is_contiguous() and _rows_ok(a) and _rows_ok(b)
+    lib = load()
+    from . import coll as _coll
+    clib = _coll.load()
+    clib.sy_comm_device_view.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    clib.sy_comm_device_view.restype = C.c_size_t
+    size = clib.sy_comm_device_view(comm._h, None, 0)
+    view = (C.c_uint8 * size)()
+    clib.sy_comm_device_view(comm._h, view, size)
+    rc = lib.sy_gemm_bf16_tn_allreduce(view, size, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), comm.heap_offset(out_sym), m, n, k,
+                                       a.stride(0), b.stride(0), out_sym.stride(0), block_n,
+                                       C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_gemm_bf16_tn_allreduce failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out_sym

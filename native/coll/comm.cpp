@@ -92,6 +92,14 @@ extern "C" int sy_comm_has_multicast(const sy_comm* c) { return c->has_mc ? 1 : 
 extern "C" int sy_comm_status(sy_comm* c) { return c->status_host ? (int)*c->status_host : 0; }
 extern "C" uint64_t sy_comm_launch_count(const sy_comm* c) { return c->launches; }
 extern "C" size_t sy_heap_bytes(const sy_comm* c) { return c->heap_bytes; }
+// device-side view (heap pointers, multicast VA, epoch counters) for kernels living in other libraries
+extern "C" size_t sy_comm_device_view(sy_comm* c, void* out, size_t cap) {
+  CommDev d = c->dev;
+  d.timeout_ns = (unsigned long long)c->timeout_ms * 1000000ull;
+  if (out && cap >= sizeof d) memcpy(out, &d, sizeof d);
+  return sizeof d;
+}
+extern "C" void sy_comm_count_launch(sy_comm* c) { c->launches++; }
 extern "C" void* sy_heap_base(sy_comm* c, int peer) { return peer >= 0 && peer < c->world ? c->dev.heap[peer] : nullptr; }
 extern "C" void* sy_mc_base(sy_comm* c) { return c->dev.mc; }
 extern "C" int sy_is_symmetric(sy_comm* c, const void* p) { size_t o; return sym_off(c, p, &o) ? 1 : 0; }

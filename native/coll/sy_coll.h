@@ -70,6 +70,9 @@ void* sy_heap_base(sy_comm* c, int peer);           // local VA of peer's heap
 void* sy_mc_base(sy_comm* c);                       // multicast VA or NULL
 size_t sy_heap_bytes(const sy_comm* c);
 int sy_is_symmetric(sy_comm* c, const void* p);
+// copy of the device-side communicator view (struct CommDev) for fused compute+collective kernels
+size_t sy_comm_device_view(sy_comm* c, void* out, size_t cap);
+void sy_comm_count_launch(sy_comm* c);
 
 // ---- tuning ---------------------------------------------------------------
 // knob names: "max_blocks", "threads", "ll_max_bytes", "oneshot_max_bytes",

@@ -26,7 +26,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
+#include "device_sync.cuh"   // cross-GPU block barrier shared with libshipyard_coll
 
 namespace {
 
@@ -37,7 +39,9 @@ constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kEpiChunk = 64;    // columns per epilogue step (one 128B row of bf16)
 
+#ifndef DEVI
 #define DEVI __device__ __forceinline__
+#endif
 
 DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -305,6 +309,139 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
 }
 
+
+// ===================================================================================================
+// K10: GEMM + all-reduce in ONE kernel.  Every rank multiplies its K-shard (C_r = A_r x B_r^T); the
+// epilogue adds each fp32 tile straight into the multicast mapping of the output with multimem.red, so the
+// NVSwitch applies the addition in every GPU's copy while the next tile's MMAs are already running —
+// there is no partial-C round trip through HBM and no separate collective launch.  A cross-GPU flag barrier
+// at the end of the kernel makes all contributions visible before any rank's kernel completes.
+// `out` must be zero before the first contribution (caller zeroes it and synchronises the ranks).
+// ===================================================================================================
+DEVI void mc_red_add_v4_f32(void* mc, float a, float b, float c, float d) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+DEVI void p2p_red_add_f32(float* p, float v) { asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_allreduce_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              const __grid_constant__ CommDev comm, size_t out_off, int ldc, int M, int N, int K) {
+  using C = Cfg<BN>;
+  constexpr int kRowPitch = 32 * 4 + 16;          // 32 fp32 columns + 16 B pad: conflict-free 16 B accesses
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint8_t* smem_c = smem + C::kStages * C::kStageBytes;      // 32 KB staging (BM * kRowPitch = 18 KB used)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C::kCBytes);
+  uint64_t* full_bar = bars; uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages; uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
+  const int num_tiles = num_m * num_n;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t / num_m, m_blk = t % num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4, et = threadIdx.x - 128;
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    char* out_mc = comm.mc ? comm.mc + out_off : nullptr;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_blk = t / num_m, m_blk = t % num_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      constexpr int kChunks32 = BN / 32;
+#pragma unroll 1
+      for (int c = 0; c < kChunks32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        tmem_ld_wait();
+        if (c == kChunks32 - 1) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+        named_bar_sync(1, kEpiThreads);                        // previous chunk fully drained from the staging tile
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(smem_c + row * kRowPitch + q * 16) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        named_bar_sync(2, kEpiThreads);
+        const int n0 = n_blk * BN + c * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                          // coalesced: 8 consecutive threads cover one 128 B row segment
+          const int idx = i * kEpiThreads + et, r = idx >> 3, q = idx & 7;
+          const int grow = m_blk * BM + r, gcol = n0 + q * 4;
+          if (grow < M && gcol < N) {
+            const float4 f = *reinterpret_cast<const float4*>(smem_c + r * kRowPitch + q * 16);
+            const size_t eoff = ((size_t)grow * ldc + gcol) * sizeof(float);
+            if (out_mc) mc_red_add_v4_f32(out_mc + eoff, f.x, f.y, f.z, f.w);     // one op, reduced in every GPU's copy by the switch
+            else {
+              for (int p = 0; p < comm.world; ++p) {
+                float* dst = reinterpret_cast<float*>(comm.heap[p] + out_off + eoff);
+                p2p_red_add_f32(dst, f.x); p2p_red_add_f32(dst + 1, f.y); p2p_red_add_f32(dst + 2, f.z); p2p_red_add_f32(dst + 3, f.w);
+              }
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    __threadfence_system();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
+  // every rank's contributions are in flight or landed: publish + wait for all peers (one flag per CTA)
+  uint32_t ep = epoch_load(comm);
+  block_barrier(comm, ep);
+  epoch_store(comm, ep);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -382,6 +519,43 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
     case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// GEMM + all-reduce (K10).  `comm_view` = bytes of struct CommDev from sy_comm_device_view(); `out` is a
+// symmetric fp32 [M, ldc] buffer at heap offset out_off, zeroed by the caller on every rank.
+extern "C" int sy_gemm_bf16_tn_allreduce(const void* comm_view, size_t comm_view_bytes, const void* A, const void* B, size_t out_off,
+                                         int M, int N, int K, int lda, int ldb, int ldc, int block_n, void* stream) {
+  if (comm_view_bytes != sizeof(CommDev)) { snprintf(g_err, sizeof g_err, "communicator view size mismatch"); return 1; }
+  if ((lda | ldb) & 7 || (ldc & 3) || (N & 3) || ((uintptr_t)A | (uintptr_t)B) & 15 || (out_off & 15)) {
+    snprintf(g_err, sizeof g_err, "alignment: A/B 16B aligned, lda/ldb %% 8, N/ldc %% 4, out offset %% 16"); return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable"); return 6; }
+  CommDev cd; memcpy(&cd, comm_view, sizeof cd);
+  if (block_n <= 0) block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto go = [&](auto kern, int BN, int smem) -> int {
+    CUtensorMap ta, tb;
+    if (!make_map(&ta, A, K, M, lda, BK, BM) || !make_map(&tb, B, K, N, ldb, BK, BN)) return 3;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = tiles < sms ? tiles : sms;
+    if (grid > SY_MAX_BLOCKS) grid = SY_MAX_BLOCKS;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, cd, out_off, ldc, M, N, K);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  switch (block_n) {
+    case 64: return go(gemm_bf16_tn_allreduce_kernel<64>, 64, Cfg<64>::kSmemBytes);
+    case 128: return go(gemm_bf16_tn_allreduce_kernel<128>, 128, Cfg<128>::kSmemBytes);
+    case 256: return go(gemm_bf16_tn_allreduce_kernel<256>, 256, Cfg<256>::kSmemBytes);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

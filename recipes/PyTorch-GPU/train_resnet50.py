@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""PyTorch-GPU recipe body (north-star retarget): multi-instance ResNet-50 training, one rank per GPU.
+
+The reference recipe launches a stock PyTorch MNIST container on one K80
+(/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8).  Here the task runner starts one
+rank per GPU (RANK / WORLD_SIZE / SHIPYARD_GPU in the environment) and the step runs on the
+fused trainer: flat symmetric parameters, one fused all-reduce+SGD+all-gather kernel per step,
+CUDA-graph captured, uint8 batches staged from pinned memory.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.environ.get("SHIPYARD_HOME") or os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+import torch  # noqa: E402
+
+from batch_shipyard_b200.models.resnet import resnet50, resnet_tiny  # noqa: E402
+from batch_shipyard_b200.ops.coll import Communicator  # noqa: E402
+from batch_shipyard_b200.parallel.ddp import FusedDataParallelTrainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "tiny"])
+    ap.add_argument("--lr", type=float, default=0.1)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    gpu = os.environ.get("SHIPYARD_GPU", os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available() and gpu not in ("", "-1")
+    dev_index = int(gpu) % max(1, torch.cuda.device_count()) if use_cuda else None
+    if use_cuda:
+        torch.cuda.set_device(dev_index)
+    torch.manual_seed(1234)
+    session = os.environ.get("SHIPYARD_COLL_SESSION", f"pytorch-gpu-{os.getppid()}") + "-train"
+    comm = Communicator(rank, world, session, dev_index, heap_bytes=(1 << 30) if use_cuda else (256 << 20))
+    nclass = 1000 if a.model == "resnet50" else 10
+    model = resnet50() if a.model == "resnet50" else resnet_tiny(nclass)
+    tr = FusedDataParallelTrainer(model, comm, (a.batch, 3, a.image, a.image), nclass, lr=a.lr)
+    st = tr.make_stager()
+    st.fill_synthetic(seed=rank)
+    for hy in st.host_y:
+        hy.remainder_(nclass)
+    st.prefetch(0); st.run_step(0); st.read_loss(0)          # first batch on the device before capture
+    tr.prepare(warmup=2)
+    t0 = time.time()
+    losses = []
+    st.prefetch(0)
+    for i in range(a.steps):
+        st.run_step(i % 2)
+        st.prefetch((i + 1) % 2)
+        losses.append(st.read_loss(i % 2))
+    dt = time.time() - t0
+    comm.check_status()
+    if rank == 0:
+        print(json.dumps({"images_per_sec": round(a.batch * world * a.steps / dt, 1), "world": world, "steps": a.steps,
+                          "first_loss": round(losses[0], 4), "last_loss": round(losses[-1], 4), "transport": comm.transport,
+                          "own_kernels_per_step": tr.kernels_per_step}), flush=True)
+    comm.close()
+
+
+if __name__ == "__main__":
+    main()

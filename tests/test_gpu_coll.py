@@ -41,3 +41,11 @@ def test_nccl_preload_shim_under_torch_distributed():
                        stderr=subprocess.STDOUT, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-4000:]
     assert p.stdout.count("ok=True") == world
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("transport", ["auto", "p2p"])
+def test_k10_gemm_allreduce_fused(transport):
+    world = min(_ngpu(), 8)
+    ok, outs = run_ranks("_k10_worker.py", world, extra=["--transport", transport], gpu=True, timeout=600)
+    assert ok, "\n".join(o[-3000:] for o in outs)
