@@ -61,10 +61,10 @@ def _bind_bn(lib):
         return
     vp, fp = C.c_void_p, C.c_void_p
     lib.sy_ops_bn_fwd.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float, C.c_float,
-                                  C.c_int, vp]
+                                  C.c_int, vp, vp]
     lib.sy_ops_bn_apply_only.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float,
-                                         C.c_float, C.c_int, vp]
-    lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp]
+                                         C.c_float, C.c_int, vp, vp]
+    lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.sy_ops_maxpool3x3s2_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.sy_ops_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.sy_ops_u8_to_s2d_norm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
@@ -98,18 +98,21 @@ class _FusedBNAct(torch.autograd.Function):
         save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
         if residual is not None:
             assert residual.shape == x.shape and _is_nhwc(residual) and residual.dtype == x.dtype
+        # ReLU sign bits (1 bit / element) saved for backward instead of re-reading the activation
+        mask = torch.empty(m * (c // 8), dtype=torch.uint8, device=x.device) if relu else None
         if stats is None:
             ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
             rc = lib.sy_ops_bn_fwd(_ptr(x), _ptr(residual), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
                                    _ptr(running_var), _ptr(save_mean), _ptr(save_invstd), _ptr(ws), m, c, eps,
-                                   momentum, 1 if relu else 0, _stream(x))
+                                   momentum, 1 if relu else 0, _ptr(mask), _stream(x))
         else:
             rc = lib.sy_ops_bn_apply_only(_ptr(x), _ptr(residual), _ptr(out), _ptr(gamma), _ptr(beta),
                                           _ptr(running_mean), _ptr(running_var), _ptr(save_mean), _ptr(save_invstd),
-                                          _ptr(stats), m, c, eps, momentum, 1 if relu else 0, _stream(x))
+                                          _ptr(stats), m, c, eps, momentum, 1 if relu else 0, _ptr(mask), _stream(x))
         if rc != 0:
             raise RuntimeError(f"fused BN forward failed (rc={rc}, C={c})")
-        ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
+        ctx.save_for_backward(x, mask if mask is not None else save_mean, save_mean, save_invstd, gamma)
+        ctx.has_mask = mask is not None
         ctx.relu, ctx.has_res = bool(relu), residual is not None
         ctx.beta_ref = beta if isinstance(beta, torch.nn.Parameter) else None
         return out
@@ -117,7 +120,8 @@ class _FusedBNAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         lib = load(); _bind_bn(lib)
-        x, out, mean, invstd, gamma = ctx.saved_tensors
+        x, mask, mean, invstd, gamma = ctx.saved_tensors
+        mask = mask if ctx.has_mask else None
         n, c, h, w = x.shape
         m = n * h * w
         if not _is_nhwc(dout):
@@ -135,9 +139,9 @@ class _FusedBNAct(torch.autograd.Function):
             dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
             dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
         ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
-        rc = lib.sy_ops_bn_bwd(_ptr(dout), _ptr(out), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
+        rc = lib.sy_ops_bn_bwd(_ptr(dout), None, _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
                                _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
-                               1 if direct else 0, _stream(x))
+                               1 if direct else 0, _ptr(mask), _stream(x))
         if rc != 0:
             raise RuntimeError(f"fused BN backward failed (rc={rc})")
         if direct:

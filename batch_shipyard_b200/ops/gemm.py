@@ -60,6 +60,9 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[1] == b.shape[1]
     m, k = a.shape
     n = b.shape[0]
+    if k % 8:                                   # TMA needs 16-byte row pitches: zero-pad K (zeros do not change the product)
+        pad = 8 - k % 8
+        a = torch.nn.functional.pad(a, (0, pad)); b = torch.nn.functional.pad(b, (0, pad)); k += pad
     if not _rows_ok(a):
         a = a.contiguous()
     if not _rows_ok(b):

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/coll_sweep.jsonl")
     ap.add_argument("--algos", default="auto,ll,oneshot,twoshot_p2p,twoshot_nvls")
     ap.add_argument("--max-blocks", default="")
+    ap.add_argument("--nvls-copy", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -48,6 +49,8 @@ def main():
     comm = Communicator(rank, world, session=f"sweep-{os.environ.get('MASTER_PORT')}-{os.getppid()}", device=local, heap_bytes=heap)
     if a.max_blocks:
         comm.set_tuning(max_blocks=int(a.max_blocks))
+    if a.nvls_copy != "":
+        comm.set_tuning(nvls_copy=int(a.nvls_copy), nvls_min_world=2 if int(a.nvls_copy) else 99)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sizes = []
     s = lo

@@ -141,7 +141,7 @@ k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                float* __restrict__ running_mean, float* __restrict__ running_var,
                float* __restrict__ save_mean, float* __restrict__ save_invstd,
-               long M, int C, float eps, float momentum, int relu) {
+               long M, int C, float eps, float momentum, int relu, uint8_t* __restrict__ mask) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float sc[8], sh[8];
   const float invM = 1.f / (float)M;
@@ -175,8 +175,11 @@ k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
       for (int i = 0; i < 8; ++i) f[i] += q[i];
     }
     if (relu) {
+      uint32_t bits = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      for (int i = 0; i < 8; ++i) { bits |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = fmaxf(f[i], 0.f); }
+      // 1 bit per element for the backward pass: 16x less traffic than re-reading the activation
+      if (mask) mask[(size_t)r * G + cg] = (uint8_t)bits;
     }
     stg16(out + off, pack8(f));
   }
@@ -186,7 +189,8 @@ k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                 const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-                const float* __restrict__ invstd, float* __restrict__ sums, long M, int C, int relu) {
+                const float* __restrict__ invstd, float* __restrict__ sums, long M, int C, int relu,
+                const uint8_t* __restrict__ mask) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float mu[8], is[8];
 #pragma unroll
@@ -198,9 +202,15 @@ k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __r
     float d[8], xv[8];
     unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
     if (relu) {
-      float o[8]; unpack8(ldg16(out + off), o);
+      if (mask) {
+        const uint32_t bits = mask[(size_t)r * G + cg];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+        for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+      } else {
+        float o[8]; unpack8(ldg16(out + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[0][i] += d[i]; acc[1][i] += d[i] * (xv[i] - mu[i]) * is[i]; }
@@ -215,7 +225,7 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
                const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ gamma,
                const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
                __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dgamma,
-               __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu, int accum) {
+               __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu, int accum, const uint8_t* __restrict__ mask) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float mu[8], is[8], k0[8], k1[8], k2[8];
   const float invM = 1.f / (float)M;
@@ -239,9 +249,15 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
     float d[8], xv[8];
     unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
     if (relu) {
-      float o[8]; unpack8(ldg16(out + off), o);
+      if (mask) {
+        const uint32_t bits = mask[(size_t)r * G + cg];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+        for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+      } else {
+        float o[8]; unpack8(ldg16(out + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      }
     }
     if (dres) stg16(dres + off, pack8(d));
     float g[8];
@@ -268,7 +284,7 @@ static inline bool bn_shape_ok(int C) {
 // ws: float[2*C] scratch (zeroed here).  Returns 0 or a cuda error / -1 for bad shape.
 extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const void* gamma, const void* beta,
                              float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                             float* ws, long M, int C, float eps, float momentum, int relu, void* stream) {
+                             float* ws, long M, int C, float eps, float momentum, int relu, void* mask, void* stream) {
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
@@ -277,7 +293,7 @@ extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const vo
   COUNT_LAUNCH();
   k_bn_apply_fwd<<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, ws,
                                    (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, running_mean, running_var,
-                                   save_mean, save_invstd, M, C, eps, momentum, relu);
+                                   save_mean, save_invstd, M, C, eps, momentum, relu, (uint8_t*)mask);
   COUNT_LAUNCH();
   RET_LAST();
 }
@@ -285,29 +301,29 @@ extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const vo
 // variant used when the producing GEMM already accumulated the statistics in its epilogue
 extern "C" int sy_ops_bn_apply_only(const void* x, const void* res, void* out, const void* gamma, const void* beta,
                                     float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                                    const float* sums, long M, int C, float eps, float momentum, int relu, void* stream) {
+                                    const float* sums, long M, int C, float eps, float momentum, int relu, void* mask, void* stream) {
   if (!bn_shape_ok(C)) return -1;
   const int g = bn_grid(M, C);
   k_bn_apply_fwd<<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out,
                                                       sums, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, running_mean,
-                                                      running_var, save_mean, save_invstd, M, C, eps, momentum, relu);
+                                                      running_var, save_mean, save_invstd, M, C, eps, momentum, relu, (uint8_t*)mask);
   COUNT_LAUNCH();
   RET_LAST();
 }
 
 extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
                              const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
-                             int relu, int accum, void* stream) {
+                             int relu, int accum, const void* mask, void* stream) {
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
   const int g = bn_grid(M, C);
   k_bn_bwd_reduce<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
-                                    ws, M, C, relu);
+                                    ws, M, C, relu, (const uint8_t*)mask);
   COUNT_LAUNCH();
   k_bn_bwd_apply<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
                                    (const __nv_bfloat16*)gamma, ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
-                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum);
+                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum, (const uint8_t*)mask);
   COUNT_LAUNCH();
   RET_LAST();
 }

@@ -21,7 +21,9 @@ def test_single_gpu_collectives():
 @pytest.mark.parametrize("transport", ["auto", "p2p"])
 def test_multi_gpu_collectives(transport):
     world = min(_ngpu(), 8)
-    ok, outs = run_ranks("_coll_worker.py", world, extra=["--transport", transport], gpu=True, timeout=600)
+    import os
+    extra = ["--transport", transport] + (["--quick"] if os.environ.get("SHIPYARD_TEST_QUICK") else [])
+    ok, outs = run_ranks("_coll_worker.py", world, extra=extra, gpu=True, timeout=600)
     assert ok, "\n".join(o[-3000:] for o in outs)
 
 
