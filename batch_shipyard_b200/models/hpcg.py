@@ -1,0 +1,248 @@
+"""HPCG retarget: preconditioned CG on a 27-point stencil with a 4-level multigrid V-cycle.
+
+The reference recipe only launches Intel's CPU ``xhpcg_skx --n=256 --t=120`` over Intel MPI / InfiniBand
+(/root/reference/recipes/HPCG-Infiniband-IntelMPI/config/docker/jobs.yaml:5-20).  This is a GPU re-authoring
+from the public HPCG 3.x description: symmetric Gauss-Seidel smoother (8-colour
+ordering), 50-iteration CG sets, flop accounting SpMV 2*nnz, SYMGS 4*nnz, dot 2n, WAXPBY 2n.
+
+Communication on one NVSwitch box:
+  * global dot products -> 8-byte all-reduce on the LL kernel (one NVLink store latency, no barrier)
+  * halo exchange       -> ONE fused kernel per exchange: strided gather of the boundary plane, P2P store into
+                           the neighbour's ghost buffer, release-signal, wait for my own neighbours' signals
+                           (``Communicator.halo_exchange``; ghost buffers double-buffered by parity)
+Deviations (documented): the operator is applied matrix-free (no explicit sparse matrix), the process grid is
+1 x 1 x P (z slabs), the smoother is multi-coloured (allowed for optimised HPCG).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from ..ops import coll as _coll
+from ..ops import fused as _fused
+
+
+def _bind(lib):
+    if getattr(lib, "_hpcg_bound", False):
+        return
+    vp, i = C.c_void_p, C.c_int
+    lib.sy_hpcg_spmv.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    lib.sy_hpcg_symgs.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    lib.sy_hpcg_rhs.argtypes = [vp, i, i, i, i, i, vp]
+    lib.sy_hpcg_restrict.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.sy_hpcg_prolong.argtypes = [vp, vp, i, i, i, vp]
+    lib._hpcg_bound = True
+
+
+@dataclass
+class Level:
+    nx: int
+    ny: int
+    nz: int
+    ghosts: torch.Tensor      # symmetric: [2 parity, 2 (lo, hi), ny*nx] fp64
+    x: torch.Tensor
+    r: torch.Tensor
+    ax: torch.Tensor
+    parity: int = 0
+
+
+class HPCG:
+    def __init__(self, comm: _coll.Communicator, nx: int = 64, ny: int = 64, nz: int = 64, levels: int = 4):
+        assert nx % (1 << (levels - 1)) == 0 and ny % (1 << (levels - 1)) == 0 and nz % (1 << (levels - 1)) == 0, \
+            "local grid must be divisible by 2^(levels-1)"
+        self.comm, self.dev = comm, comm.torch_device
+        self.cuda = self.dev.type == "cuda"
+        self.rank, self.world = comm.rank, comm.world
+        self.lo_nbr = self.rank - 1 if self.rank > 0 else None
+        self.hi_nbr = self.rank + 1 if self.rank + 1 < self.world else None
+        if self.cuda:
+            self.lib = _fused.load(); _bind(self.lib)
+        self.levels: list[Level] = []
+        for l in range(levels):
+            n = (nx >> l, ny >> l, nz >> l)
+            g = comm.alloc((2, 2, n[0] * n[1]), torch.float64)
+            g.zero_()
+            z = lambda: torch.zeros(n[0] * n[1] * n[2], dtype=torch.float64, device=self.dev)  # noqa: E731
+            self.levels.append(Level(n[0], n[1], n[2], g, z(), z(), z()))
+        self.scalar = comm.alloc(8, torch.float64)        # staging for the dot-product all-reduce
+        self._sync(); comm.barrier(); self._sync()
+        self.launches0 = self._launches()
+
+    def _sync(self):
+        if self.cuda:
+            torch.cuda.synchronize(self.dev)
+
+    def _launches(self) -> int:
+        return self.comm.launches + (_fused.launch_count() if self.cuda else 0)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    # -- communication --------------------------------------------------------------------------------
+    def exchange(self, li: int, v: torch.Tensor):
+        """Push my boundary planes to the z-neighbours, wait for theirs; returns (lo, hi) ghost planes."""
+        L = self.levels[li]
+        if self.world == 1:
+            return None, None
+        par = L.parity
+        L.parity ^= 1
+        plane = L.nx * L.ny
+        descs, waits = [], []
+        base = self.comm.heap_offset(L.ghosts)
+        esz = 8
+        if self.lo_nbr is not None:      # my z=0 plane -> lower neighbour's HI ghost
+            descs.append(_coll.HaloDesc(self.lo_nbr, li * 2 + 1, base + ((par * 2 + 1) * plane) * esz, L.nx, L.ny, 1, 1, L.nx, plane, 0))
+            waits.append(li * 2 + 0)
+        if self.hi_nbr is not None:      # my z=nz-1 plane -> upper neighbour's LO ghost
+            descs.append(_coll.HaloDesc(self.hi_nbr, li * 2 + 0, base + ((par * 2 + 0) * plane) * esz, L.nx, L.ny, 1, 1, L.nx, plane, (L.nz - 1) * plane))
+            waits.append(li * 2 + 1)
+        self.comm.halo_exchange(v, descs, waits)
+        lo = L.ghosts[par, 0] if self.lo_nbr is not None else None
+        hi = L.ghosts[par, 1] if self.hi_nbr is not None else None
+        return lo, hi
+
+    def dot(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        s = self.scalar[:1]
+        s.copy_(torch.dot(a, b).view(1))
+        if self.world > 1:
+            self.comm.all_reduce(s, s)               # 8 bytes: LL path
+        return s.clone()
+
+    # -- operators --------------------------------------------------------------------------------------
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _nbr_sum_cpu(self, L: Level, x, lo, hi):
+        v = x.view(1, 1, L.nz, L.ny, L.nx)
+        z0 = lo.view(1, 1, 1, L.ny, L.nx) if lo is not None else torch.zeros(1, 1, 1, L.ny, L.nx, dtype=x.dtype)
+        z1 = hi.view(1, 1, 1, L.ny, L.nx) if hi is not None else torch.zeros(1, 1, 1, L.ny, L.nx, dtype=x.dtype)
+        full = torch.cat([z0, v, z1], dim=2)
+        full = F.pad(full, (1, 1, 1, 1, 0, 0))
+        s = F.conv3d(full, torch.ones(1, 1, 3, 3, 3, dtype=x.dtype)).view(-1)
+        return s - x                                                  # all 27 minus self
+
+    def spmv(self, li: int, x: torch.Tensor, y: torch.Tensor) -> None:
+        L = self.levels[li]
+        lo, hi = self.exchange(li, x)
+        if self.cuda:
+            self.lib.sy_hpcg_spmv(self._ptr(x), self._ptr(lo), self._ptr(hi), self._ptr(y), L.nx, L.ny, L.nz, self._stream())
+        else:
+            y.copy_(26.0 * x - self._nbr_sum_cpu(L, x, lo, hi))
+
+    def symgs(self, li: int, r: torch.Tensor, x: torch.Tensor) -> None:
+        L = self.levels[li]
+        lo, hi = self.exchange(li, x)
+        zoff = (self.rank * L.nz) & 1
+        if self.cuda:
+            self.lib.sy_hpcg_symgs(self._ptr(r), self._ptr(x), self._ptr(lo), self._ptr(hi), L.nx, L.ny, L.nz, zoff, self._stream())
+            return
+        xv = x.view(L.nz, L.ny, L.nx)
+        rv = r.view(L.nz, L.ny, L.nx)
+        for color in list(range(8)) + list(range(7, -1, -1)):
+            cx, cy, cz = color & 1, (color >> 1) & 1, (color >> 2) & 1
+            z0 = (cz - zoff) % 2
+            s = self._nbr_sum_cpu(L, x, lo, hi).view(L.nz, L.ny, L.nx)
+            xv[z0::2, cy::2, cx::2] = (rv[z0::2, cy::2, cx::2] + s[z0::2, cy::2, cx::2]) / 26.0
+
+    def mg(self, li: int, r: torch.Tensor, x: torch.Tensor) -> None:
+        x.zero_()
+        if li == len(self.levels) - 1:
+            self.symgs(li, r, x)
+            return
+        L, Lc = self.levels[li], self.levels[li + 1]
+        self.symgs(li, r, x)
+        self.spmv(li, x, L.ax)
+        if self.cuda:
+            self.lib.sy_hpcg_restrict(self._ptr(r), self._ptr(L.ax), self._ptr(Lc.r), Lc.nx, Lc.ny, Lc.nz, self._stream())
+        else:
+            Lc.r.copy_((r - L.ax).view(L.nz, L.ny, L.nx)[::2, ::2, ::2].reshape(-1))
+        self.mg(li + 1, Lc.r, Lc.x)
+        if self.cuda:
+            self.lib.sy_hpcg_prolong(self._ptr(x), self._ptr(Lc.x), Lc.nx, Lc.ny, Lc.nz, self._stream())
+        else:
+            x.view(L.nz, L.ny, L.nx)[::2, ::2, ::2] += Lc.x.view(Lc.nz, Lc.ny, Lc.nx)
+        self.symgs(li, r, x)
+
+    def rhs(self) -> torch.Tensor:
+        L = self.levels[0]
+        b = torch.empty(L.nx * L.ny * L.nz, dtype=torch.float64, device=self.dev)
+        if self.cuda:
+            self.lib.sy_hpcg_rhs(self._ptr(b), L.nx, L.ny, L.nz, self.rank * L.nz, self.world * L.nz, self._stream())
+        else:
+            gz = torch.arange(L.nz) + self.rank * L.nz
+            cz = 1 + (gz > 0).long() + (gz < self.world * L.nz - 1).long()
+            cy = 1 + (torch.arange(L.ny) > 0).long() + (torch.arange(L.ny) < L.ny - 1).long()
+            cx = 1 + (torch.arange(L.nx) > 0).long() + (torch.arange(L.nx) < L.nx - 1).long()
+            b.copy_((26.0 - (cz[:, None, None] * cy[None, :, None] * cx[None, None, :] - 1).double()).reshape(-1))
+        return b
+
+    # -- CG -----------------------------------------------------------------------------------------------
+    def cg(self, b: torch.Tensor, x: torch.Tensor, iters: int = 50, precondition: bool = True) -> list[float]:
+        L = self.levels[0]
+        r, z, p, ap = L.r, L.x, torch.zeros_like(b), L.ax
+        self.spmv(0, x, ap)
+        r.copy_(b - ap)
+        norms = [float(self.dot(r, r).sqrt())]
+        rtz_old = None
+        zz = torch.zeros_like(b)
+        for k in range(iters):
+            if precondition:
+                self.mg(0, r, zz)
+            else:
+                zz.copy_(r)
+            rtz = self.dot(r, zz)
+            if k == 0:
+                p.copy_(zz)
+            else:
+                p.mul_(rtz / rtz_old).add_(zz)
+            rtz_old = rtz
+            self.spmv(0, p, ap)
+            alpha = rtz / self.dot(p, ap)
+            x.add_(p * alpha)
+            r.sub_(ap * alpha)
+            norms.append(float(self.dot(r, r).sqrt()))
+        return norms
+
+    def flops_per_iteration(self) -> float:
+        def nnz(L, gz):
+            return (3 * L.nx - 2) * (3 * L.ny - 2) * (3 * gz - 2)
+        n0 = self.levels[0].nx * self.levels[0].ny * self.levels[0].nz * self.world
+        f = 2.0 * nnz(self.levels[0], self.levels[0].nz * self.world) + 3 * 2.0 * n0 + 3 * 2.0 * n0
+        for li, L in enumerate(self.levels):
+            z = nnz(L, L.nz * self.world)
+            f += (4.0 * z) if li == len(self.levels) - 1 else (2 * 4.0 * z + 2.0 * z)
+        return f
+
+    def benchmark(self, seconds: float = 10.0, iters_per_set: int = 50) -> dict:
+        b = self.rhs()
+        x = torch.zeros_like(b)
+        norms = self.cg(b, x, iters=min(10, iters_per_set))            # warm-up + validity
+        self._sync(); self.comm.barrier(); self._sync()
+        t0 = time.time(); sets = 0; total_iters = 0
+        l0 = self._launches()
+        while True:
+            x.zero_()
+            norms = self.cg(b, x, iters=iters_per_set)
+            self._sync()
+            sets += 1; total_iters += iters_per_set
+            # every rank must agree on when to stop
+            flag = self.scalar[1:2]
+            flag.fill_(1.0 if time.time() - t0 < seconds else 0.0)
+            if self.world > 1:
+                self.comm.all_reduce(flag, flag, op="min")
+            self._sync()
+            if float(flag) == 0.0 or sets >= 1000:
+                break
+        dt = time.time() - t0
+        err = float((x - 1.0).abs().max())
+        self.comm.check_status()
+        return {"gflops": self.flops_per_iteration() * total_iters / dt / 1e9, "seconds": dt, "cg_sets": sets, "iterations": total_iters,
+                "residual_reduction": norms[-1] / max(norms[0], 1e-300), "max_error_vs_ones": err, "world": self.world,
+                "local_grid": [self.levels[0].nx, self.levels[0].ny, self.levels[0].nz], "own_kernel_launches": self._launches() - l0,
+                "transport": self.comm.transport}

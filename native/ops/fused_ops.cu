@@ -461,3 +461,118 @@ extern "C" int sy_ops_u8_to_s2d_norm(const void* in, void* out, int N, int H, in
   COUNT_LAUNCH();
   RET_LAST();
 }
+
+// ===========================================================================
+// HPCG retarget kernels (fp64, 27-point stencil, matrix-free: diagonal 26, off-diagonals -1 for every
+// neighbour inside the global domain).  The local grid is nx*ny*nz with a 1-D decomposition along z;
+// the z-neighbour planes arrive in `lo` / `hi` ghost buffers written by the neighbours' fused halo push.
+// ===========================================================================
+DEVI double stencil_nbr_sum(const double* __restrict__ x, const double* __restrict__ lo, const double* __restrict__ hi,
+                            int ix, int iy, int iz, int nx, int ny, int nz, int* count) {
+  double s = 0.0; int c = 0;
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int z = iz + dz;
+    const double* plane;
+    if (z < 0) { if (!lo) continue; plane = lo; }
+    else if (z >= nz) { if (!hi) continue; plane = hi; }
+    else plane = x + (size_t)z * nx * ny;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = iy + dy;
+      if (y < 0 || y >= ny) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = ix + dx;
+        if (xx < 0 || xx >= nx || (dx == 0 && dy == 0 && dz == 0)) continue;
+        s += plane[(size_t)y * nx + xx]; ++c;
+      }
+    }
+  }
+  if (count) *count = c;
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_hpcg_spmv(const double* __restrict__ x, const double* __restrict__ lo, const double* __restrict__ hi, double* __restrict__ y,
+            int nx, int ny, int nz) {
+  const size_t n = (size_t)nx * ny * nz;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / ((size_t)nx * ny));
+    y[i] = 26.0 * x[i] - stencil_nbr_sum(x, lo, hi, ix, iy, iz, nx, ny, nz, nullptr);
+  }
+}
+
+// one colour of the 8-colour Gauss-Seidel sweep: x_i = (r_i + sum of neighbours) / 26
+__global__ void __launch_bounds__(256)
+k_hpcg_symgs_color(const double* __restrict__ r, double* __restrict__ x, const double* __restrict__ lo, const double* __restrict__ hi,
+                   int nx, int ny, int nz, int color, int zoff) {
+  const int cx = color & 1, cy = (color >> 1) & 1, cz = (color >> 2) & 1;
+  const int hx = (nx - cx + 1) / 2, hy = (ny - cy + 1) / 2;
+  const int z0 = ((cz - zoff) % 2 + 2) % 2;             // first local z with global parity cz
+  const int hz = (nz - z0 + 1) / 2;
+  const size_t n = (size_t)hx * hy * hz;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = 2 * (int)(t % hx) + cx, iy = 2 * (int)((t / hx) % hy) + cy, iz = 2 * (int)(t / ((size_t)hx * hy)) + z0;
+    const size_t i = ((size_t)iz * ny + iy) * nx + ix;
+    x[i] = (r[i] + stencil_nbr_sum(x, lo, hi, ix, iy, iz, nx, ny, nz, nullptr)) * (1.0 / 26.0);
+  }
+}
+
+// b = A * ones  (26 - number of in-domain neighbours); gz0 / gnz give this rank's place in the global z range
+__global__ void k_hpcg_rhs(double* __restrict__ b, int nx, int ny, int nz, int gz0, int gnz) {
+  const size_t n = (size_t)nx * ny * nz;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / ((size_t)nx * ny)) + gz0;
+    const int cx = 1 + (ix > 0) + (ix < nx - 1), cy = 1 + (iy > 0) + (iy < ny - 1), cz = 1 + (iz > 0) + (iz < gnz - 1);
+    b[i] = 26.0 - (double)(cx * cy * cz - 1);
+  }
+}
+
+// coarse residual: rc[c] = rf[f] - Axf[f] at f = (2x, 2y, 2z)
+__global__ void k_hpcg_restrict(const double* __restrict__ rf, const double* __restrict__ axf, double* __restrict__ rc, int nxc, int nyc, int nzc) {
+  const size_t n = (size_t)nxc * nyc * nzc;
+  const int nxf = 2 * nxc, nyf = 2 * nyc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % nxc), iy = (int)((i / nxc) % nyc), iz = (int)(i / ((size_t)nxc * nyc));
+    const size_t f = ((size_t)(2 * iz) * nyf + 2 * iy) * nxf + 2 * ix;
+    rc[i] = rf[f] - axf[f];
+  }
+}
+__global__ void k_hpcg_prolong(double* __restrict__ xf, const double* __restrict__ xc, int nxc, int nyc, int nzc) {
+  const size_t n = (size_t)nxc * nyc * nzc;
+  const int nxf = 2 * nxc, nyf = 2 * nyc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % nxc), iy = (int)((i / nxc) % nyc), iz = (int)(i / ((size_t)nxc * nyc));
+    xf[((size_t)(2 * iz) * nyf + 2 * iy) * nxf + 2 * ix] += xc[i];
+  }
+}
+
+static inline int hpcg_grid(size_t n) { size_t b = (n + 255) / 256; return (int)(b < 148 * 8 ? (b ? b : 1) : 148 * 8); }
+extern "C" int sy_hpcg_spmv(const void* x, const void* lo, const void* hi, void* y, int nx, int ny, int nz, void* stream) {
+  k_hpcg_spmv<<<hpcg_grid((size_t)nx * ny * nz), 256, 0, (cudaStream_t)stream>>>((const double*)x, (const double*)lo, (const double*)hi, (double*)y, nx, ny, nz);
+  COUNT_LAUNCH(); RET_LAST();
+}
+// one symmetric sweep: colours 0..7 then 7..0
+extern "C" int sy_hpcg_symgs(const void* r, void* x, const void* lo, const void* hi, int nx, int ny, int nz, int zoff, void* stream) {
+  const int g = hpcg_grid((size_t)nx * ny * nz / 8 + 1);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int k = 0; k < 8; ++k) {
+      const int color = pass == 0 ? k : 7 - k;
+      k_hpcg_symgs_color<<<g, 256, 0, (cudaStream_t)stream>>>((const double*)r, (double*)x, (const double*)lo, (const double*)hi, nx, ny, nz, color, zoff);
+      COUNT_LAUNCH();
+    }
+  RET_LAST();
+}
+extern "C" int sy_hpcg_rhs(void* b, int nx, int ny, int nz, int gz0, int gnz, void* stream) {
+  k_hpcg_rhs<<<hpcg_grid((size_t)nx * ny * nz), 256, 0, (cudaStream_t)stream>>>((double*)b, nx, ny, nz, gz0, gnz);
+  COUNT_LAUNCH(); RET_LAST();
+}
+extern "C" int sy_hpcg_restrict(const void* rf, const void* axf, void* rc, int nxc, int nyc, int nzc, void* stream) {
+  k_hpcg_restrict<<<hpcg_grid((size_t)nxc * nyc * nzc), 256, 0, (cudaStream_t)stream>>>((const double*)rf, (const double*)axf, (double*)rc, nxc, nyc, nzc);
+  COUNT_LAUNCH(); RET_LAST();
+}
+extern "C" int sy_hpcg_prolong(void* xf, const void* xc, int nxc, int nyc, int nzc, void* stream) {
+  k_hpcg_prolong<<<hpcg_grid((size_t)nxc * nyc * nzc), 256, 0, (cudaStream_t)stream>>>((double*)xf, (const double*)xc, nxc, nyc, nzc);
+  COUNT_LAUNCH(); RET_LAST();
+}
