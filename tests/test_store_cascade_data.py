@@ -148,3 +148,26 @@ def test_ingress_bin_packing_split_and_filters(tmp_path):
     assert len(parts) == 4 and sum(p.size for p in parts) == len(data)
     stats = ingress.transfer(ingress.bin_pack(parts, ["n0", "n1", "n2"]), str(tmp_path / "dst"), 2)
     assert (tmp_path / "dst" / "big.bin").read_bytes() == data and stats["bytes"] == len(data) and stats["mbit_per_s"] > 0
+
+
+def test_perfgraph_coalesces_intervals(tmp_path):
+    from batch_shipyard_b200.misc import perfgraph
+    from batch_shipyard_b200.state.store import Store
+    st = Store(str(tmp_path / "state"))
+    t = 1000.0
+    st.record_event("nodeprep", "start", pool="p", node="n0", ts=t)
+    st.record_event("cascade", "start", pool="p", node="n0", ts=t + 1)
+    st.record_event("cascade", "pull-start", pool="p", node="n0", message="img:a", ts=t + 1.5)
+    st.record_event("cascade", "pull-end", pool="p", node="n0", message="img:a,size=10,seconds=0.5", ts=t + 2)
+    st.record_event("cascade", "gr-done", pool="p", node="n0", message="nglobalresources=1", ts=t + 2.5)
+    st.record_event("nodeprep", "end", pool="p", node="n0", ts=t + 3)
+    tl = perfgraph.coalesce(st.events("p"))
+    iv = {name: (round(a, 3), round(b, 3)) for name, a, b in tl["n0"]["intervals"]}
+    assert iv["nodeprep:run"] == (0.0, 3.0)
+    assert iv["cascade:run"] == (1.0, 2.5)
+    assert iv["cascade:pull[img:a]"] == (1.5, 2.0)
+    text = perfgraph.render_text(tl)
+    assert "cascade:pull[img:a]" in text and "#" in text
+    dat, gp = perfgraph.render_gnuplot(tl, str(tmp_path / "tl"))
+    assert open(dat).read().count("\n") == 3 and "boxxyerrorbars" in open(gp).read()
+    assert perfgraph.main(["--state-dir", str(tmp_path / "state"), "--pool", "p", "--format", "json"]) == 0
