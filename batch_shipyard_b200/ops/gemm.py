@@ -36,6 +36,10 @@ def load() -> C.CDLL:
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_tn_allreduce.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_nt_splitk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -86,21 +90,110 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     return out
 
 
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[K,N] with b row-major (N contiguous): the dgrad shape dX = dY @ W.  The kernel reads b as an
+    MN-major tcgen05 operand, so no transposed copy of the weight is made."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[1] == b.shape[0]
+    m, k = a.shape
+    n = b.shape[1]
+    if not _rows_ok(a):
+        a = a.contiguous()
+    if not _rows_ok(b):
+        b = b.contiguous()
+    if k % 8 or not _rows_ok(a):
+        return gemm_tn(a, b.t().contiguous(), out=out, block_n=block_n, max_ctas=max_ctas)
+    if out is None:
+        ldc = (n + 7) // 8 * 8
+        buf = torch.empty((m, ldc), dtype=torch.bfloat16, device=a.device)
+        out = buf[:, :n] if ldc != n else buf
+    assert out.shape == (m, n) and out.dtype == torch.bfloat16 and _rows_ok(out)
+    lib = load()
+    rc = lib.sy_gemm_bf16_nn(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
+                             a.stride(0), b.stride(0), out.stride(0), block_n, max_ctas,
+                             C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_gemm_bf16_nn failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out
+
+
+_WS: dict = {}
+_WS_FLOATS = 4 << 20          # covers I*J up to 2048 x 2048
+_WS_TICKETS = 4096
+
+
+def _workspace(dev: torch.device):
+    """Per-device split-K workspace: zero on entry AND on exit of every wgrad kernel (the finalising CTA cleans up),
+    so one allocation serves every layer and the kernel stays CUDA-graph capturable."""
+    key = (dev.type, dev.index)
+    if key not in _WS:
+        _WS[key] = (torch.zeros(_WS_FLOATS, dtype=torch.float32, device=dev), torch.zeros(_WS_TICKETS, dtype=torch.int32, device=dev))
+    return _WS[key]
+
+
+def gemm_nt_wgrad(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+                  block_n: int = 0, splits: int = 0) -> torch.Tensor:
+    """out[J, I] (+)= b[K,J]^T @ a[K,I]  — the weight gradient dW[Cout,Cin] = dY^T X with a = X[pixels,Cin], b = dY[pixels,Cout].
+    One split-K tcgen05 kernel (both operands MN-major through TMA); the last CTA of a tile writes bf16 into `out`."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[0] == b.shape[0]
+    k, i = a.shape
+    j = b.shape[1]
+    if not _rows_ok(a):
+        a = a.contiguous()
+    if not _rows_ok(b):
+        b = b.contiguous()
+    assert _rows_ok(a) and _rows_ok(b), "wgrad operands need 16-byte aligned rows (channel counts multiple of 8)"
+    if out is None:
+        out = torch.empty((j, i), dtype=torch.bfloat16, device=a.device)
+        accumulate = False
+    assert out.shape == (j, i) and out.dtype == torch.bfloat16 and out.stride(1) == 1
+    ws, tickets = _workspace(a.device)
+    if i * j > ws.numel():
+        raise RuntimeError(f"wgrad output {j}x{i} exceeds the split-K workspace")
+    lib = load()
+    rc = lib.sy_gemm_bf16_nt_splitk(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), i, j, k,
+                                    a.stride(0), b.stride(0), out.stride(0), C.c_void_p(ws.data_ptr()), C.c_void_p(tickets.data_ptr()),
+                                    1 if accumulate else 0, block_n, splits, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_gemm_bf16_nt_splitk failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out
+
+
+def _grad_view_2d(p: torch.Tensor, rows: int, cols: int) -> Optional[torch.Tensor]:
+    """The parameter's existing .grad as a contiguous [rows, cols] view (NHWC-stored conv weights included), or None."""
+    g = getattr(p, "grad", None)
+    if g is None or g.dtype != torch.bfloat16:
+        return None
+    v = g.permute(0, 2, 3, 1) if g.dim() == 4 else g
+    if not v.is_contiguous():
+        return None
+    return v.reshape(rows, cols)
+
+
 class _LinearTN(torch.autograd.Function):
-    """y = x @ w^T (+ b): forward and dgrad on the tcgen05 kernel; wgrad (both operands MN-major) via cuBLAS."""
+    """y = x @ w^T (+ b): forward, dgrad (W read as an MN-major operand) and wgrad (split-K, both MN-major) all on tcgen05."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
+        ctx.w_ref = w
         return gemm_tn(x, w, bias=b)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = gemm_tn(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None     # dX = dY @ W  (W^T is small)
-        dw = (dy.t() @ x) if ctx.needs_input_grad[1] else None
+        if not _rows_ok(dy):
+            dy = dy.contiguous()
+        dx = gemm_nn(dy, w) if ctx.needs_input_grad[0] else None                        # dX = dY @ W
+        dw = None
+        if ctx.needs_input_grad[1]:
+            gv = _grad_view_2d(ctx.w_ref, w.shape[0], w.shape[1])
+            if gv is not None and x.shape[1] % 8 == 0 and _rows_ok(dy):
+                gemm_nt_wgrad(x, dy, out=gv, accumulate=True)                           # straight into the flat gradient buffer
+            elif x.shape[1] % 8 == 0 and _rows_ok(dy):
+                dw = gemm_nt_wgrad(x, dy)
+            else:
+                dw = dy.t() @ x
         db = dy.float().sum(0).to(dy.dtype) if ctx.has_bias else None
         return dx, dw, db
 
@@ -122,6 +215,7 @@ class _Conv1x1NHWC(torch.autograd.Function):
         stats = torch.zeros(2 * cout, dtype=torch.float32, device=x.device) if want_stats else None
         y2 = gemm_tn(x2, w2, stats=stats)
         ctx.save_for_backward(x, w)
+        ctx.w_ref = w
         y = y2.view(n, h, wd, cout).permute(0, 3, 1, 2)
         ctx.mark_non_differentiable(stats) if stats is not None else None
         return (y, stats) if want_stats else (y, None)
@@ -136,11 +230,15 @@ class _Conv1x1NHWC(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            wt = w.permute(0, 2, 3, 1).reshape(cout, cin).t().contiguous()          # [Cin, Cout], small
-            dx = gemm_tn(dy2, wt).view(n, h, wd, cin).permute(0, 3, 1, 2)
+            w2 = w.permute(0, 2, 3, 1).reshape(cout, cin)                            # [K=Cout, N=Cin]: MN-major B, no transpose
+            dx = gemm_nn(dy2, w2).view(n, h, wd, cin).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             x2 = x.permute(0, 2, 3, 1).reshape(n * h * wd, cin)
-            dw = (dy2.t() @ x2).view(cout, 1, 1, cin).permute(0, 3, 1, 2)
+            gv = _grad_view_2d(ctx.w_ref, cout, cin)
+            if gv is not None:
+                gemm_nt_wgrad(x2, dy2, out=gv, accumulate=True)                      # written into w.grad by the kernel itself
+            else:
+                dw = gemm_nt_wgrad(x2, dy2).view(cout, 1, 1, cin).permute(0, 3, 1, 2)
         return dx, dw, None
 
 

@@ -121,9 +121,24 @@ DEVI uint64_t make_kmajor_sw128_desc(const void* smem_tile) {
   d |= (uint64_t)2 << 61;                                  // layout type: SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-template <int BN> DEVI constexpr uint32_t make_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major operand (the M/N index is the contiguous one), 128-byte swizzle.  Canonical layout in 16-byte units
+// ((8,n),(8,k)):((1,LBO),(8,SBO)): a 64-element MN slab is one 128 B row per k; 8 k-rows form a 1024 B swizzle
+// group (SBO); the next 64-element MN slab starts LBO bytes later.  Each slab is exactly what one TMA box
+// {64 elements, BK rows} with SWIZZLE_128B writes.
+DEVI uint64_t make_mnmajor_sw128_desc(const void* smem_tile, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr int kSlabBytes = 64 * BK * 2;   // one MN-major slab: 64 MN elements x BK k-rows = 8 KB
+// instruction descriptor: D=f32, A=B=bf16, M=128, N=BN; bit 15 / 16 = A / B is MN-major
+template <int BN, bool kAMN = false, bool kBMN = false> DEVI constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((kAMN ? 1u : 0u) << 15) | ((kBMN ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 DEVI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -147,7 +162,7 @@ template <int BN> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool kStats, bool kBias>
+template <int BN, bool kStats, bool kBias, bool kBMN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
@@ -189,9 +204,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n_blk = t / num_m, m_blk = t % num_m;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          int nb = BN / 64;
+          if constexpr (kBMN) { nb = 0; for (int sl = 0; sl < BN / 64; ++sl) nb += (n_blk * BN + sl * 64 < N); }
+          mbar_expect_tx(&full_bar[stage], kBMN ? (uint32_t)(C::kABytes + nb * kSlabBytes) : (uint32_t)C::kStageBytes);
           tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (kBMN) {
+            // B given as [K, N] with N contiguous (e.g. W[Cout, Cin] for dgrad): one 64-wide slab per TMA box;
+            // slabs entirely past N are skipped (they only feed output columns the TMA store clips)
+            for (int sl = 0; sl < nb; ++sl)
+              tma_load_2d(smem_b + stage * C::kBBytes + sl * kSlabBytes, &tmap_b, &full_bar[stage], n_blk * BN + sl * 64, kb * BK);
+          } else {
+            tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -199,7 +223,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<BN>();
+      constexpr uint32_t idesc = make_idesc<BN, false, kBMN>();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -210,11 +234,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
           const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
-          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+          const uint64_t bdesc = kBMN ? make_mnmajor_sw128_desc(smem_b + stage * C::kBBytes, kSlabBytes)
+                                      : make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+          // K advance: K-major = +32 bytes inside the 128B swizzle atom; MN-major = +16 k-rows x 128 B
+          constexpr uint64_t kBStep = kBMN ? (UK * 128 >> 4) : (UK * 2 >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            // advancing K inside the 128B swizzle atom = +32 bytes on the start address (encoded >>4)
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)k * kBStep, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -309,6 +335,158 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
 }
 
+
+// ===================================================================================================
+// Weight-gradient GEMM: D[i, j] = sum_k A[k, i] * B[k, j], both operands MN-major (a 1x1-conv / Linear wgrad:
+// A = X[pixels, Cin], B = dY[pixels, Cout], D = dW[Cout, Cin] stored as out[j * ldo + i]).  The reduction
+// dimension is the huge one (pixels) and the output is tiny, so the work is split along K over all SMs:
+// every CTA accumulates its K-range in TMEM, adds the fp32 tile into a workspace with red.global.add, and the
+// LAST CTA to finish a tile (atomic ticket) converts it to bf16 straight into the gradient buffer and leaves
+// workspace + ticket zeroed for the next launch — one kernel, no split-K reduce pass, no transposes, no
+// separate gradient-accumulate kernel, CUDA-graph capturable (no host-side memset).
+// ===================================================================================================
+DEVI void red_add_f32(float* p, float v) { asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                           int I, int J, int K, int splits, float* __restrict__ ws, int* __restrict__ tickets,
+                           __nv_bfloat16* __restrict__ out, int ldo, int accumulate) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + 2 * C::kCBytes);
+  uint64_t* full_bar = bars; uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages; uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  uint32_t* s_last = tmem_ptr + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (I + BM - 1) / BM, num_n = (J + BN - 1) / BN, num_k = (K + BK - 1) / BK;
+  const int num_items = num_m * num_n * splits;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+        const int tile = w / splits, sp = w % splits;
+        const int n_blk = tile / num_m, m_blk = tile % num_m;
+        const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
+        // slabs that start beyond the matrix edge are not loaded at all: their smem stays stale, which only
+        // feeds accumulator rows / columns the epilogue never stores (rows and columns are independent)
+        int na = 0, nb = 0;
+        for (int sl = 0; sl < BM / 64; ++sl) na += (m_blk * BM + sl * 64 < I);
+        for (int sl = 0; sl < BN / 64; ++sl) nb += (n_blk * BN + sl * 64 < J);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(na + nb) * kSlabBytes);
+          for (int sl = 0; sl < na; ++sl)
+            tma_load_2d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], m_blk * BM + sl * 64, kb * BK);
+          for (int sl = 0; sl < nb; ++sl)
+            tma_load_2d(smem_b + stage * C::kBBytes + sl * kSlabBytes, &tmap_b, &full_bar[stage], n_blk * BN + sl * 64, kb * BK);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN, true, true>();
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+        const int sp = w % splits;
+        const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_mnmajor_sw128_desc(smem_a + stage * C::kABytes, kSlabBytes);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(smem_b + stage * C::kBBytes, kSlabBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)       // 16 k-rows x 128 B per UMMA_K step
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 128 >> 4), bdesc + (uint64_t)(k * UK * 128 >> 4), idesc, (kb != kb0) || k != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4, et = threadIdx.x - 128;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      const int tile = w / splits;
+      const int n_blk = tile / num_m, m_blk = tile % num_m;
+      const int i = m_blk * BM + ew * 32 + lane;           // TMEM lane = output row i = contiguous index of `out`
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+        const int j0 = n_blk * BN + c * 32;
+        if (i < I) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + jj;
+            if (j < J) {
+              const float val = __uint_as_float(v[jj]);
+              if (splits == 1) {          // whole K in this CTA: write the gradient directly (a warp covers 64 contiguous bytes)
+                __nv_bfloat16* o = out + (size_t)j * ldo + i;
+                *o = __float2bfloat16_rn(val + (accumulate ? __bfloat162float(*o) : 0.f));
+              } else {
+                red_add_f32(ws + (size_t)j * I + i, val);   // one 128 B line per warp instruction
+              }
+            }
+          }
+        }
+      }
+      if (splits > 1) {
+        __threadfence();
+        named_bar_sync(1, kEpiThreads);
+        if (et == 0) *s_last = (atomicAdd(&tickets[tile], 1) == splits - 1) ? 1u : 0u;
+        named_bar_sync(2, kEpiThreads);
+        if (*s_last) {                                      // every K-split of this tile has been added: finalise it
+          __threadfence();
+          const int ii = m_blk * BM + et;
+          if (ii < I) {
+            for (int jj = 0; jj < BN; ++jj) {
+              const int j = n_blk * BN + jj;
+              if (j >= J) break;
+              float* wp = ws + (size_t)j * I + ii;
+              const float val = __ldcg(wp);
+              __stcg(wp, 0.f);
+              __nv_bfloat16* o = out + (size_t)j * ldo + ii;
+              *o = __float2bfloat16_rn(val + (accumulate ? __bfloat162float(*o) : 0.f));
+            }
+          }
+          if (et == 0) tickets[tile] = 0;
+        }
+        named_bar_sync(1, kEpiThreads);                     // s_last is rewritten by the next item
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
+}
 
 // ===================================================================================================
 // K10: GEMM + all-reduce in ONE kernel.  Every rank multiplies its K-shard (C_r = A_r x B_r^T); the
@@ -473,10 +651,11 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
 
 template <int BN>
 int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, const void* bias, float* stats,
-           int max_ctas, cudaStream_t s) {
+           int max_ctas, cudaStream_t s, bool b_mn = false) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb, tc;
-  if (!make_map(&ta, A, K, M, lda, BK, BM) || !make_map(&tb, B, K, N, ldb, BK, BN) || !make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
+  if (!make_map(&ta, A, K, M, lda, BK, BM) || !make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
+  if (!(b_mn ? make_map(&tb, B, N, K, ldb, 64, BK) : make_map(&tb, B, K, N, ldb, BK, BN))) return 3;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -492,6 +671,10 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
     return 0;
   };
   if (stats && bias) { snprintf(g_err, sizeof g_err, "stats and bias cannot be combined"); return 2; }
+  if (b_mn) {
+    if (stats || bias) { snprintf(g_err, sizeof g_err, "MN-major B: no fused epilogue"); return 2; }
+    return go(gemm_bf16_tn_kernel<BN, false, false, true>);
+  }
   if (stats) return go(gemm_bf16_tn_kernel<BN, true, false>);
   if (bias) return go(gemm_bf16_tn_kernel<BN, false, true>);
   return go(gemm_bf16_tn_kernel<BN, false, false>);
@@ -519,6 +702,68 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
     case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// C[M,N] = A[M,K] * B[K,N]; B row-major with N contiguous (MN-major operand, no transpose copy).  ldb % 8 == 0.
+extern "C" int sy_gemm_bf16_nn(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                               int block_n, int max_ctas, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda | ldb | ldc) & 7 || ((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) {
+    snprintf(g_err, sizeof g_err, "alignment: pointers must be 16B aligned and leading dimensions multiples of 8");
+    return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_n <= 0) block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  switch (block_n) {
+    case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
+    case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
+    case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// out[j * ldo + i] (+)= sum_k A[k, i] * B[k, j]   (A: [K, I] row-major, B: [K, J] row-major; the wgrad shape).
+// ws: float[I * J] and tickets: int[ceil(I/128) * ceil(J/block_n)], both zero on entry and zero again on exit.
+// splits <= 0: chosen so that tiles * splits ~ number of SMs.
+extern "C" int sy_gemm_bf16_nt_splitk(const void* A, const void* B, void* out, int I, int J, int K, int lda, int ldb, int ldo,
+                                      float* ws, int* tickets, int accumulate, int block_n, int splits, void* stream) {
+  if (I <= 0 || J <= 0 || K <= 0) return 0;
+  if ((lda | ldb) & 7 || ((uintptr_t)A | (uintptr_t)B) & 15) {
+    snprintf(g_err, sizeof g_err, "alignment: A/B 16B aligned and lda/ldb multiples of 8"); return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
+  if (block_n <= 0) block_n = J > 128 ? 256 : (J > 64 ? 128 : 64);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto go = [&](auto kern, int BN, int smem) -> int {
+    CUtensorMap ta, tb;
+    if (!make_map(&ta, A, I, K, lda, 64, BK) || !make_map(&tb, B, J, K, ldb, 64, BK)) return 3;
+    const int tiles = ((I + BM - 1) / BM) * ((J + BN - 1) / BN), num_k = (K + BK - 1) / BK;
+    int sp = splits;
+    if (sp <= 0) { sp = sms / tiles; if (sp > num_k / 4) sp = num_k / 4; }
+    if (sp < 1) sp = 1;
+    if (sp > num_k) sp = num_k;
+    if (sp > 1 && (!ws || !tickets)) { snprintf(g_err, sizeof g_err, "split-K needs a workspace"); return 2; }
+    const long items = (long)tiles * sp;
+    const int grid = (int)(items < sms ? items : sms);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)out, ldo, accumulate);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  switch (block_n) {
+    case 64: return go(gemm_bf16_nt_splitk_kernel<64>, 64, Cfg<64>::kSmemBytes);
+    case 128: return go(gemm_bf16_nt_splitk_kernel<128>, 128, Cfg<128>::kSmemBytes);
+    case 256: return go(gemm_bf16_nt_splitk_kernel<256>, 256, Cfg<256>::kSmemBytes);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

@@ -113,24 +113,30 @@ DEVI void block_reduce_atomic(float (&acc)[NACC][8], float* __restrict__ out, in
   }
 }
 
+// Row loops are unrolled kU deep with every 16-byte load of a batch issued before the first use, so a
+// thread keeps kU x (1-3) vectors in flight: HBM needs ~35 KB outstanding per SM (Little's law at
+// 6.5 TB/s x ~800 ns) and 2 vectors per thread at ~50% occupancy is not enough.
+constexpr int kU = 4;
+
 __global__ void __launch_bounds__(256)
 k_bn_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long M, int C) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float acc[2][8] = {};
   const long stride = (long)gridDim.x * rpi;
   long r = (long)blockIdx.x * rpi + rl;
-  for (; r + stride < M; r += 2 * stride) {
-    V16 a = ldg16(x + r * C + cg * 8), b = ldg16(x + (r + stride) * C + cg * 8);
-    float fa[8], fb[8]; unpack8(a, fa); unpack8(b, fb);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[0][i] += fa[i] + fb[i]; acc[1][i] += fa[i] * fa[i] + fb[i] * fb[i]; }
-  }
-  for (; r < M; r += stride) {
-    V16 a = ldg16(x + r * C + cg * 8);
+  auto body = [&](const V16& a) {
     float fa[8]; unpack8(a, fa);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[0][i] += fa[i]; acc[1][i] += fa[i] * fa[i]; }
+    for (int i = 0; i < 8; ++i) { acc[0][i] += fa[i]; acc[1][i] = fmaf(fa[i], fa[i], acc[1][i]); }
+  };
+  for (; r + (2 * kU - 1) * stride < M; r += 2 * kU * stride) {
+    V16 v[2 * kU];
+#pragma unroll
+    for (int u = 0; u < 2 * kU; ++u) v[u] = ldg16(x + (r + u * stride) * C + cg * 8);
+#pragma unroll
+    for (int u = 0; u < 2 * kU; ++u) body(v[u]);
   }
+  for (; r < M; r += stride) body(ldg16(x + r * C + cg * 8));
   block_reduce_atomic<2>(acc, sums, C, G);
 }
 
@@ -164,13 +170,15 @@ k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     }
   }
   const long stride = (long)gridDim.x * rpi;
-  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
-    const size_t off = (size_t)r * C + cg * 8;
-    float f[8]; unpack8(ldg16(x + off), f);
+  // walk the rows from the END: the producer (conv / stats pass) touched the last rows most recently, so
+  // whatever part of x still sits in the 126 MB L2 is consumed before it is evicted
+  auto body = [&](long rr, const V16& vx, const V16& vr) {
+    const size_t off = (size_t)rr * C + cg * 8;
+    float f[8]; unpack8(vx, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
     if (res) {
-      float q[8]; unpack8(ldg16(res + off), q);
+      float q[8]; unpack8(vr, q);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] += q[i];
     }
@@ -179,9 +187,38 @@ k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 #pragma unroll
       for (int i = 0; i < 8; ++i) { bits |= (f[i] > 0.f ? 1u : 0u) << i; f[i] = fmaxf(f[i], 0.f); }
       // 1 bit per element for the backward pass: 16x less traffic than re-reading the activation
-      if (mask) mask[(size_t)r * G + cg] = (uint8_t)bits;
+      if (mask) mask[(size_t)rr * G + cg] = (uint8_t)bits;
     }
     stg16(out + off, pack8(f));
+  };
+  long r = (long)blockIdx.x * rpi + rl;
+  for (; r + (kU - 1) * stride < M; r += kU * stride) {
+    V16 vx[kU], vr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t off = (size_t)(M - 1 - (r + u * stride)) * C + cg * 8;
+      vx[u] = ldg16(x + off);
+      if (res) vr[u] = ldg16(res + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) body(M - 1 - (r + u * stride), vx[u], vr[u]);
+  }
+  for (; r < M; r += stride) {
+    const size_t off = (size_t)(M - 1 - r) * C + cg * 8;
+    V16 vr{}; if (res) vr = ldg16(res + off);
+    body(M - 1 - r, ldg16(x + off), vr);
+  }
+}
+
+DEVI void relu_gate(float* d, bool relu, bool has_mask, uint32_t bits, const V16& vo) {
+  if (!relu) return;
+  if (has_mask) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
+  } else {
+    float o[8]; unpack8(vo, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
   }
 }
 
@@ -192,29 +229,40 @@ k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __r
                 const float* __restrict__ invstd, float* __restrict__ sums, long M, int C, int relu,
                 const uint8_t* __restrict__ mask) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
-  float mu[8], is[8];
+  float mu[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
+  for (int i = 0; i < 8; ++i) mu[i] = mean[cg * 8 + i];
   float acc[2][8] = {};
   const long stride = (long)gridDim.x * rpi;
-  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
-    const size_t off = (size_t)r * C + cg * 8;
+  const bool use_out = relu && !mask;
+  auto body = [&](const V16& vd, const V16& vx, uint32_t bits, const V16& vo) {
     float d[8], xv[8];
-    unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
-    if (relu) {
-      if (mask) {
-        const uint32_t bits = mask[(size_t)r * G + cg];
+    unpack8(vd, d); unpack8(vx, xv);
+    relu_gate(d, relu, mask != nullptr, bits, vo);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
-      } else {
-        float o[8]; unpack8(ldg16(out + off), o);
+    for (int i = 0; i < 8; ++i) { acc[0][i] += d[i]; acc[1][i] = fmaf(d[i], xv[i] - mu[i], acc[1][i]); }
+  };
+  long r = (long)blockIdx.x * rpi + rl;
+  for (; r + (kU - 1) * stride < M; r += kU * stride) {
+    V16 vd[kU], vx[kU], vo[kU]; uint32_t mb[kU];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
-      }
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * stride;
+      const size_t off = (size_t)rr * C + cg * 8;
+      vd[u] = ldg16(dout + off); vx[u] = ldg16(x + off);
+      mb[u] = (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu;
+      if (use_out) vo[u] = ldg16(out + off);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[0][i] += d[i]; acc[1][i] += d[i] * (xv[i] - mu[i]) * is[i]; }
+    for (int u = 0; u < kU; ++u) body(vd[u], vx[u], mb[u], vo[u]);
   }
+  for (; r < M; r += stride) {
+    const size_t off = (size_t)r * C + cg * 8;
+    V16 vo{}; if (use_out) vo = ldg16(out + off);
+    body(ldg16(dout + off), ldg16(x + off), (relu && mask) ? mask[(size_t)r * G + cg] : 0xffu, vo);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[1][i] *= invstd[cg * 8 + i];       // xhat = (x - mean) * invstd, factored out of the loop
   block_reduce_atomic<2>(acc, sums, C, G);
 }
 
@@ -227,16 +275,17 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
                __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dgamma,
                __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu, int accum, const uint8_t* __restrict__ mask) {
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
-  float mu[8], is[8], k0[8], k1[8], k2[8];
+  float k0[8], k1[8], k2[8];
   const float invM = 1.f / (float)M;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cg * 8 + i;
-    mu[i] = mean[c]; is[i] = invstd[c];
+    const float mu = mean[c], is = invstd[c];
     const float g = __bfloat162float(gamma[c]), s1 = sums[c], s2 = sums[C + c];
-    k0[i] = g * is[i];                 // dz coefficient
-    k1[i] = -g * is[i] * s1 * invM;    // constant term
-    k2[i] = -g * is[i] * s2 * invM;    // xhat coefficient
+    // dx = g*is*dz + (-g*is*s2/M * is) * x + (-g*is*s1/M + g*is*s2/M * is * mu)
+    k0[i] = g * is;
+    k2[i] = -g * is * s2 * invM * is;
+    k1[i] = -g * is * s1 * invM - k2[i] * mu;
     if (blockIdx.x == 0 && rl == 0) {
       // accum: add straight into the parameter's .grad view (no separate AccumulateGrad kernel)
       dgamma[c] = __float2bfloat16_rn(s2 + (accum ? __bfloat162float(dgamma[c]) : 0.f));
@@ -244,34 +293,48 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
     }
   }
   const long stride = (long)gridDim.x * rpi;
-  for (long r = (long)blockIdx.x * rpi + rl; r < M; r += stride) {
-    const size_t off = (size_t)r * C + cg * 8;
+  const bool use_out = relu && !mask;
+  auto body = [&](long rr, const V16& vd, const V16& vx, uint32_t bits, const V16& vo) {
+    const size_t off = (size_t)rr * C + cg * 8;
     float d[8], xv[8];
-    unpack8(ldg16(dout + off), d); unpack8(ldg16(x + off), xv);
-    if (relu) {
-      if (mask) {
-        const uint32_t bits = mask[(size_t)r * G + cg];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = (bits >> i) & 1u ? d[i] : 0.f;
-      } else {
-        float o[8]; unpack8(ldg16(out + off), o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
-      }
-    }
+    unpack8(vd, d); unpack8(vx, xv);
+    relu_gate(d, relu, mask != nullptr, bits, vo);
     if (dres) stg16(dres + off, pack8(d));
     float g[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = fmaf(d[i], k0[i], fmaf((xv[i] - mu[i]) * is[i], k2[i], k1[i]));
+    for (int i = 0; i < 8; ++i) g[i] = fmaf(d[i], k0[i], fmaf(xv[i], k2[i], k1[i]));
     stg16(dx + off, pack8(g));
+  };
+  // reversed row order: the reduce pass that ran just before ended on the last rows, so they are the ones in L2
+  long r = (long)blockIdx.x * rpi + rl;
+  for (; r + (kU - 1) * stride < M; r += kU * stride) {
+    V16 vd[kU], vx[kU], vo[kU]; uint32_t mb[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long rr = M - 1 - (r + u * stride);
+      const size_t off = (size_t)rr * C + cg * 8;
+      vd[u] = ldg16(dout + off); vx[u] = ldg16(x + off);
+      mb[u] = (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu;
+      if (use_out) vo[u] = ldg16(out + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) body(M - 1 - (r + u * stride), vd[u], vx[u], mb[u], vo[u]);
+  }
+  for (; r < M; r += stride) {
+    const long rr = M - 1 - r;
+    const size_t off = (size_t)rr * C + cg * 8;
+    V16 vo{}; if (use_out) vo = ldg16(out + off);
+    body(rr, ldg16(dout + off), ldg16(x + off), (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu, vo);
   }
 }
 
+static int g_bn_blocks_per_sm = 4;
+extern "C" void sy_ops_set_bn_blocks_per_sm(int n) { if (n > 0 && n <= 8) g_bn_blocks_per_sm = n; }
 static inline int bn_grid(long M, int C) {
   const int rpi = 256 / (C / 8);
   long b = (M + rpi - 1) / rpi;
   b = (b + 3) / 4;                    // >= 4 rows per thread
-  if (b > 148 * 6) b = 148 * 6;
+  if (b > 148 * g_bn_blocks_per_sm) b = 148 * g_bn_blocks_per_sm;
   if (b < 1) b = 1;
   return (int)b;
 }

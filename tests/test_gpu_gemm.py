@@ -66,3 +66,63 @@ def test_conv1x1_and_linear_autograd():
     torch.testing.assert_close(yl.float(), ref, atol=0.08, rtol=2e-2)
     yl.sum().backward()
     torch.testing.assert_close(bl.grad.float(), torch.full((1000,), 33.0, device="cuda"), atol=0.5, rtol=1e-2)
+
+
+NN_SHAPES = [(256, 64, 64), (1000, 256, 64), (4096, 64, 256), (3000, 512, 128), (777, 128, 1000), (50176, 64, 256), (640, 2048, 512),
+             (256, 2048, 1000), (512, 192, 320)]
+
+
+@pytest.mark.parametrize("m,n,k", NN_SHAPES)
+def test_gemm_nn_mn_major_b(m, n, k):
+    """dgrad shape: B given as [K, N] row-major and consumed as an MN-major tcgen05 operand."""
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(m + 3 * n + k)
+    a = (torch.randn(m, k, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(k, n, device="cuda") * 0.5).to(torch.bfloat16)
+    out = gemm.gemm_nn(a, b)
+    ref = a.float() @ b.float()
+    torch.testing.assert_close(out.float(), ref, atol=0.02 * (k ** 0.5) * 0.25 + 0.02, rtol=2e-2)
+
+
+NT_SHAPES = [(256, 64, 64), (4096, 64, 256), (4096, 256, 64), (50176, 128, 512), (12544, 512, 2048), (12544, 2048, 512), (256, 2048, 1000),
+             (1000, 72, 200), (200704, 64, 64), (333, 128, 128)]
+
+
+@pytest.mark.parametrize("k,i,j", NT_SHAPES)
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_gemm_nt_wgrad_splitk(k, i, j, splits):
+    """wgrad shape: out[J, I] = B[K,J]^T A[K,I]; split-K with in-kernel finalisation; workspace must come back zeroed."""
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(k + i + j)
+    a = (torch.randn(k, i, device="cuda") * 0.25).to(torch.bfloat16)
+    b = (torch.randn(k, j, device="cuda") * 0.25).to(torch.bfloat16)
+    ref = b.float().t() @ a.float()
+    out = gemm.gemm_nt_wgrad(a, b, splits=splits)
+    tol = 0.01 * (k ** 0.5) * 0.0625 * 4 + 0.02
+    torch.testing.assert_close(out.float(), ref, atol=tol, rtol=2e-2)
+    ws, tickets = gemm._workspace(a.device)
+    assert float(ws.abs().max()) == 0.0 and int(tickets.abs().max()) == 0
+    # accumulate into an existing gradient buffer (run twice: workspace reuse across launches)
+    base = torch.randn(j, i, device="cuda").to(torch.bfloat16)
+    out2 = base.clone()
+    gemm.gemm_nt_wgrad(a, b, out=out2, accumulate=True, splits=splits)
+    torch.testing.assert_close(out2.float(), ref + base.float(), atol=tol + 0.05, rtol=3e-2)
+
+
+def test_conv1x1_wgrad_written_into_existing_grad():
+    """With a pre-existing .grad (the flat gradient buffer of the trainer) the kernels write into it directly."""
+    from batch_shipyard_b200.ops import gemm
+    import torch.nn.functional as F
+    torch.manual_seed(2)
+    x = torch.randn(8, 256, 14, 14, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    flat = torch.zeros(64 * 256, device="cuda", dtype=torch.bfloat16)
+    w = torch.nn.Parameter((torch.randn(64, 256, 1, 1, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    w.grad = flat.view(64, 1, 1, 256).permute(0, 3, 1, 2)
+    y, _ = gemm.conv1x1_nhwc(x, w, want_stats=False)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    F.conv2d(xr, wr).backward(g.float())
+    torch.testing.assert_close(flat.view(64, 256).float(), wr.grad.view(64, 256), atol=0.5, rtol=3e-2)
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.08, rtol=3e-2)
+    assert w.grad.data_ptr() == flat.data_ptr()
