@@ -40,6 +40,8 @@ def load() -> C.CDLL:
                                         C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_nt_splitk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_tn_rsag.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -267,4 +269,43 @@ def gemm_tn_allreduce(comm, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Ten
                                        C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
     if rc != 0:
         raise RuntimeError(f"sy_gemm_bf16_tn_allreduce failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out_sym
+
+
+def _comm_view(comm):
+    from . import coll as _coll
+    clib = _coll.load()
+    clib.sy_comm_device_view.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    clib.sy_comm_device_view.restype = C.c_size_t
+    size = clib.sy_comm_device_view(comm._h, None, 0)
+    view = (C.c_uint8 * size)()
+    clib.sy_comm_device_view(comm._h, view, size)
+    return view, size
+
+
+def gemm_tn_allreduce_bf16(comm, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Tensor, inbox: Optional[torch.Tensor] = None,
+                           block_n: int = 0) -> torch.Tensor:
+    """K10 v2: ``out_sym = sum_ranks(a_r @ b_r.T)`` in ONE kernel with a reduce-scatter / all-gather schedule and bf16 on
+    the wire: partial tiles are stored straight from TMEM into the owning rank's inbox over NVLink, the owner reduces in
+    fp32 and multicasts the bf16 result (multimem.st).  ``out_sym``: bf16 [M, N] from ``comm.alloc`` (no zeroing needed)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out_sym.dtype == torch.bfloat16
+    m, k = a.shape
+    n = b.shape[0]
+    assert tuple(out_sym.shape) == (m, n) and out_sym.is_contiguous() and _rows_ok(a) and _rows_ok(b) and n % 8 == 0
+    lib = load()
+    view, size = _comm_view(comm)
+    rpr = C.c_int(0)
+    lib.sy_gemm_bf16_tn_rsag(view, size, None, None, 0, 0, m, n, k, 8, 8, block_n, C.byref(rpr), None)
+    need = comm.world * rpr.value * n
+    if inbox is None:
+        cache = comm.__dict__.setdefault("_k10_inbox", {})
+        inbox = cache.get(need)
+        if inbox is None:
+            inbox = cache[need] = comm.alloc(need, torch.bfloat16)
+    assert inbox.dtype == torch.bfloat16 and inbox.numel() >= need
+    rc = lib.sy_gemm_bf16_tn_rsag(view, size, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), comm.heap_offset(inbox),
+                                  comm.heap_offset(out_sym), m, n, k, a.stride(0), b.stride(0), block_n, C.byref(rpr),
+                                  C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_gemm_bf16_tn_rsag failed ({rc}): {lib.sy_gemm_last_error().decode()}")
     return out_sym

@@ -7,9 +7,7 @@ timeout 200 python -m pytest tests/test_gpu_ops.py tests/test_hpcg.py -m gpu -x 
 timeout 200 python bench/wgrad_bench.py 2>&1 | tee gpurun_out/wgrad_bench6.log
 timeout 200 python bench/bn_bench.py 2>&1 | tee gpurun_out/bn_bench6.log
 timeout 120 python bench/bn_bench.py --blocks-per-sm 2 2>&1 | tail -1 | tee -a gpurun_out/bn_bench6.log
-timeout 120 python bench/bn_bench.py --blocks-per-sm 8 2>&1 | tail -1 | tee -a gpurun_out/bn_bench6.log
 timeout 300 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench6_n1.log
-SHIPYARD_NO_TC_GEMM=1 timeout 300 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench6_n1_notc.log
 timeout 200 python recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --n 128 --t 5 2>&1 | tail -2 | tee gpurun_out/hpcg6_n1.log
 # ncu: one capture of the top kernels (BN backward pair + forward) on the largest layer shape, full set, for profiles/
 cat > /tmp/bn_one.py <<'PY'

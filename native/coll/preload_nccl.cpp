@@ -36,10 +36,28 @@ std::atomic<unsigned long long> g_hit{0}, g_fwd{0};
 bool g_disable = false, g_stats = false;
 size_t g_min_bytes = 0;
 
-template <typename F> F real(const char* name) {
-  return reinterpret_cast<F>(dlsym(RTLD_NEXT, name));
+// The real NCCL may sit in the global scope (linked / RTLD_GLOBAL: found by RTLD_NEXT) or only in a local scope
+// (a DT_NEEDED of a dlopen'ed extension module, as with PyTorch wheels): then RTLD_NEXT cannot see it and we ask the
+// loader for the already-loaded object by soname (RTLD_NOLOAD never loads anything new).
+void* real_handle() {
+  static std::atomic<void*> h{nullptr};
+  void* cur = h.load();
+  if (cur) return cur;
+  for (const char* so : {"libnccl.so.2", "libnccl.so"}) {
+    if (void* x = dlopen(so, RTLD_NOLOAD | RTLD_NOW | RTLD_LOCAL)) {
+      if (dlsym(x, "shipyard_preload_hits") == nullptr) { h.store(x); return x; }   // not ourselves under an alias
+    }
+  }
+  return nullptr;
 }
-bool have_real() { static bool h = dlsym(RTLD_NEXT, "ncclCommInitRank") != nullptr; return h; }
+void* real_sym(const char* name) {
+  if (void* f = dlsym(RTLD_NEXT, name)) return f;
+  if (void* h = real_handle()) return dlsym(h, name);
+  return nullptr;
+}
+template <typename F> F real(const char* name) { return reinterpret_cast<F>(real_sym(name)); }
+bool have_real() { return real_sym("ncclCommInitRank") != nullptr; }
+std::map<void*, bool> g_native;          // communicators created by the shim itself (guarded by g_mu)
 
 struct Init {
   Init() {
@@ -78,7 +96,7 @@ sy_comm* bind(ncclComm_t comm) {
   e.tried = true;
   int world = 0, rank = 0, dev = 0;
   std::string base;
-  if (have_real()) {
+  if (!g_native.count((void*)comm) && have_real()) {
     auto cnt = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCount");
     auto urk = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommUserRank");
     auto cud = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCuDevice");
@@ -87,6 +105,7 @@ sy_comm* bind(ncclComm_t comm) {
     const char* p = getenv("MASTER_PORT");
     base = std::string(s && *s ? s : "nccl") + "-" + (p ? p : "0");
   } else {
+    if (!g_native.count((void*)comm)) return nullptr;               // not ours and no NCCL to ask: never guess
     Native* n = reinterpret_cast<Native*>(comm);
     world = n->world; rank = n->rank; dev = n->device; base = n->session;
   }
@@ -101,6 +120,8 @@ sy_comm* bind(ncclComm_t comm) {
   e.sy = c; e.world = world;
   return c;
 }
+
+bool is_native(const void* comm) { std::lock_guard<std::mutex> lk(g_mu); return g_native.count(const_cast<void*>(comm)) > 0; }
 
 }  // namespace
 
@@ -192,6 +213,7 @@ ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId id, int
   n->rank = rank; n->world = nranks; n->session = std::string(id.internal, strnlen(id.internal, sizeof id.internal));
   cudaGetDevice(&n->device);
   *comm = reinterpret_cast<ncclComm_t>(n);
+  { std::lock_guard<std::mutex> lk(g_mu); g_native[(void*)n] = true; }
   return ncclSuccess;
 }
 
@@ -201,21 +223,23 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm) {
     auto it = g_comms.find((void*)comm);
     if (it != g_comms.end()) { if (it->second.sy) sy_comm_destroy(it->second.sy); g_comms.erase(it); }
   }
+  bool native = false;
+  { std::lock_guard<std::mutex> lk(g_mu); native = g_native.erase((void*)comm) > 0; }
+  if (native) { delete reinterpret_cast<Native*>(comm); return ncclSuccess; }
   if (auto f = real<ncclResult_t (*)(ncclComm_t)>("ncclCommDestroy")) return f(comm);
-  delete reinterpret_cast<Native*>(comm);
-  return ncclSuccess;
+  return ncclInvalidArgument;
 }
 
 ncclResult_t ncclCommCount(const ncclComm_t comm, int* count) {
-  if (auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCount")) return f(comm, count);
+  if (!is_native(comm)) { auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCount"); return f ? f(comm, count) : ncclInvalidArgument; }
   *count = reinterpret_cast<Native*>(comm)->world; return ncclSuccess;
 }
 ncclResult_t ncclCommUserRank(const ncclComm_t comm, int* rank) {
-  if (auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommUserRank")) return f(comm, rank);
+  if (!is_native(comm)) { auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommUserRank"); return f ? f(comm, rank) : ncclInvalidArgument; }
   *rank = reinterpret_cast<Native*>(comm)->rank; return ncclSuccess;
 }
 ncclResult_t ncclCommCuDevice(const ncclComm_t comm, int* dev) {
-  if (auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCuDevice")) return f(comm, dev);
+  if (!is_native(comm)) { auto f = real<ncclResult_t (*)(const ncclComm_t, int*)>("ncclCommCuDevice"); return f ? f(comm, dev) : ncclInvalidArgument; }
   *dev = reinterpret_cast<Native*>(comm)->device; return ncclSuccess;
 }
 ncclResult_t ncclGroupStart() { if (auto f = real<ncclResult_t (*)()>("ncclGroupStart")) return f(); return ncclSuccess; }

@@ -620,6 +620,214 @@ gemm_bf16_tn_allreduce_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   epoch_store(comm, ep);
 }
 
+// ===================================================================================================
+// K10 v2: GEMM + all-reduce with a reduce-scatter / all-gather schedule and bf16 on the wire.
+// The multimem.red version above makes every GPU receive N full-size fp32 contributions (ingress = N x |C|),
+// which is NVLink-bound at 8 GPUs.  Here every output row-block has an OWNER rank:
+//   phase 1  mainloop + epilogue: each rank's partial tile goes (bf16, plain 128 B P2P stores straight from the
+//            TMEM read-back, overlapped with the next tile's MMAs) into inbox[src] on the tile's owner
+//            -> ingress per GPU = (N-1)/N x |C| x 2 B
+//   barrier  cross-GPU flag barrier per CTA + a local grid barrier (all CTAs of all ranks have published)
+//   phase 2  the owner sums its N inbox slices in fp32 and multicasts the bf16 result to every GPU with
+//            multimem.st (P2P stores when NVLS is unavailable) -> ingress per GPU = (N-1)/N x |C| x 2 B
+//   barrier  so nobody's kernel completes before its copy of C is complete.
+// One launch, no partial C in the local HBM, fp32 accumulation of the cross-rank sum.
+// ===================================================================================================
+__device__ unsigned g_gb_count = 0;
+__device__ unsigned g_gb_gen = 0;
+
+DEVI void grid_barrier(const CommDev& c) {          // all CTAs are co-resident (persistent grid <= #SMs, 1 CTA/SM)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&g_gb_gen) : "memory");
+    __threadfence();
+    if (atomicAdd(&g_gb_count, 1u) == gridDim.x - 1) {
+      g_gb_count = 0;
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_gb_gen) : "memory");
+    } else {
+      unsigned cur, it = 0; unsigned long long t0 = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&g_gb_gen) : "memory");
+        if (((++it) & 0x3ff) == 0) {
+          const unsigned long long t = globaltimer_ns();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > c.timeout_ns) { *reinterpret_cast<volatile uint32_t*>(c.status) = SY_ERR_TIMEOUT; __threadfence_system(); break; }
+        }
+      } while (cur == gen);
+    }
+  }
+  __syncthreads();
+}
+DEVI void st_global_v4(void* p, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+DEVI void mc_st_v4(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CommDev comm, size_t inbox_off, size_t out_off, int M, int N, int K, int rows_per_rank) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + 2 * C::kCBytes);
+  uint64_t* full_bar = bars; uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages; uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
+  const int num_tiles = num_m * num_n;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile order: owners interleaved (tile t -> owner t % world first), so at any moment the CTAs of one rank push to
+  // all peers at once instead of all hammering the same owner's NVLink port
+  const int m_per_rank = rows_per_rank / BM;
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+    const int per_owner = m_per_rank * num_n;                 // tiles per owner (owners past the matrix edge own fewer)
+    const int o = t % comm.world, q = t / comm.world;
+    // rotate by my rank so rank r starts on owner r+1 (spreads the first wave)
+    const int owner = (o + comm.rank + 1) % comm.world;
+    m_blk = owner * m_per_rank + q / num_n; n_blk = q % num_n;
+    (void)per_owner;
+  };
+  const int virt_tiles = m_per_rank * num_n * comm.world;     // includes tiles past M (skipped)
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < virt_tiles; t += gridDim.x) {
+        int m_blk, n_blk; tile_coords(t, m_blk, n_blk);
+        if (m_blk >= num_m) continue;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < virt_tiles; t += gridDim.x) {
+        int m_blk, n_blk; tile_coords(t, m_blk, n_blk);
+        if (m_blk >= num_m) continue;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < virt_tiles; t += gridDim.x) {
+      int m_blk, n_blk; tile_coords(t, m_blk, n_blk);
+      if (m_blk >= num_m) continue;
+      const int owner = m_blk / m_per_rank;
+      const int grow = m_blk * BM + row;
+      // inbox on the owner: [src rank][local row][N] bf16
+      __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(comm.heap[owner] + inbox_off) +
+                               ((size_t)comm.rank * rows_per_rank + (size_t)(grow - owner * rows_per_rank)) * N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / kEpiChunk; ++c) {
+        uint32_t v[2][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * kEpiChunk);
+        tmem_ld32(taddr, v[0]);
+        tmem_ld32(taddr + 32, v[1]);
+        tmem_ld_wait();
+        if (c == BN / kEpiChunk - 1) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+        const int n0 = n_blk * BN + c * kEpiChunk;
+        if (grow < M) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {          // 8 x 16 B = one full 128 B line of this thread's row
+            if (n0 + q * 8 < N) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
+              st_global_v4(dst_row + n0 + q * 8, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    __threadfence_system();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<C::kTmemCols>(tmem_base); }
+
+  uint32_t ep = epoch_load(comm);
+  block_barrier(comm, ep);          // CTA b of every rank has published its partial tiles
+  grid_barrier(comm);               // ... and so have all my sibling CTAs => every contribution to my rows is in my inbox
+
+  // ---- phase 2: reduce my rows over the N inbox slices (fp32) and multicast the bf16 result ----
+  const int my_row0 = comm.rank * rows_per_rank;
+  int my_rows = M - my_row0; if (my_rows > rows_per_rank) my_rows = rows_per_rank; if (my_rows < 0) my_rows = 0;
+  const int vec_per_row = N / 8;
+  const long total = (long)my_rows * vec_per_row;
+  const __nv_bfloat16* inbox = reinterpret_cast<const __nv_bfloat16*>(comm.heap[comm.rank] + inbox_off);
+  for (long idx = (long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long)gridDim.x * kThreads) {
+    const int r = (int)(idx / vec_per_row), c8 = (int)(idx % vec_per_row);
+    float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint4 in[SY_MAXR];
+#pragma unroll
+    for (int src = 0; src < SY_MAXR; ++src)
+      if (src < comm.world) in[src] = __ldcg(reinterpret_cast<const uint4*>(inbox + ((size_t)src * rows_per_rank + r) * N + c8 * 8));
+#pragma unroll
+    for (int src = 0; src < SY_MAXR; ++src) {
+      if (src < comm.world) {
+        const uint32_t w[4] = {in[src].x, in[src].y, in[src].z, in[src].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc8[2 * i] += __uint_as_float(w[i] << 16); acc8[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u); }
+      }
+    }
+    const uint4 o = make_uint4(pack_bf16(acc8[0], acc8[1]), pack_bf16(acc8[2], acc8[3]), pack_bf16(acc8[4], acc8[5]), pack_bf16(acc8[6], acc8[7]));
+    const size_t eoff = out_off + ((size_t)(my_row0 + r) * N + c8 * 8) * 2;
+    if (comm.mc) mc_st_v4(comm.mc + eoff, o);                 // one store, delivered to every GPU by the switch
+    else {
+      for (int p = 0; p < comm.world; ++p) st_global_v4(comm.heap[p] + eoff, o);
+    }
+  }
+  __threadfence_system();
+  block_barrier(comm, ep);          // my copy of C is complete once every rank's CTA b has finished multicasting
+  epoch_store(comm, ep);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -702,6 +910,48 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
     case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// K10 v2: out (bf16 [M,N], symmetric, dense) = sum over ranks of A_r x B_r^T.  inbox: symmetric bf16 scratch of
+// world * rows_per_rank * N elements, rows_per_rank = ceil(ceil(M/128) / world) * 128 (returned through *rows_per_rank_out
+// when the pointers are null, so callers can size it).
+extern "C" int sy_gemm_bf16_tn_rsag(const void* comm_view, size_t comm_view_bytes, const void* A, const void* B, size_t inbox_off,
+                                    size_t out_off, int M, int N, int K, int lda, int ldb, int block_n, int* rows_per_rank_out, void* stream) {
+  if (comm_view_bytes != sizeof(CommDev)) { snprintf(g_err, sizeof g_err, "communicator view size mismatch"); return 1; }
+  CommDev cd; memcpy(&cd, comm_view, sizeof cd);
+  const int num_m = (M + BM - 1) / BM;
+  const int rpr = ((num_m + cd.world - 1) / cd.world) * BM;
+  if (rows_per_rank_out) *rows_per_rank_out = rpr;
+  if (!A || !B) return 0;                                    // size query
+  if ((lda | ldb) & 7 || (N & 7) || ((uintptr_t)A | (uintptr_t)B) & 15 || ((inbox_off | out_off) & 15)) {
+    snprintf(g_err, sizeof g_err, "alignment: A/B 16B aligned, lda/ldb/N %% 8, offsets %% 16"); return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable"); return 6; }
+  if (block_n <= 0) block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto go = [&](auto kern, int BN, int smem) -> int {
+    CUtensorMap ta, tb;
+    if (!make_map(&ta, A, K, M, lda, BK, BM) || !make_map(&tb, B, K, N, ldb, BK, BN)) return 3;
+    const int tiles = (rpr / BM) * cd.world * ((N + BN - 1) / BN);
+    int grid = tiles < sms ? tiles : sms;
+    if (grid > SY_MAX_BLOCKS) grid = SY_MAX_BLOCKS;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, cd, inbox_off, out_off, M, N, K, rpr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  switch (block_n) {
+    case 64: return go(gemm_bf16_tn_rsag_kernel<64>, 64, Cfg<64>::kSmemBytes);
+    case 128: return go(gemm_bf16_tn_rsag_kernel<128>, 128, Cfg<128>::kSmemBytes);
+    case 256: return go(gemm_bf16_tn_rsag_kernel<256>, 256, Cfg<256>::kSmemBytes);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

@@ -41,7 +41,10 @@ def test_nccl_preload_shim_under_torch_distributed():
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", "29577", os.path.join(root, "tests", "_preload_worker.py")], env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout[-4000:]
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "preload_test.log"), "w") as f:
+        f.write(p.stdout)
+    assert p.returncode == 0, p.stdout[-6000:]
     assert p.stdout.count("ok=True") == world
 
 
