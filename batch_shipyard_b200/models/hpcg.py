@@ -183,30 +183,66 @@ class HPCG:
         return b
 
     # -- CG -----------------------------------------------------------------------------------------------
-    def cg(self, b: torch.Tensor, x: torch.Tensor, iters: int = 50, precondition: bool = True) -> list[float]:
+    def _cg_state(self, b: torch.Tensor):
+        if getattr(self, "_st", None) is None or self._st["p"].shape != b.shape:
+            z = lambda n=b.numel(): torch.zeros(n, dtype=torch.float64, device=self.dev)  # noqa: E731
+            self._st = {"p": z(), "z": z(), "rtz_old": z(1), "rnorm2": z(1)}
+            self._graph = None
+        return self._st
+
+    def _cg_step(self, x: torch.Tensor, precondition: bool) -> None:
+        """One CG iteration with every scalar kept on the device (no host sync: the step is CUDA-graph capturable)."""
+        L, st = self.levels[0], self._st
+        r, ap, p, z = L.r, L.ax, st["p"], st["z"]
+        if precondition:
+            self.mg(0, r, z)
+        else:
+            z.copy_(r)
+        rtz = self.dot(r, z)
+        p.mul_(rtz / st["rtz_old"]).add_(z)             # first iteration: rtz_old = inf -> beta = 0 -> p = z
+        st["rtz_old"].copy_(rtz)
+        self.spmv(0, p, ap)
+        alpha = rtz / self.dot(p, ap)
+        x.add_(p * alpha)
+        r.sub_(ap * alpha)
+        st["rnorm2"].copy_(self.dot(r, r))
+
+    def cg(self, b: torch.Tensor, x: torch.Tensor, iters: int = 50, precondition: bool = True, graph: Optional[bool] = None) -> list[float]:
+        """Returns the residual-norm history (eager mode) or [initial, final] (graph mode: two iterations per replay so
+        every level does an even number of halo exchanges and the ghost-buffer parity returns to where it started)."""
         L = self.levels[0]
-        r, z, p, ap = L.r, L.x, torch.zeros_like(b), L.ax
+        st = self._cg_state(b)
+        r, ap = L.r, L.ax
+        use_graph = (self.cuda and precondition and iters % 2 == 0 and iters >= 4) if graph is None else (graph and self.cuda)
         self.spmv(0, x, ap)
-        r.copy_(b - ap)
+        torch.sub(b, ap, out=r)
+        st["p"].zero_(); st["rtz_old"].fill_(float("inf"))
         norms = [float(self.dot(r, r).sqrt())]
-        rtz_old = None
-        zz = torch.zeros_like(b)
-        for k in range(iters):
-            if precondition:
-                self.mg(0, r, zz)
-            else:
-                zz.copy_(r)
-            rtz = self.dot(r, zz)
-            if k == 0:
-                p.copy_(zz)
-            else:
-                p.mul_(rtz / rtz_old).add_(zz)
-            rtz_old = rtz
-            self.spmv(0, p, ap)
-            alpha = rtz / self.dot(p, ap)
-            x.add_(p * alpha)
-            r.sub_(ap * alpha)
-            norms.append(float(self.dot(r, r).sqrt()))
+        if not use_graph:
+            for _ in range(iters):
+                self._cg_step(x, precondition)
+                norms.append(float(st["rnorm2"].sqrt()))
+            return norms
+        key = (b.data_ptr(), x.data_ptr())
+        done = 0
+        if self._graph is None or self._graph_key != key:
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):               # warm-up outside capture (allocator, lazy module loads)
+                self._cg_step(x, True); self._cg_step(x, True)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            self._sync()
+            done = 2
+            self._graph = torch.cuda.CUDAGraph()
+            l0 = self._launches()
+            with torch.cuda.graph(self._graph):
+                self._cg_step(x, True); self._cg_step(x, True)
+            self._graph_launches = self._launches() - l0        # our kernels inside one replay (2 iterations)
+            self._graph_key = key
+        while done < iters:
+            self._graph.replay(); done += 2
+            self._replays = getattr(self, "_replays", 0) + 1
+        norms.append(float(st["rnorm2"].sqrt()))
         return norms
 
     def flops_per_iteration(self) -> float:
@@ -225,7 +261,7 @@ class HPCG:
         norms = self.cg(b, x, iters=min(10, iters_per_set))            # warm-up + validity
         self._sync(); self.comm.barrier(); self._sync()
         t0 = time.time(); sets = 0; total_iters = 0
-        l0 = self._launches()
+        l0 = self._launches(); r0 = getattr(self, "_replays", 0) * getattr(self, "_graph_launches", 0)
         while True:
             x.zero_()
             norms = self.cg(b, x, iters=iters_per_set)
@@ -244,5 +280,7 @@ class HPCG:
         self.comm.check_status()
         return {"gflops": self.flops_per_iteration() * total_iters / dt / 1e9, "seconds": dt, "cg_sets": sets, "iterations": total_iters,
                 "residual_reduction": norms[-1] / max(norms[0], 1e-300), "max_error_vs_ones": err, "world": self.world,
-                "local_grid": [self.levels[0].nx, self.levels[0].ny, self.levels[0].nz], "own_kernel_launches": self._launches() - l0,
+                "local_grid": [self.levels[0].nx, self.levels[0].ny, self.levels[0].nz],
+                "own_kernel_launches": self._launches() - l0 + getattr(self, "_replays", 0) * getattr(self, "_graph_launches", 0) - r0,
+                "cuda_graph": bool(getattr(self, "_graph", None) is not None),
                 "transport": self.comm.transport}

@@ -36,11 +36,15 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--bps3", default="", help="stats,fwd,bwd blocks per SM")
+    ap.add_argument("--big-only", action="store_true", help="only the layers large enough not to be host-launch bound")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = fused.load()
     if a.blocks_per_sm:
         lib.sy_ops_set_bn_blocks_per_sm(a.blocks_per_sm)
+    if a.bps3:
+        lib.sy_ops_set_bn_blocks_per_sm3(*[int(v) for v in a.bps3.split(",")])
     peak = 6583.8
     try:
         peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -48,6 +52,8 @@ def main():
         pass
     tot = {"fwd": 0.0, "bwd": 0.0, "fwd_ideal": 0.0, "bwd_ideal": 0.0}
     for hw, c in SHAPES:
+        if a.big_only and hw * hw * c * a.batch * 2 < 100e6:
+            continue
         n = a.batch
         numel = n * hw * hw * c
         nbytes = numel * 2
@@ -86,7 +92,7 @@ def main():
         del sets
         torch.cuda.empty_cache()
     print(json.dumps({"sum_fwd_us": round(tot["fwd"], 1), "sum_bwd_us": round(tot["bwd"], 1), "ideal_fwd_us": round(tot["fwd_ideal"], 1),
-                      "ideal_bwd_us": round(tot["bwd_ideal"], 1), "hbm_gbs_measured": peak, "blocks_per_sm": a.blocks_per_sm or 4}))
+                      "ideal_bwd_us": round(tot["bwd_ideal"], 1), "hbm_gbs_measured": peak, "blocks_per_sm": a.bps3 or a.blocks_per_sm or "default"}))
 
 
 if __name__ == "__main__":

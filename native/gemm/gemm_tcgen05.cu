@@ -442,18 +442,18 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         if (c == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
         const int j0 = n_blk * BN + c * 32;
         if (i < I) {
+          if (splits == 1) {              // whole K in this CTA: write the gradient directly (a warp covers 64 contiguous bytes)
+            float prev[32];
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = j0 + jj;
-            if (j < J) {
-              const float val = __uint_as_float(v[jj]);
-              if (splits == 1) {          // whole K in this CTA: write the gradient directly (a warp covers 64 contiguous bytes)
-                __nv_bfloat16* o = out + (size_t)j * ldo + i;
-                *o = __float2bfloat16_rn(val + (accumulate ? __bfloat162float(*o) : 0.f));
-              } else {
-                red_add_f32(ws + (size_t)j * I + i, val);   // one 128 B line per warp instruction
-              }
-            }
+            for (int jj = 0; jj < 32; ++jj)          // all read-modify-write loads first: one memory round trip, not 32
+              prev[jj] = (accumulate && j0 + jj < J) ? __bfloat162float(out[(size_t)(j0 + jj) * ldo + i]) : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (j0 + jj < J) out[(size_t)(j0 + jj) * ldo + i] = __float2bfloat16_rn(__uint_as_float(v[jj]) + prev[jj]);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (j0 + jj < J) red_add_f32(ws + (size_t)(j0 + jj) * I + i, __uint_as_float(v[jj]));   // one 128 B line per warp instruction
           }
         }
       }
@@ -464,16 +464,34 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         named_bar_sync(2, kEpiThreads);
         if (*s_last) {                                      // every K-split of this tile has been added: finalise it
           __threadfence();
-          const int ii = m_blk * BM + et;
+          // thread -> 4 consecutive i (16 B of fp32) x every 4th column; kFin loads in flight per thread so the
+          // L2 round trips overlap instead of serialising (I % 8 == 0, so a 4-wide group is all-in or all-out)
+          constexpr int kFin = 8;
+          const int ii = m_blk * BM + (et & 31) * 4, jsub = et >> 5;
           if (ii < I) {
-            for (int jj = 0; jj < BN; ++jj) {
-              const int j = n_blk * BN + jj;
-              if (j >= J) break;
-              float* wp = ws + (size_t)j * I + ii;
-              const float val = __ldcg(wp);
-              __stcg(wp, 0.f);
-              __nv_bfloat16* o = out + (size_t)j * ldo + ii;
-              *o = __float2bfloat16_rn(val + (accumulate ? __bfloat162float(*o) : 0.f));
+            for (int jb = 0; jb < BN / 4; jb += kFin) {
+              float4 acc4[kFin]; uint2 prev[kFin];
+#pragma unroll
+              for (int u = 0; u < kFin; ++u) {
+                const int j = n_blk * BN + jsub + 4 * (jb + u);
+                if (j < J) {
+                  acc4[u] = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)j * I + ii));
+                  if (accumulate) prev[u] = *reinterpret_cast<const uint2*>(out + (size_t)j * ldo + ii);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < kFin; ++u) {
+                const int j = n_blk * BN + jsub + 4 * (jb + u);
+                if (j < J) {
+                  float4 a = acc4[u];
+                  if (accumulate) {
+                    a.x += __uint_as_float(prev[u].x << 16); a.y += __uint_as_float(prev[u].x & 0xffff0000u);
+                    a.z += __uint_as_float(prev[u].y << 16); a.w += __uint_as_float(prev[u].y & 0xffff0000u);
+                  }
+                  __stcg(reinterpret_cast<float4*>(ws + (size_t)j * I + ii), make_float4(0.f, 0.f, 0.f, 0.f));
+                  *reinterpret_cast<uint2*>(out + (size_t)j * ldo + ii) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+                }
+              }
             }
           }
           if (et == 0) tickets[tile] = 0;
@@ -983,8 +1001,8 @@ extern "C" int sy_gemm_bf16_nn(const void* A, const void* B, void* C, int M, int
 extern "C" int sy_gemm_bf16_nt_splitk(const void* A, const void* B, void* out, int I, int J, int K, int lda, int ldb, int ldo,
                                       float* ws, int* tickets, int accumulate, int block_n, int splits, void* stream) {
   if (I <= 0 || J <= 0 || K <= 0) return 0;
-  if ((lda | ldb) & 7 || ((uintptr_t)A | (uintptr_t)B) & 15) {
-    snprintf(g_err, sizeof g_err, "alignment: A/B 16B aligned and lda/ldb multiples of 8"); return 1;
+  if ((lda | ldb) & 7 || ((uintptr_t)A | (uintptr_t)B) & 15 || (ldo & 3) || ((uintptr_t)out & 7) || (I & 7)) {
+    snprintf(g_err, sizeof g_err, "alignment: A/B 16B aligned, lda/ldb/I multiples of 8, out 8B aligned with ldo %% 4"); return 1;
   }
   if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
   if (block_n <= 0) block_n = J > 128 ? 256 : (J > 64 ? 128 : 64);

@@ -141,7 +141,7 @@ k_bn_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long M
 }
 
 // out = act(gamma * (x - mean) * invstd + beta [+ res]); also finalises mean/invstd and running stats
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // <= 85 registers: three resident blocks = 48 KB of loads in flight per SM
 k_bn_apply_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                __nv_bfloat16* __restrict__ out, const float* __restrict__ sums,
                const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
@@ -328,9 +328,16 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
   }
 }
 
-static int g_bn_blocks_per_sm = 4;
-extern "C" void sy_ops_set_bn_blocks_per_sm(int n) { if (n > 0 && n <= 8) g_bn_blocks_per_sm = n; }
-static inline int bn_grid(long M, int C) {
+// blocks per SM: [0] stats (43 regs), [1] forward apply (88 regs), [2] backward reduce / apply (114 regs: 2 resident)
+static int g_bn_bps[3] = {5, 3, 2};   // = resident blocks per SM of each kernel: exactly one wave
+extern "C" void sy_ops_set_bn_blocks_per_sm(int n) { if (n > 0 && n <= 8) g_bn_bps[0] = g_bn_bps[1] = g_bn_bps[2] = n; }
+extern "C" void sy_ops_set_bn_blocks_per_sm3(int stats, int fwd, int bwd) {
+  if (stats > 0 && stats <= 8) g_bn_bps[0] = stats;
+  if (fwd > 0 && fwd <= 8) g_bn_bps[1] = fwd;
+  if (bwd > 0 && bwd <= 8) g_bn_bps[2] = bwd;
+}
+static inline int bn_grid(long M, int C, int which = 1) {
+  const int g_bn_blocks_per_sm = g_bn_bps[which];
   const int rpi = 256 / (C / 8);
   long b = (M + rpi - 1) / rpi;
   b = (b + 3) / 4;                    // >= 4 rows per thread
@@ -351,8 +358,8 @@ extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const vo
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
-  const int g = bn_grid(M, C);
-  k_bn_stats<<<g, 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, C);
+  const int g = bn_grid(M, C, 1);
+  k_bn_stats<<<bn_grid(M, C, 0), 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, C);
   COUNT_LAUNCH();
   k_bn_apply_fwd<<<g, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, ws,
                                    (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, running_mean, running_var,
@@ -380,7 +387,7 @@ extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, c
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
-  const int g = bn_grid(M, C);
+  const int g = bn_grid(M, C, 2);
   k_bn_bwd_reduce<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
                                     ws, M, C, relu, (const uint8_t*)mask);
   COUNT_LAUNCH();
