@@ -42,6 +42,7 @@ def load() -> C.CDLL:
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_tn_rsag.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -309,3 +310,86 @@ def gemm_tn_allreduce_bf16(comm, a: torch.Tensor, b: torch.Tensor, out_sym: torc
     if rc != 0:
         raise RuntimeError(f"sy_gemm_bf16_tn_rsag failed ({rc}): {lib.sy_gemm_last_error().decode()}")
     return out_sym
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Convolution as implicit GEMM (TMA im2col loads feeding tcgen05; no im2col buffer)
+# ---------------------------------------------------------------------------------------------------------
+def _nhwc_storage(t: torch.Tensor) -> torch.Tensor:
+    """[N,C,H,W] channels_last tensor -> its dense [N,H,W,C] storage view (copy only if it is not channels_last)."""
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def conv_supported(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> bool:
+    n, cin, h, wd = x.shape
+    cout, _, r, s = w.shape
+    p, q = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - s) // stride + 1
+    return (x.is_cuda and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 8 == 0 and (n * p * q) % 128 == 0)
+
+
+def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 1, stats: Optional[torch.Tensor] = None,
+                    block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """y = conv2d(x, w) for channels_last bf16 x[N,Cin,H,W], w[Cout,Cin,R,S] (stored KRSC); returns channels_last y."""
+    n, cin, h, wd = x.shape
+    cout, _, r, s = w.shape
+    p, q = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - s) // stride + 1
+    xs, ws = _nhwc_storage(x), _nhwc_storage(w)
+    y = torch.empty((n, p, q, cout), dtype=torch.bfloat16, device=x.device)
+    lib = load()
+    rc = lib.sy_conv_bf16_nhwc(C.c_void_p(xs.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, cin, cout, r, s,
+                               pad, stride, 0, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
+                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_conv_bf16_nhwc fprop failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return y.permute(0, 3, 1, 2)
+
+
+def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, pad: int = 1, block_n: int = 0) -> torch.Tensor:
+    """dx of a stride-1 'same' convolution: implicit GEMM over dY with the weights read in place (rotated by tap index,
+    transposed by reading them as an MN-major operand)."""
+    n, cout, p, q = dy.shape
+    _, cin, r, s = w.shape
+    dys, ws = _nhwc_storage(dy), _nhwc_storage(w)
+    dx = torch.empty((n, p, q, cin), dtype=torch.bfloat16, device=dy.device)
+    lib = load()
+    rc = lib.sy_conv_bf16_nhwc(C.c_void_p(dys.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(dx.data_ptr()), n, p, q, cout, cin, r, s,
+                               pad, 1, 1, None, block_n, 0, C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_conv_bf16_nhwc dgrad failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return dx.permute(0, 3, 1, 2)
+
+
+class _ConvNHWC(torch.autograd.Function):
+    """KxK convolution on channels_last bf16 activations: fprop (+ BN statistics) and stride-1 dgrad on the tcgen05
+    implicit-GEMM kernel; wgrad through cuDNN for now."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad, want_stats):
+        cout = w.shape[0]
+        stats = torch.zeros(2 * cout, dtype=torch.float32, device=x.device) if want_stats else None
+        y = conv_fprop_nhwc(x, w, stride, pad, stats=stats)
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.pad = stride, pad
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[0]:
+            if ctx.stride == 1 and dy.shape[1] % 64 == 0 and dy.shape[2:] == x.shape[2:]:
+                dx = conv_dgrad_nhwc(dy, w, ctx.pad)
+            else:
+                dx = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=ctx.stride, padding=ctx.pad)
+        if ctx.needs_input_grad[1]:
+            dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=ctx.stride, padding=ctx.pad)
+        return dx, dw, None, None, None
+
+
+def conv_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 1, want_stats: bool = False):
+    return _ConvNHWC.apply(x, w, stride, pad, want_stats)

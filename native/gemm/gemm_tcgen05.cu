@@ -74,6 +74,18 @@ DEVI void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// im2col-mode load (4D NHWC activation): `pixels` consecutive base pixels starting at (w, h, n), walking W then H then N
+// inside the descriptor's bounding box, `channels` wide from channel c; (off_w, off_h) is the filter tap added to every
+// base pixel; taps that land in the padding are zero-filled by the TMA unit.  Lands as [pixels rows x 128 B], 128B swizzle —
+// byte-identical to a 2D tile load of a K-major operand, so the convolution needs no materialised im2col matrix.
+DEVI void tma_load_im2col_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+DEVI void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 DEVI void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
@@ -162,11 +174,20 @@ template <int BN> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool kStats, bool kBias, bool kBMN = false>
+// Implicit-GEMM convolution geometry (kConv): GEMM row m = output pixel (n, p, q), GEMM k = (tap, channel block).
+struct ConvGeom {
+  int P, Q;          // output height / width
+  int S, taps;       // filter width, R*S
+  int cblocks;       // A-operand channels / 64
+  int stride, lower; // base pixel of output (p, q) = (lower + stride*p, lower + stride*q)
+  int flip;          // dgrad: B is W[co][taps-1-tap][ci] read through a 3D map as an MN-major operand
+};
+
+template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
-                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats) {
+                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats, const ConvGeom geom) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -202,11 +223,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_blk = t / num_m, m_blk = t % num_m;
+        int cn = 0, ch = 0, cw = 0;
+        if constexpr (kConv) {               // first output pixel of this M tile -> base-pixel coordinates
+          const int pq = geom.P * geom.Q, m0 = m_blk * BM;
+          cn = m0 / pq; const int rem = m0 - cn * pq, p0 = rem / geom.Q;
+          ch = geom.lower + geom.stride * p0; cw = geom.lower + geom.stride * (rem - p0 * geom.Q);
+        }
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           int nb = BN / 64;
           if constexpr (kBMN) { nb = 0; for (int sl = 0; sl < BN / 64; ++sl) nb += (n_blk * BN + sl * 64 < N); }
           mbar_expect_tx(&full_bar[stage], kBMN ? (uint32_t)(C::kABytes + nb * kSlabBytes) : (uint32_t)C::kStageBytes);
+          if constexpr (kConv) {
+            const int tap = kb / geom.cblocks, cb = kb - tap * geom.cblocks, r = tap / geom.S, sx = tap - r * geom.S;
+            tma_load_im2col_4d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], cb * 64, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+            if constexpr (kBMN) {           // dgrad: B[k = co, n = ci] = W[co][taps-1-tap][ci], 3D map {ci, tap, co}
+              for (int sl = 0; sl < nb; ++sl)
+                tma_load_3d(smem_b + stage * C::kBBytes + sl * kSlabBytes, &tmap_b, &full_bar[stage], n_blk * BN + sl * 64,
+                            geom.flip ? geom.taps - 1 - tap : tap, cb * 64);
+            } else {
+              tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
           if constexpr (kBMN) {
             // B given as [K, N] with N contiguous (e.g. W[Cout, Cin] for dgrad): one 64-wide slab per TMA box;
@@ -875,6 +915,76 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
   return true;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn g_encode_im2col = nullptr;
+bool load_encode_im2col() {
+  if (g_encode_im2col) return true;
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+  g_encode_im2col = (EncodeIm2colFn)fn;
+  return true;
+}
+// NHWC bf16 activation [N, H, W, C] as an im2col tensor map: box = 128 pixels x 64 channels, filter extent (R, S), padding `pad`
+bool make_im2col_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int R, int S, int pad, int stride, uint32_t pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (S - 1), pad - (R - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, pixels, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeIm2col failed (%d)", (int)r); return false; }
+  return true;
+}
+// weights [Cout][taps][Cin] as a 3D map {Cin, taps, Cout}, box {64, 1, 64}: one MN-major slab (64 co-rows x 64 ci) per load
+bool make_w3d_map(CUtensorMap* m, const void* ptr, int Cout, int taps, int Cin) {
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)taps * Cin * 2};
+  cuuint32_t box[3] = {64, 1, 64};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(3D) failed (%d)", (int)r); return false; }
+  return true;
+}
+
+// Implicit-GEMM convolution launch.  dgrad == false: y[N,P,Q,Co] = conv(x[N,H,W,Ci], w[Co,R,S,Ci]) (+BN statistics);
+// dgrad == true (stride 1): x_grad[N,H,W,Ci] = conv(dy[N,P,Q,Co], rot180(w)^T), weights read in place as an MN-major operand.
+template <int BN>
+int launch_conv(const void* act, const void* wgt, void* out, int Nb, int H, int W, int Ca, int Cn, int R, int S, int pad, int stride,
+                bool dgrad, float* stats, int max_ctas, cudaStream_t s) {
+  using C = Cfg<BN>;
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  const int M = Nb * P * Q, N = Cn, K = R * S * Ca;
+  CUtensorMap ta, tb, tc;
+  if (!make_im2col_map(&ta, act, Nb, H, W, Ca, R, S, pad, stride, BM)) return 3;
+  if (dgrad) { if (!make_w3d_map(&tb, wgt, Ca, R * S, Cn)) return 3; }        // wgt = W[Co = Ca][taps][Ci = Cn]
+  else if (!make_map(&tb, wgt, K, N, K, BK, BN)) return 3;
+  if (!make_map(&tc, out, N, M, N, kEpiChunk, BM)) return 3;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = tiles < sms ? tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  ConvGeom g{P, Q, S, R * S, Ca / 64, stride, -pad, dgrad ? 1 : 0};
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, stats, g);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  if (dgrad) return go(gemm_bf16_tn_kernel<BN, false, false, true, true>);
+  if (stats) return go(gemm_bf16_tn_kernel<BN, true, false, false, true>);
+  return go(gemm_bf16_tn_kernel<BN, false, false, false, true>);
+}
+
 template <int BN>
 int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, const void* bias, float* stats,
            int max_ctas, cudaStream_t s, bool b_mn = false) {
@@ -890,7 +1000,7 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats);
+    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats, ConvGeom{});
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
@@ -928,6 +1038,32 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
     case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// Convolution as implicit GEMM on tcgen05 with TMA im2col loads (no im2col buffer, padding by TMA zero fill).
+//   dgrad == 0: out[N,P,Q,Cout] = conv(act[N,H,W,Cin], wgt[Cout,R,S,Cin]), optional BN statistics of `out` in stats[2*Cout]
+//   dgrad == 1: out[N,H,W,Cin]  = dgrad of the same convolution from act = dY[N,P,Q,Cout] (stride 1 only); wgt as above
+// c_act = channels of `act`, c_out = channels of `out`.  Requirements: channels of `act` %% 64 == 0, c_out %% 8 == 0,
+// N*P*Q %% 128 == 0 (whole M tiles), tensors dense NHWC / KRSC and 16-byte aligned.
+extern "C" int sy_conv_bf16_nhwc(const void* act, const void* wgt, void* out, int Nb, int H, int W, int c_act, int c_out, int R, int S,
+                                 int pad, int stride, int dgrad, float* stats, int block_n, int max_ctas, void* stream) {
+  if (c_act % 64 || c_out % 8 || ((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out) & 15) {
+    snprintf(g_err, sizeof g_err, "conv: act channels %% 64, out channels %% 8, 16B aligned tensors"); return 1;
+  }
+  if (dgrad && (stride != 1 || stats)) { snprintf(g_err, sizeof g_err, "conv dgrad: stride 1, no stats"); return 1; }
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (((long)Nb * P * Q) % BM) { snprintf(g_err, sizeof g_err, "conv: N*P*Q must be a multiple of 128"); return 1; }
+  if (dgrad && (P != H || Q != W)) { snprintf(g_err, sizeof g_err, "conv dgrad: 'same' padding only"); return 1; }
+  if (!load_encode() || !load_encode_im2col()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncode* unavailable (no driver?)"); return 6; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_n <= 0) block_n = c_out > 128 ? 256 : (c_out > 64 ? 128 : 64);
+  switch (block_n) {
+    case 64: return launch_conv<64>(act, wgt, out, Nb, H, W, c_act, c_out, R, S, pad, stride, dgrad != 0, stats, max_ctas, s);
+    case 128: return launch_conv<128>(act, wgt, out, Nb, H, W, c_act, c_out, R, S, pad, stride, dgrad != 0, stats, max_ctas, s);
+    case 256: return launch_conv<256>(act, wgt, out, Nb, H, W, c_act, c_out, R, S, pad, stride, dgrad != 0, stats, max_ctas, s);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

@@ -126,3 +126,46 @@ def test_conv1x1_wgrad_written_into_existing_grad():
     torch.testing.assert_close(flat.view(64, 256).float(), wr.grad.view(64, 256), atol=0.5, rtol=3e-2)
     torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.08, rtol=3e-2)
     assert w.grad.data_ptr() == flat.data_ptr()
+
+
+CONV_CASES = [  # n, cin, h, w, cout, k, stride
+    (8, 64, 16, 16, 64, 3, 1), (4, 128, 28, 28, 128, 3, 1), (2, 256, 16, 16, 256, 3, 1), (16, 64, 8, 8, 192, 3, 1),
+    (8, 128, 16, 16, 128, 3, 2), (8, 256, 16, 16, 512, 1, 2), (2, 64, 56, 56, 64, 3, 1), (32, 512, 4, 4, 512, 3, 1)]
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,k,stride", CONV_CASES)
+def test_conv_implicit_gemm_fprop_and_dgrad(n, cin, h, w, cout, k, stride):
+    """TMA-im2col implicit GEMM vs F.conv2d in fp32 (padding handled by TMA zero fill, taps by im2col offsets)."""
+    from batch_shipyard_b200.ops import gemm
+    import torch.nn.functional as F
+    torch.manual_seed(n + cin + h + cout + k)
+    pad = k // 2
+    x = (torch.randn(n, cin, h, w, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda") * (1.0 / (cin * k * k) ** 0.5)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert gemm.conv_supported(x, wt, stride, pad)
+    stats = torch.zeros(2 * cout, dtype=torch.float32, device="cuda")
+    y = gemm.conv_fprop_nhwc(x, wt, stride, pad, stats=stats)
+    ref = F.conv2d(x.float(), wt.float(), stride=stride, padding=pad)
+    torch.testing.assert_close(y.float(), ref, atol=0.03, rtol=2e-2)
+    torch.testing.assert_close(stats[:cout], y.float().sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
+    torch.testing.assert_close(stats[cout:], (y.float() ** 2).sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
+    if stride == 1 and cout % 64 == 0:
+        dy = (torch.randn_like(ref) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = gemm.conv_dgrad_nhwc(dy, wt, pad)
+        dref = torch.nn.grad.conv2d_input(x.shape, wt.float(), dy.float(), stride=1, padding=pad)
+        torch.testing.assert_close(dx.float(), dref, atol=0.05, rtol=2e-2)
+
+
+def test_conv_autograd_matches_cudnn():
+    from batch_shipyard_b200.ops import gemm
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    x = torch.randn(8, 64, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(128, 64, 3, 3, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y, _ = gemm.conv_nhwc(x, w, 1, 1, want_stats=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    F.conv2d(xr, wr, padding=1).backward(g.float())
+    torch.testing.assert_close(x.grad.float(), xr.grad, atol=0.1, rtol=3e-2)
+    torch.testing.assert_close(w.grad.float(), wr.grad, atol=0.6, rtol=3e-2)
