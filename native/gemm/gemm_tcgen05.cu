@@ -36,6 +36,8 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle row of bf16
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int kThreads = 256;
+constexpr int kEpiGroups = 2;                             // TN / conv kernel: two epilogue warpgroups drain alternate 64-column chunks
+constexpr int kThreadsTN = 128 + kEpiGroups * 128;        // warps 0-3: TMA / MMA / TMEM alloc / idle, then 4 warps per epilogue group
 constexpr int kEpiThreads = 128;
 constexpr int kEpiChunk = 64;    // columns per epilogue step (one 128B row of bf16)
 
@@ -169,7 +171,8 @@ template <int BN> struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kCBytes = BM * kEpiChunk * 2;          // 16 KB staging tile (x2 buffers)
-  static constexpr int kStages = ((200 * 1024 - 2 * kCBytes) / kStageBytes) > 6 ? 6 : ((200 * 1024 - 2 * kCBytes) / kStageBytes);
+  static constexpr int kBudget = 227 * 1024 - 1024 - 256 - 512;   // opt-in max dynamic smem minus alignment slack and barriers
+  static constexpr int kStages = ((kBudget - 2 * kCBytes) / kStageBytes) > 6 ? 6 : ((kBudget - 2 * kCBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // two accumulator stages (power of two: BN in {64,128,256})
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -184,7 +187,7 @@ struct ConvGeom {
 };
 
 template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
                     const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats, const ConvGeom geom) {
@@ -208,7 +211,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_c); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    constexpr int kActiveGroups = (BN / kEpiChunk) < kEpiGroups ? (BN / kEpiChunk) : kEpiGroups;
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * kActiveGroups); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
@@ -290,85 +294,102 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
-    const int ew = warp - 4, et = threadIdx.x - 128;      // 0..127
-    const int row = ew * 32 + lane;                       // row of the 128-row tile owned by this thread
-    const bool issuer = et == 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    int buf = 0;
-    // statistics: thread (wcol = et % 32, rgrp = et / 32) owns word-column wcol (2 bf16 columns) of rows rgrp*32..+31
+    // ===================== epilogue: two warpgroups, TMEM lane quarter = warp % 4 =====================
+    // Group g drains chunks g, g+2, ... of every tile through its own staging buffer, so the TMEM-read latency,
+    // the smem round trip and the TMA store of one chunk overlap with the other group's chunk; inside a group the
+    // tcgen05.ld of the next chunk is issued as soon as the current one has been packed into registers.
     constexpr int kChunks = BN / kEpiChunk;
-    float st[kChunks][4];
+    const int grp = (warp - 4) >> 2;
+    if (grp < kChunks) {
+      const int ew = warp & 3, et = threadIdx.x - 128 - grp * 128;   // 0..127 inside the group
+      const int row = ew * 32 + lane;                               // row of the 128-row tile owned by this thread
+      const bool issuer = et == 0;
+      const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+      uint8_t* cbuf = smem_c + grp * C::kCBytes;
+      int acc = 0; uint32_t acc_phase = 0;
+      // statistics: thread (wcol = et % 32, rgrp = et / 32) owns word-column wcol (2 bf16 columns) of rows rgrp*32..+31
+      constexpr int kMyChunks = (kChunks + kEpiGroups - 1) / kEpiGroups;
+      float st[kMyChunks][4];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) { st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f; }
-    int cur_n = -1;
-    auto flush_stats = [&](int n_blk) {
-      if (!kStats || n_blk < 0) return;
-      const int wcol = et & 31;
+      for (int c = 0; c < kMyChunks; ++c) { st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f; }
+      int cur_n = -1;
+      auto flush_stats = [&](int n_blk) {
+        if (!kStats || n_blk < 0) return;
+        const int wcol = et & 31;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int col = n_blk * BN + c * kEpiChunk + 2 * wcol;
-        if (col < N) { atomicAdd(&stats[col], st[c][0]); atomicAdd(&stats[N + col], st[c][2]); }
-        if (col + 1 < N) { atomicAdd(&stats[col + 1], st[c][1]); atomicAdd(&stats[N + col + 1], st[c][3]); }
-        st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f;
-      }
-    };
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int n_blk = t / num_m, m_blk = t % num_m;
-      if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = grp + ci * kEpiGroups;
+          if (c < kChunks) {
+            const int col = n_blk * BN + c * kEpiChunk + 2 * wcol;
+            if (col < N) { atomicAdd(&stats[col], st[ci][0]); atomicAdd(&stats[N + col], st[ci][2]); }
+            if (col + 1 < N) { atomicAdd(&stats[col + 1], st[ci][1]); atomicAdd(&stats[N + col + 1], st[ci][3]); }
+          }
+          st[ci][0] = st[ci][1] = st[ci][2] = st[ci][3] = 0.f;
+        }
+      };
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t / num_m, m_blk = t % num_m;
+        if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
         uint32_t v[2][32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * kEpiChunk);
-        tmem_ld32(taddr, v[0]);
-        tmem_ld32(taddr + 32, v[1]);
-        tmem_ld_wait();
-        if (c == kChunks - 1) {           // accumulator fully read: hand it back to the MMA warp early
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
-        }
-        // staging buffer `buf` must no longer be read by the TMA store issued two chunks ago
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(1, kEpiThreads);
-        uint8_t* cbuf = smem_c + buf * C::kCBytes;
-        const int n0 = n_blk * BN + c * kEpiChunk;
+        tmem_ld32(tbase + grp * kEpiChunk, v[0]);
+        tmem_ld32(tbase + grp * kEpiChunk + 32, v[1]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {     // 8 x 16-byte chunks = 64 bf16 columns of this thread's row
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
-          if (kBias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const int col = n0 + q * 8 + i; f[i] += col < N ? __bfloat162float(bias[col]) : 0.f; }
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = grp + ci * kEpiGroups;
+          if (c >= kChunks) break;
+          tmem_ld_wait();
+          const bool last = c + kEpiGroups >= kChunks;
+          if (last) {                       // this group's part of the accumulator is in registers: hand it back early
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
           }
-          uint4 w = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          // 128B swizzle: 16-byte chunk index XOR (row % 8) — matches the TMA store's SWIZZLE_128B and is bank-conflict free
-          *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
-        if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m_blk * BM); tma_store_commit(); }
-        if (kStats) {
-          const int wcol = et & 31, rgrp = et >> 5;
-          const int q = wcol >> 2, wi = wcol & 3;
-          const int rows_valid = M - m_blk * BM;          // OOB rows hold zeros from the zero-filled A tile (no bias with stats)
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int n0 = n_blk * BN + c * kEpiChunk;
+          uint4 w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {     // 8 x 16-byte chunks = 64 bf16 columns of this thread's row
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
+            if (kBias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const int col = n0 + q * 8 + i; f[i] += col < N ? __bfloat162float(bias[col]) : 0.f; }
+            }
+            w[q] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+          if (!last) {                      // prefetch this group's next chunk; its latency hides behind the store phase below
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk, v[0]);
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk + 32, v[1]);
+          }
+          if (issuer) tma_store_wait_read<0>();   // the previous TMA store of this group has finished reading cbuf
+          named_bar_sync(bar_a, kEpiThreads);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)       // 128B swizzle: 16-byte chunk index XOR (row % 8) — matches the TMA store, bank-conflict free
+            *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w[q];
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, kEpiThreads);
+          if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m_blk * BM); tma_store_commit(); }
+          if (kStats) {
+            const int wcol = et & 31, rgrp = et >> 5;
+            const int q = wcol >> 2, wi = wcol & 3;
+            const int rows_valid = M - m_blk * BM;          // OOB rows hold zeros from the zero-filled A tile (no bias with stats)
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
-          for (int r = rgrp * 32; r < rgrp * 32 + 32; ++r) {
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(cbuf + r * 128 + ((q ^ (r & 7)) << 4) + wi * 4);
-            const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
-            if (r < rows_valid) { s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); }
+            for (int r = rgrp * 32; r < rgrp * 32 + 32; ++r) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(cbuf + r * 128 + ((q ^ (r & 7)) << 4) + wi * 4);
+              const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
+              if (r < rows_valid) { s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); }
+            }
+            st[ci][0] += s0; st[ci][1] += s1; st[ci][2] += q0; st[ci][3] += q1;
           }
-          st[c][0] += s0; st[c][1] += s1; st[c][2] += q0; st[c][3] += q1;
         }
-        buf ^= 1;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      flush_stats(cur_n);
+      if (issuer) tma_store_wait_all();
     }
-    flush_stats(cur_n);
-    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -974,7 +995,7 @@ int launch_conv(const void* act, const void* wgt, void* out, int Nb, int H, int 
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, stats, g);
+    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, stats, g);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
@@ -1000,7 +1021,7 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats, ConvGeom{});
+    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats, ConvGeom{});
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);

@@ -41,7 +41,7 @@ def main():
     assert (ab - b).abs().max().item() < 1e-10, "rhs != A*1"
     x = torch.zeros_like(b)
     iters = 12
-    norms = h.cg(b, x, iters=iters)
+    norms = h.cg(b, x, iters=iters, graph=False)            # eager: full residual history
     # reference: the same algorithm on ONE domain of the global size, plain PyTorch on the CPU (stub communicator).
     # z-slab decomposition + globally consistent colouring make the distributed sweep order identical, so the residual
     # history must agree to rounding, not just "converge".
@@ -62,6 +62,12 @@ def main():
         assert (x.cpu() - xs).abs().max().item() < 50 * (xref - 1).abs().max().item() + 1e-6
     assert norms[-1] / norms[0] < 5e-2 if a.n * a.world > 16 else norms[-1] / norms[0] < 1e-5, f"CG did not converge: {norms[-1] / norms[0]}"
     ref_comm.close()
+    if comm.torch_device.type == "cuda":
+        # CUDA-graph mode (two iterations per replay, device-resident scalars) must land on the same final residual
+        xg = torch.zeros_like(b)
+        ng = h.cg(b, xg, iters=iters, graph=True)
+        assert len(ng) == 2 and abs(ng[-1] - norms[-1]) <= 1e-6 * norms[0] + 1e-3 * norms[-1], f"graph CG differs: {ng[-1]} vs {norms[-1]}"
+        assert (xg - x).abs().max().item() < 1e-6
     comm.check_status()
     print(f"rank {a.rank} HPCG OK reduction {norms[-1] / norms[0]:.2e} spmv_err {err:.1e}", flush=True)
     comm.close()
