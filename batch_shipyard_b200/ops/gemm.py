@@ -42,6 +42,7 @@ def load() -> C.CDLL:
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_tn_rsag.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        lib.sy_conv_bf16_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
         try:
@@ -360,9 +361,33 @@ def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, pad: int = 1, block_n: in
     return dx.permute(0, 3, 1, 2)
 
 
+def conv_wgrad_nhwc(x: torch.Tensor, dy: torch.Tensor, wshape, stride: int = 1, pad: int = 1, out: Optional[torch.Tensor] = None,
+                    accumulate: bool = False, block_n: int = 0, splits: int = 0) -> torch.Tensor:
+    """dW[Cout,Cin,R,S] (stored KRSC) of conv2d(x, w): one split-K tcgen05 launch over all filter taps, im2col(x) through TMA,
+    dY read as an MN-major operand; with `out` (a KRSC-dense [Cout,R,S,Cin] view, e.g. the flat gradient buffer) the last CTA
+    of every tile writes / accumulates the bf16 gradient in place."""
+    n, cin, h, wd = x.shape
+    cout, _, r, s = wshape
+    xs, dys = _nhwc_storage(x), _nhwc_storage(dy)
+    if out is None:
+        out = torch.empty((cout, r, s, cin), dtype=torch.bfloat16, device=x.device)
+        accumulate = False
+    assert out.is_contiguous() and tuple(out.shape) == (cout, r, s, cin) and out.dtype == torch.bfloat16
+    ws, tickets = _workspace(x.device)
+    if r * s * cin * cout > ws.numel():
+        raise RuntimeError("conv wgrad output exceeds the split-K workspace")
+    lib = load()
+    rc = lib.sy_conv_bf16_wgrad(C.c_void_p(xs.data_ptr()), C.c_void_p(dys.data_ptr()), C.c_void_p(out.data_ptr()), n, h, wd, cin, cout, r, s,
+                                pad, stride, C.c_void_p(ws.data_ptr()), C.c_void_p(tickets.data_ptr()), 1 if accumulate else 0, block_n, splits,
+                                C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_conv_bf16_wgrad failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out.permute(0, 3, 1, 2)
+
+
 class _ConvNHWC(torch.autograd.Function):
-    """KxK convolution on channels_last bf16 activations: fprop (+ BN statistics) and stride-1 dgrad on the tcgen05
-    implicit-GEMM kernel; wgrad through cuDNN for now."""
+    """KxK (strided) convolution on channels_last bf16 activations, all three passes on tcgen05 implicit-GEMM kernels:
+    fprop (+ BN statistics), stride-1 dgrad (weights read in place), wgrad (split-K over pixels, all taps in one launch)."""
 
     @staticmethod
     def forward(ctx, x, w, stride, pad, want_stats):
@@ -371,6 +396,7 @@ class _ConvNHWC(torch.autograd.Function):
         y = conv_fprop_nhwc(x, w, stride, pad, stats=stats)
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.pad = stride, pad
+        ctx.w_ref = w
         if stats is not None:
             ctx.mark_non_differentiable(stats)
         return y, stats
@@ -387,7 +413,12 @@ class _ConvNHWC(torch.autograd.Function):
             else:
                 dx = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=ctx.stride, padding=ctx.pad)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=ctx.stride, padding=ctx.pad)
+            g = getattr(ctx.w_ref, "grad", None)
+            gv = g.permute(0, 2, 3, 1) if (g is not None and g.dtype == torch.bfloat16 and g.dim() == 4) else None
+            if gv is not None and gv.is_contiguous():
+                conv_wgrad_nhwc(x, dy, w.shape, ctx.stride, ctx.pad, out=gv, accumulate=True)   # straight into the flat gradient buffer
+            else:
+                dw = conv_wgrad_nhwc(x, dy, w.shape, ctx.stride, ctx.pad)
         return dx, dw, None, None, None
 
 

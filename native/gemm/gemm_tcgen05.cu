@@ -166,6 +166,15 @@ DEVI bool elect_one() {
   return pred != 0;
 }
 
+// Implicit-GEMM convolution geometry (kConv): GEMM row m = output pixel (n, p, q), GEMM k = (tap, channel block).
+struct ConvGeom {
+  int P, Q;          // output height / width
+  int S, taps;       // filter width, R*S
+  int cblocks;       // A-operand channels / 64
+  int stride, lower; // base pixel of output (p, q) = (lower + stride*p, lower + stride*q)
+  int flip;          // dgrad: B is W[co][taps-1-tap][ci] read through a 3D map as an MN-major operand
+};
+
 template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
@@ -175,15 +184,6 @@ template <int BN> struct Cfg {
   static constexpr int kStages = ((kBudget - 2 * kCBytes) / kStageBytes) > 6 ? 6 : ((kBudget - 2 * kCBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // two accumulator stages (power of two: BN in {64,128,256})
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-// Implicit-GEMM convolution geometry (kConv): GEMM row m = output pixel (n, p, q), GEMM k = (tap, channel block).
-struct ConvGeom {
-  int P, Q;          // output height / width
-  int S, taps;       // filter width, R*S
-  int cblocks;       // A-operand channels / 64
-  int stride, lower; // base pixel of output (p, q) = (lower + stride*p, lower + stride*q)
-  int flip;          // dgrad: B is W[co][taps-1-tap][ci] read through a 3D map as an MN-major operand
 };
 
 template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false>
@@ -408,11 +408,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ===================================================================================================
 DEVI void red_add_f32(float* p, float v) { asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
-template <int BN>
+// kConv: A is the im2col view of an NHWC activation (one filter tap per work item: the tile index carries the tap), so the
+// same kernel produces dW[Cout][tap][Cin] of a KxK (strided) convolution: out/ws are offset by tap * I per tap.
+template <int BN, bool kConv = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                           int I, int J, int K, int splits, float* __restrict__ ws, int* __restrict__ tickets,
-                           __nv_bfloat16* __restrict__ out, int ldo, int accumulate) {
+                           int I, int J, int K, int splits, float* __restrict__ ws_base, int* __restrict__ tickets,
+                           __nv_bfloat16* __restrict__ out_base, int ldo, int accumulate, const ConvGeom geom) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -425,7 +427,8 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   uint32_t* s_last = tmem_ptr + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (I + BM - 1) / BM, num_n = (J + BN - 1) / BN, num_k = (K + BK - 1) / BK;
-  const int num_items = num_m * num_n * splits;
+  const int num_mn = num_m * num_n;
+  const int num_items = num_mn * (kConv ? geom.taps : 1) * splits;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -443,16 +446,26 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
         const int tile = w / splits, sp = w % splits;
-        const int n_blk = tile / num_m, m_blk = tile % num_m;
+        const int tap = tile / num_mn, mn = tile - tap * num_mn;
+        const int n_blk = mn / num_m, m_blk = mn % num_m;
         const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
         // slabs that start beyond the matrix edge are not loaded at all: their smem stays stale, which only
         // feeds accumulator rows / columns the epilogue never stores (rows and columns are independent)
         int na = 0, nb = 0;
         for (int sl = 0; sl < BM / 64; ++sl) na += (m_blk * BM + sl * 64 < I);
         for (int sl = 0; sl < BN / 64; ++sl) nb += (n_blk * BN + sl * 64 < J);
+        const int tr = kConv ? tap / geom.S : 0, ts = kConv ? tap - tr * geom.S : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], (uint32_t)(na + nb) * kSlabBytes);
+          if constexpr (kConv) {           // 64 output pixels starting at linear index kb*64 -> im2col box [64 pixels x 64 channels]
+            const int pq = geom.P * geom.Q, m0 = kb * BK;
+            const int cn = m0 / pq, rem = m0 - cn * pq, p0 = rem / geom.Q;
+            const int ch = geom.lower + geom.stride * p0, cw = geom.lower + geom.stride * (rem - p0 * geom.Q);
+            for (int sl = 0; sl < na; ++sl)
+              tma_load_im2col_4d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], m_blk * BM + sl * 64, cw, ch, cn,
+                                 (uint16_t)ts, (uint16_t)tr);
+          } else
           for (int sl = 0; sl < na; ++sl)
             tma_load_2d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], m_blk * BM + sl * 64, kb * BK);
           for (int sl = 0; sl < nb; ++sl)
@@ -491,7 +504,10 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
       const int tile = w / splits;
-      const int n_blk = tile / num_m, m_blk = tile % num_m;
+      const int tap = tile / num_mn, mn = tile - tap * num_mn;
+      const int n_blk = mn / num_m, m_blk = mn % num_m;
+      __nv_bfloat16* const out = out_base + (size_t)tap * I;            // dW[co][tap][ci]: ldo = taps * I
+      float* const ws = ws_base + (size_t)tap * I * J;
       const int i = m_blk * BM + ew * 32 + lane;           // TMEM lane = output row i = contiguous index of `out`
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -1090,6 +1106,52 @@ extern "C" int sy_conv_bf16_nhwc(const void* act, const void* wgt, void* out, in
   return 1;
 }
 
+// Convolution weight gradient: dW[Cout][R][S][Cin] (+)= sum over output pixels of dY[pix][Cout] * im2col(x)[pix][(r,s,Cin)].
+// One split-K launch covers every filter tap (work item = (tap, tile, K-split)).  ws: float[R*S*Cin*Cout], tickets:
+// int[R*S*tiles]; both zero on entry and on exit.  Requirements: Cin %% 64, Cout %% 8, N*P*Q %% 128.
+extern "C" int sy_conv_bf16_wgrad(const void* x, const void* dy, void* dw, int Nb, int H, int W, int Cin, int Cout, int R, int S, int pad,
+                                  int stride, float* ws, int* tickets, int accumulate, int block_n, int splits, void* stream) {
+  if (Cin % 64 || Cout % 8 || ((uintptr_t)x | (uintptr_t)dy) & 15 || ((uintptr_t)dw & 7)) {
+    snprintf(g_err, sizeof g_err, "conv wgrad: Cin %% 64, Cout %% 8, aligned tensors"); return 1;
+  }
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  const long Kl = (long)Nb * P * Q;
+  if (Kl % BM) { snprintf(g_err, sizeof g_err, "conv wgrad: N*P*Q must be a multiple of 128"); return 1; }
+  if (!load_encode() || !load_encode_im2col()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncode* unavailable (no driver?)"); return 6; }
+  const int I = Cin, J = Cout, K = (int)Kl, taps = R * S;
+  if (block_n <= 0) block_n = J > 128 ? 256 : (J > 64 ? 128 : 64);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto go = [&](auto kern, int BN, int smem) -> int {
+    CUtensorMap ta, tb;
+    if (!make_im2col_map(&ta, x, Nb, H, W, Cin, R, S, pad, stride, 64) || !make_map(&tb, dy, J, K, J, 64, BK)) return 3;
+    const int tiles = ((I + BM - 1) / BM) * ((J + BN - 1) / BN) * taps, num_k = (K + BK - 1) / BK;
+    int sp = splits;
+    if (sp <= 0) { sp = (sms + tiles - 1) / tiles; if (sp > num_k / 4) sp = num_k / 4; }
+    if (sp < 1) sp = 1;
+    if (sp > num_k) sp = num_k;
+    if (sp > 1 && (!ws || !tickets)) { snprintf(g_err, sizeof g_err, "split-K needs a workspace"); return 2; }
+    const long items = (long)tiles * sp;
+    const int grid = (int)(items < sms ? items : sms);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    ConvGeom g{P, Q, S, taps, Cin / 64, stride, -pad, 0};
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)dw, taps * I, accumulate, g);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  switch (block_n) {
+    case 64: return go(gemm_bf16_nt_splitk_kernel<64, true>, 64, Cfg<64>::kSmemBytes);
+    case 128: return go(gemm_bf16_nt_splitk_kernel<128, true>, 128, Cfg<128>::kSmemBytes);
+    case 256: return go(gemm_bf16_nt_splitk_kernel<256, true>, 256, Cfg<256>::kSmemBytes);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
 // K10 v2: out (bf16 [M,N], symmetric, dense) = sum over ranks of A_r x B_r^T.  inbox: symmetric bf16 scratch of
 // world * rows_per_rank * N elements, rows_per_rank = ceil(ceil(M/128) / world) * 128 (returned through *rows_per_rank_out
 // when the pointers are null, so callers can size it).
@@ -1179,16 +1241,16 @@ extern "C" int sy_gemm_bf16_nt_splitk(const void* A, const void* B, void* out, i
     const int grid = (int)(items < sms ? items : sms);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)out, ldo, accumulate);
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)out, ldo, accumulate, ConvGeom{});
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
     return 0;
   };
   switch (block_n) {
-    case 64: return go(gemm_bf16_nt_splitk_kernel<64>, 64, Cfg<64>::kSmemBytes);
-    case 128: return go(gemm_bf16_nt_splitk_kernel<128>, 128, Cfg<128>::kSmemBytes);
-    case 256: return go(gemm_bf16_nt_splitk_kernel<256>, 256, Cfg<256>::kSmemBytes);
+    case 64: return go(gemm_bf16_nt_splitk_kernel<64, false>, 64, Cfg<64>::kSmemBytes);
+    case 128: return go(gemm_bf16_nt_splitk_kernel<128, false>, 128, Cfg<128>::kSmemBytes);
+    case 256: return go(gemm_bf16_nt_splitk_kernel<256, false>, 256, Cfg<256>::kSmemBytes);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

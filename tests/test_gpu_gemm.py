@@ -149,11 +149,22 @@ def test_conv_implicit_gemm_fprop_and_dgrad(n, cin, h, w, cout, k, stride):
     torch.testing.assert_close(y.float(), ref, atol=0.03, rtol=2e-2)
     torch.testing.assert_close(stats[:cout], y.float().sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
     torch.testing.assert_close(stats[cout:], (y.float() ** 2).sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
+    dy = (torch.randn_like(ref) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     if stride == 1 and cout % 64 == 0:
-        dy = (torch.randn_like(ref) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         dx = gemm.conv_dgrad_nhwc(dy, wt, pad)
         dref = torch.nn.grad.conv2d_input(x.shape, wt.float(), dy.float(), stride=1, padding=pad)
         torch.testing.assert_close(dx.float(), dref, atol=0.05, rtol=2e-2)
+    # weight gradient: all taps in one split-K launch, then again accumulating into an existing buffer
+    wref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, dy.float(), stride=stride, padding=pad)
+    tol = 0.02 * (n * ref.shape[2] * ref.shape[3]) ** 0.5 * 0.25 + 0.05
+    dw = gemm.conv_wgrad_nhwc(x, dy, wt.shape, stride, pad)
+    torch.testing.assert_close(dw.float(), wref, atol=tol, rtol=3e-2)
+    base = torch.randn(cout, k, k, cin, device="cuda").to(torch.bfloat16)
+    buf = base.clone()
+    gemm.conv_wgrad_nhwc(x, dy, wt.shape, stride, pad, out=buf, accumulate=True, splits=3)
+    torch.testing.assert_close(buf.permute(0, 3, 1, 2).float(), wref + base.permute(0, 3, 1, 2).float(), atol=tol + 0.05, rtol=3e-2)
+    ws, tickets = gemm._workspace(x.device)
+    assert float(ws.abs().max()) == 0.0 and int(tickets.abs().max()) == 0
 
 
 def test_conv_autograd_matches_cudnn():
