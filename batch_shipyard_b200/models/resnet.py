@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops import conv as _conv
 from ..ops import fused as _fused
 from ..ops import gemm as _gemm
 
@@ -35,19 +36,15 @@ class ConvBN(nn.Module):
         self.register_buffer("running_var", torch.ones(cout, dtype=torch.float32))
         self.momentum, self.eps = 0.1, 1e-5
         import os as _os
-        self.use_tc_gemm = not _os.environ.get("SHIPYARD_NO_TC_GEMM")
-        self.use_tc_conv = _os.environ.get("SHIPYARD_TC_CONV", "1") not in ("", "0")
+        self.use_tc_gemm = not _os.environ.get("SHIPYARD_NO_TC_GEMM")     # off: plain cuDNN path, no dispatcher
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         fast = x.is_cuda and self.training and x.dtype == torch.bfloat16
         stats = None
-        if fast and self.k == 1 and self.stride == 1 and self.use_tc_gemm and self.cin % 8 == 0:
-            # 1x1 convolution == GEMM over NHWC pixels: tcgen05 kernel, BN statistics from its epilogue
-            y, stats = _gemm.conv1x1_nhwc(x, self.weight, want_stats=self.cin >= 256)   # short-K layers: the separate stats pass is as cheap
-        elif (fast and self.use_tc_conv and self.k in (1, 3) and self.cin % 64 == 0
-              and _gemm.conv_supported(x, self.weight, self.stride, self.k // 2)):
-            # 3x3 (and strided 1x1) convolutions: implicit GEMM, TMA im2col loads feeding tcgen05, BN statistics in the epilogue
-            y, stats = _gemm.conv_nhwc(x, self.weight, self.stride, self.k // 2, want_stats=True)
+        if fast and self.k in (1, 3) and self.use_tc_gemm:
+            # dispatcher: per shape and per pass the faster of the tcgen05 implicit-GEMM kernels and cuDNN (measured once,
+            # during the eager warm-up step); BN statistics come from the epilogue when the tcgen05 fprop wins
+            y, stats = _conv.conv_bn_input(x, self.weight, self.stride)
         elif self.k == 7 and x.shape[1] == 16:
             # space-to-depth stem: the 7x7/s2/p3 conv as a dense 4x4/s1 conv over the 16-channel s2d input
             y = F.conv2d(x, _fused.stem_weight_s2d(self.weight).contiguous(memory_format=torch.channels_last))
@@ -121,12 +118,10 @@ def resnet_tiny(num_classes: int = 10) -> ResNet:
     return ResNet((1, 1, 1, 1), num_classes, width=16)
 
 
-def set_tc_gemm(m: nn.Module, flag: bool, conv: Optional[bool] = None) -> None:
+def set_tc_gemm(m: nn.Module, flag: bool) -> None:
     for mod in m.modules():
         if hasattr(mod, "use_tc_gemm"):
             mod.use_tc_gemm = flag
-        if conv is not None and hasattr(mod, "use_tc_conv"):
-            mod.use_tc_conv = conv
 
 
 def param_count(m: nn.Module) -> int:

@@ -1,0 +1,215 @@
+"""Convolution dispatcher: per layer shape and per pass (fprop / dgrad / wgrad) pick the faster of the tcgen05
+implicit-GEMM kernels (``ops.gemm``) and cuDNN, from timings taken on the device the first time a shape is seen.
+
+The reference has no compute path at all (its recipes run third-party framework containers,
+/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8); this is part of the retargeted ResNet-50 recipe.
+
+``SHIPYARD_CONV_IMPL`` = ``auto`` (default: measure, keep the faster), ``tc`` (always our kernels where the shape is
+supported) or ``cudnn`` (library only).  The chosen table is available from ``plan_table()`` and is printed by bench.py.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, asdict
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import gemm as _gemm
+
+_MODE = os.environ.get("SHIPYARD_CONV_IMPL", "auto").lower()
+_PLANS: dict = {}
+_HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics pass (profiles/ncu_bn_kernels.md)
+
+
+@dataclass
+class ConvPlan:
+    fprop: str = "cudnn"      # "tc" | "cudnn"
+    dgrad: str = "cudnn"
+    wgrad: str = "cudnn"
+    stats: bool = False       # fprop produces the BatchNorm statistics in its epilogue
+    timings_us: Optional[dict] = None
+
+
+def set_mode(mode: str) -> None:
+    global _MODE
+    assert mode in ("auto", "tc", "cudnn")
+    _MODE = mode
+    _PLANS.clear()
+
+
+def plan_table() -> dict:
+    return {"x".join(map(str, k)): {kk: vv for kk, vv in asdict(v).items()} for k, v in _PLANS.items()}
+
+
+def _key(x: torch.Tensor, w: torch.Tensor, stride: int):
+    n, cin, h, wd = x.shape
+    return (n, cin, h, wd, w.shape[0], w.shape[2], stride)
+
+
+def _tc_caps(x: torch.Tensor, w: torch.Tensor, stride: int) -> dict:
+    """Which passes the tcgen05 kernels support for this shape."""
+    n, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    pad = k // 2
+    ok = x.is_cuda and x.dtype == torch.bfloat16
+    if k == 1 and stride == 1:
+        g = ok and cin % 8 == 0 and cout % 8 == 0
+        return {"fprop": g, "dgrad": g, "wgrad": g}
+    sup = ok and _gemm.conv_supported(x, w, stride, pad)
+    return {"fprop": sup, "wgrad": sup, "dgrad": sup and stride == 1 and cout % 64 == 0}
+
+
+def _time(fn, iters: int = 5) -> float:
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+# ---- the individual passes ---------------------------------------------------------------------------------------------
+def _fprop_tc(x, w, stride, pad, stats):
+    if w.shape[2] == 1 and stride == 1:
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        y2 = _gemm.gemm_tn(x.permute(0, 2, 3, 1).reshape(n * h * wd, cin), w.permute(0, 2, 3, 1).reshape(cout, cin), stats=stats)
+        return y2.view(n, h, wd, cout).permute(0, 3, 1, 2)
+    return _gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats)
+
+
+def _dgrad_tc(dy, x, w, stride, pad):
+    if w.shape[2] == 1 and stride == 1:
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        dy2 = dy.permute(0, 2, 3, 1).reshape(n * h * wd, cout)
+        return _gemm.gemm_nn(dy2, w.permute(0, 2, 3, 1).reshape(cout, cin)).view(n, h, wd, cin).permute(0, 3, 1, 2)
+    return _gemm.conv_dgrad_nhwc(dy, w, pad)
+
+
+def _wgrad_tc(dy, x, w, stride, pad, out_view, accumulate):
+    """out_view: KRSC-dense [Cout,R,S,Cin] destination (the parameter's flat .grad) or None."""
+    cout, cin, k, _ = w.shape
+    if k == 1 and stride == 1:
+        n, _, h, wd = x.shape
+        x2 = x.permute(0, 2, 3, 1).reshape(n * h * wd, cin)
+        dy2 = dy.permute(0, 2, 3, 1).reshape(n * h * wd, cout)
+        if out_view is not None:
+            _gemm.gemm_nt_wgrad(x2, dy2, out=out_view.reshape(cout, cin), accumulate=accumulate)
+            return None
+        return _gemm.gemm_nt_wgrad(x2, dy2).view(cout, 1, 1, cin).permute(0, 3, 1, 2)
+    if out_view is not None:
+        _gemm.conv_wgrad_nhwc(x, dy, w.shape, stride, pad, out=out_view, accumulate=accumulate)
+        return None
+    return _gemm.conv_wgrad_nhwc(x, dy, w.shape, stride, pad)
+
+
+def _cudnn_bwd(dy, x, w, stride, pad, want_dx, want_dw):
+    dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                    [want_dx, want_dw, False])
+    return dx, dw
+
+
+def _grad_view(p: torch.Tensor) -> Optional[torch.Tensor]:
+    g = getattr(p, "grad", None)
+    if g is None or g.dtype != torch.bfloat16 or g.dim() != 4:
+        return None
+    v = g.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else None
+
+
+# ---- plan selection ------------------------------------------------------------------------------------------------------
+def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
+    caps = _tc_caps(x, w, stride)
+    cout, cin, k, _ = w.shape
+    pad = k // 2
+    plan = ConvPlan(timings_us={})
+    if _MODE == "cudnn" or not any(caps.values()):
+        return plan
+    if _MODE == "tc":
+        return ConvPlan("tc" if caps["fprop"] else "cudnn", "tc" if caps["dgrad"] else "cudnn", "tc" if caps["wgrad"] else "cudnn",
+                        stats=caps["fprop"] and (k > 1 or stride > 1 or cin >= 256), timings_us={})
+    t = plan.timings_us
+    with torch.no_grad():
+        xd, wd_ = x.detach(), w.detach()
+        y = F.conv2d(xd, wd_, None, stride, pad)
+        t_stats_pass = y.numel() * 2 / _HBM_BPS * 1e6 + 3.0            # the separate statistics kernel a non-fused fprop needs
+        t["fprop_cudnn"] = _time(lambda: F.conv2d(xd, wd_, None, stride, pad)) + t_stats_pass
+        if caps["fprop"]:
+            st = torch.zeros(2 * cout, dtype=torch.float32, device=x.device)
+            t["fprop_tc_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st))
+            t["fprop_tc"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None)) + t_stats_pass
+            best = min(("fprop_cudnn", "fprop_tc_stats", "fprop_tc"), key=lambda k_: t[k_])
+            plan.fprop = "cudnn" if best == "fprop_cudnn" else "tc"
+            plan.stats = best == "fprop_tc_stats"
+        dy = torch.randn_like(y)
+        t["dgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, True, False))
+        if caps["dgrad"]:
+            t["dgrad_tc"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad))
+            plan.dgrad = "tc" if t["dgrad_tc"] < t["dgrad_cudnn"] else "cudnn"
+        t_accum = w.numel() * 6 / 4e12 * 1e6 + 3.0                     # AccumulateGrad add the library path pays
+        t["wgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, False, True)) + t_accum
+        if caps["wgrad"]:
+            buf = torch.zeros((cout, k, k, cin), dtype=torch.bfloat16, device=x.device)
+            t["wgrad_tc"] = _time(lambda: _wgrad_tc(dy, xd, wd_, stride, pad, buf, True))
+            plan.wgrad = "tc" if t["wgrad_tc"] < t["wgrad_cudnn"] else "cudnn"
+    plan.timings_us = {k_: round(v, 1) for k_, v in t.items()}
+    return plan
+
+
+def plan_for(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
+    key = _key(x, w, stride)
+    p = _PLANS.get(key)
+    if p is None:
+        if not (x.is_cuda and x.dtype == torch.bfloat16) or torch.cuda.is_current_stream_capturing():
+            return ConvPlan()                      # never measure inside a graph capture; the warm-up step has filled the table
+        p = _PLANS[key] = _autotune(x, w, stride)
+    return p
+
+
+class _Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, plan: ConvPlan):
+        k = w.shape[2]
+        pad = k // 2
+        stats = None
+        if plan.fprop == "tc":
+            if plan.stats:
+                stats = torch.zeros(2 * w.shape[0], dtype=torch.float32, device=x.device)
+            y = _fprop_tc(x, w, stride, pad, stats)
+        else:
+            y = F.conv2d(x, w, None, stride, pad)
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.pad, ctx.plan, ctx.w_ref = stride, pad, plan, w
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        x, w = ctx.saved_tensors
+        plan, stride, pad = ctx.plan, ctx.stride, ctx.pad
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        lib_dx = need_dx and plan.dgrad != "tc"
+        lib_dw = need_dw and plan.wgrad != "tc"
+        if lib_dx or lib_dw:
+            dx, dw = _cudnn_bwd(dy, x, w, stride, pad, lib_dx, lib_dw)
+        if need_dx and plan.dgrad == "tc":
+            dx = _dgrad_tc(dy, x, w, stride, pad)
+        if need_dw and plan.wgrad == "tc":
+            dw = _wgrad_tc(dy, x, w, stride, pad, _grad_view(ctx.w_ref), True)     # None when written into .grad in place
+        return dx, dw, None, None
+
+
+def conv_bn_input(x: torch.Tensor, w: torch.Tensor, stride: int = 1):
+    """Convolution (kernel 1 or 3, 'same' padding) for a following BatchNorm: returns (y, stats or None)."""
+    return _Conv.apply(x, w, stride, plan_for(x, w, stride))

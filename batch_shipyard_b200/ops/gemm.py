@@ -410,8 +410,9 @@ class _ConvNHWC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.stride == 1 and dy.shape[1] % 64 == 0 and dy.shape[2:] == x.shape[2:]:
                 dx = conv_dgrad_nhwc(dy, w, ctx.pad)
-            else:
-                dx = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=ctx.stride, padding=ctx.pad)
+            else:                        # strided dgrad: cuDNN on the channels_last tensors (no layout round trip)
+                dx = torch.ops.aten.convolution_backward(dy, x, w, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
         if ctx.needs_input_grad[1]:
             g = getattr(ctx.w_ref, "grad", None)
             gv = g.permute(0, 2, 3, 1) if (g is not None and g.dtype == torch.bfloat16 and g.dim() == 4) else None

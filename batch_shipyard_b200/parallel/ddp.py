@@ -100,6 +100,8 @@ class FusedDataParallelTrainer:
         self.comm, self.model = comm, model
         self.dev = comm.torch_device
         self.is_cuda = self.dev.type == "cuda"
+        if self.is_cuda:
+            torch.backends.cudnn.benchmark = True     # the conv dispatcher compares against cuDNN's best algorithm
         self.flat = FlatParameters(model, comm, torch.bfloat16 if self.is_cuda else torch.float32)
         self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / comm.world], dtype=torch.float32, device=self.dev)
         self.loss_fn = loss_fn or (lambda logits, y: F.cross_entropy(logits.float(), y))

@@ -201,7 +201,7 @@ def run_shipyard(args, rank, world, local):
                    "seq_len": None, "parallelism": f"dp{world}", "optimizer": "sgd-momentum (fp32 master, sharded)",
                    "l2_policy": "per-step working set (activations) >> 126 MB L2; no explicit flush",
                    "cuda_graph": not args.no_graph, "collective_transport": comm.transport,
-                   "nvls_multicast": comm.has_multicast},
+                   "nvls_multicast": comm.has_multicast, "conv_dispatch": _conv_summary()},
         "clocks": clocks, "e2e": e2e,
         "gpu_launches": own * args.steps + (0 if args.no_e2e else 0),
         "own_kernels_per_step": own, "loss": round(loss_dev, 4),
@@ -211,6 +211,24 @@ def run_shipyard(args, rank, world, local):
         out["vs_baseline"] = round(out["value"] / base, 4)
     comm.close()
     return out
+
+
+def _conv_summary():
+    """How many conv passes the dispatcher put on the tcgen05 kernels vs cuDNN (per distinct layer shape)."""
+    try:
+        from batch_shipyard_b200.ops import conv as _conv
+        tab = _conv.plan_table()
+        out = {"mode": _conv._MODE, "shapes": len(tab)}
+        for pas in ("fprop", "dgrad", "wgrad"):
+            out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] == "tc")
+        out["fprop_fused_bn_stats"] = sum(1 for v in tab.values() if v["stats"])
+        if os.environ.get("SHIPYARD_CONV_PLAN_DUMP"):
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open(os.path.join("gpurun_out", "conv_plan.json"), "w") as f:
+                json.dump(tab, f, indent=1)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
 
 
 def _baseline_number(world: int):

@@ -56,11 +56,19 @@ def main():
         row = {"cin": cin, "hw": hw, "cout": cout, "k": k, "stride": stride, "fprop_cudnn_ms": round(t_cudnn, 4), "fprop_sy_ms": round(t_sy, 4),
                "fprop_sy_stats_ms": round(t_sy_stats, 4), "fprop_speedup": round(t_cudnn / t_sy, 3), "fprop_tflops": round(fl / t_sy / 1e9, 1),
                "fprop_frac_of_roofline_measured": round(roof / t_sy, 3)}
-        if stride == 1:
-            dy = torch.randn(n, cout, p, p, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            t_cd = timeit(lambda: torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=pad), 8, flush)
+        dy = torch.randn(n, cout, p, p, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+        def cudnn_bwd(dx, dw):
+            return torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [dx, dw, False])
+
+        if stride == 1 and k == 3:
+            t_cd = timeit(lambda: cudnn_bwd(True, False), 8, flush)
             t_sd = timeit(lambda: gemm.conv_dgrad_nhwc(dy, w, pad), 8, flush)
             row.update({"dgrad_cudnn_ms": round(t_cd, 4), "dgrad_sy_ms": round(t_sd, 4), "dgrad_speedup": round(t_cd / t_sd, 3)})
+        buf = torch.zeros(cout, k, k, cin, dtype=torch.bfloat16, device="cuda")
+        t_cw = timeit(lambda: cudnn_bwd(False, True), 8, flush)
+        t_sw = timeit(lambda: gemm.conv_wgrad_nhwc(x, dy, w.shape, stride, pad, out=buf, accumulate=True), 8, flush)
+        row.update({"wgrad_cudnn_ms": round(t_cw, 4), "wgrad_sy_ms": round(t_sw, 4), "wgrad_speedup": round(t_cw / t_sw, 3)})
         print(json.dumps(row), flush=True); out_f.write(json.dumps(row) + "\n")
 
 

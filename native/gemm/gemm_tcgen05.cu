@@ -408,8 +408,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ===================================================================================================
 DEVI void red_add_f32(float* p, float v) { asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
-// kConv: A is the im2col view of an NHWC activation (one filter tap per work item: the tile index carries the tap), so the
-// same kernel produces dW[Cout][tap][Cin] of a KxK (strided) convolution: out/ws are offset by tap * I per tap.
+// kConv: A is the im2col view of an NHWC activation with the GEMM's I index = tap * Cin + ci (exactly the KRSC row of dW), so
+// each 64-wide A slab is one TMA im2col box of one filter tap: a 128-row tile covers two taps of a 64-channel layer (no wasted
+// MMA rows, dY is re-read 5x instead of 9x) and the output needs no per-tap offsets.
 template <int BN, bool kConv = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -428,7 +429,7 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (I + BM - 1) / BM, num_n = (J + BN - 1) / BN, num_k = (K + BK - 1) / BK;
   const int num_mn = num_m * num_n;
-  const int num_items = num_mn * (kConv ? geom.taps : 1) * splits;
+  const int num_items = num_mn * splits;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -446,15 +447,13 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
         const int tile = w / splits, sp = w % splits;
-        const int tap = tile / num_mn, mn = tile - tap * num_mn;
-        const int n_blk = mn / num_m, m_blk = mn % num_m;
+        const int n_blk = tile / num_m, m_blk = tile % num_m;
         const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
         // slabs that start beyond the matrix edge are not loaded at all: their smem stays stale, which only
         // feeds accumulator rows / columns the epilogue never stores (rows and columns are independent)
         int na = 0, nb = 0;
         for (int sl = 0; sl < BM / 64; ++sl) na += (m_blk * BM + sl * 64 < I);
         for (int sl = 0; sl < BN / 64; ++sl) nb += (n_blk * BN + sl * 64 < J);
-        const int tr = kConv ? tap / geom.S : 0, ts = kConv ? tap - tr * geom.S : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], (uint32_t)(na + nb) * kSlabBytes);
@@ -462,9 +461,12 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
             const int pq = geom.P * geom.Q, m0 = kb * BK;
             const int cn = m0 / pq, rem = m0 - cn * pq, p0 = rem / geom.Q;
             const int ch = geom.lower + geom.stride * p0, cw = geom.lower + geom.stride * (rem - p0 * geom.Q);
-            for (int sl = 0; sl < na; ++sl)
-              tma_load_im2col_4d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], m_blk * BM + sl * 64, cw, ch, cn,
+            const int cin = geom.cblocks * 64;
+            for (int sl = 0; sl < na; ++sl) {
+              const int i0 = m_blk * BM + sl * 64, tap = i0 / cin, c0 = i0 - tap * cin, tr = tap / geom.S, ts = tap - tr * geom.S;
+              tma_load_im2col_4d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], c0, cw, ch, cn,
                                  (uint16_t)ts, (uint16_t)tr);
+            }
           } else
           for (int sl = 0; sl < na; ++sl)
             tma_load_2d(smem_a + stage * C::kABytes + sl * kSlabBytes, &tmap_a, &full_bar[stage], m_blk * BM + sl * 64, kb * BK);
@@ -504,10 +506,9 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
       const int tile = w / splits;
-      const int tap = tile / num_mn, mn = tile - tap * num_mn;
-      const int n_blk = mn / num_m, m_blk = mn % num_m;
-      __nv_bfloat16* const out = out_base + (size_t)tap * I;            // dW[co][tap][ci]: ldo = taps * I
-      float* const ws = ws_base + (size_t)tap * I * J;
+      const int n_blk = tile / num_m, m_blk = tile % num_m;
+      __nv_bfloat16* const out = out_base;
+      float* const ws = ws_base;
       const int i = m_blk * BM + ew * 32 + lane;           // TMEM lane = output row i = contiguous index of `out`
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -1118,7 +1119,7 @@ extern "C" int sy_conv_bf16_wgrad(const void* x, const void* dy, void* dw, int N
   const long Kl = (long)Nb * P * Q;
   if (Kl % BM) { snprintf(g_err, sizeof g_err, "conv wgrad: N*P*Q must be a multiple of 128"); return 1; }
   if (!load_encode() || !load_encode_im2col()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncode* unavailable (no driver?)"); return 6; }
-  const int I = Cin, J = Cout, K = (int)Kl, taps = R * S;
+  const int taps = R * S, I = taps * Cin, J = Cout, K = (int)Kl;       // I index = tap * Cin + ci = the KRSC row of dW
   if (block_n <= 0) block_n = J > 128 ? 256 : (J > 64 ? 128 : 64);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1126,7 +1127,7 @@ extern "C" int sy_conv_bf16_wgrad(const void* x, const void* dy, void* dw, int N
   auto go = [&](auto kern, int BN, int smem) -> int {
     CUtensorMap ta, tb;
     if (!make_im2col_map(&ta, x, Nb, H, W, Cin, R, S, pad, stride, 64) || !make_map(&tb, dy, J, K, J, 64, BK)) return 3;
-    const int tiles = ((I + BM - 1) / BM) * ((J + BN - 1) / BN) * taps, num_k = (K + BK - 1) / BK;
+    const int tiles = ((I + BM - 1) / BM) * ((J + BN - 1) / BN), num_k = (K + BK - 1) / BK;
     int sp = splits;
     if (sp <= 0) { sp = (sms + tiles - 1) / tiles; if (sp > num_k / 4) sp = num_k / 4; }
     if (sp < 1) sp = 1;
@@ -1137,7 +1138,7 @@ extern "C" int sy_conv_bf16_wgrad(const void* x, const void* dy, void* dw, int N
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
     ConvGeom g{P, Q, S, taps, Cin / 64, stride, -pad, 0};
-    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)dw, taps * I, accumulate, g);
+    kern<<<grid, kThreads, smem, s>>>(ta, tb, I, J, K, sp, ws, tickets, (__nv_bfloat16*)dw, I, accumulate, g);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
