@@ -42,6 +42,8 @@ def load() -> C.CDLL:
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_tn_rsag.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        lib.sy_gemm_bf16_tn_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_conv_bf16_nhwc_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
@@ -61,8 +63,14 @@ def _rows_ok(t: torch.Tensor) -> bool:
     return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0
 
 
+def two_cta_ok(m: int, n: int, block_n: int = 0) -> bool:
+    """Shapes the CTA-pair (cta_group::2, M = 256) kernels accept."""
+    bn = block_n or (256 if n % 256 == 0 else 128)
+    return n % bn == 0 and bn in (128, 256)
+
+
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-            stats: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+            stats: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0, two_cta: bool = False) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[N,K]^T (+ bias[N]); bf16, fp32 accumulation in TMEM.
     stats: zero-initialised float32[2*N] receiving column sums / sums of squares of `out`."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[1] == b.shape[1]
@@ -85,6 +93,14 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == n and bias.is_contiguous()
     lib = load()
+    if two_cta:
+        assert bias is None and two_cta_ok(m, n, block_n), "2-CTA GEMM: no bias, N % block_n == 0"
+        rc = lib.sy_gemm_bf16_tn_2cta(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
+                                      a.stride(0), b.stride(0), out.stride(0), C.c_void_p(stats.data_ptr() if stats is not None else 0),
+                                      block_n, max_ctas, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"sy_gemm_bf16_tn_2cta failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+        return out
     rc = lib.sy_gemm_bf16_tn(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
                              a.stride(0), b.stride(0), out.stride(0), C.c_void_p(bias.data_ptr() if bias is not None else 0),
                              C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
@@ -330,7 +346,7 @@ def conv_supported(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> b
 
 
 def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 1, stats: Optional[torch.Tensor] = None,
-                    block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+                    block_n: int = 0, max_ctas: int = 0, two_cta: bool = False) -> torch.Tensor:
     """y = conv2d(x, w) for channels_last bf16 x[N,Cin,H,W], w[Cout,Cin,R,S] (stored KRSC); returns channels_last y."""
     n, cin, h, wd = x.shape
     cout, _, r, s = w.shape
@@ -338,6 +354,13 @@ def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int 
     xs, ws = _nhwc_storage(x), _nhwc_storage(w)
     y = torch.empty((n, p, q, cout), dtype=torch.bfloat16, device=x.device)
     lib = load()
+    if two_cta:
+        rc = lib.sy_conv_bf16_nhwc_2cta(C.c_void_p(xs.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, cin, cout, r, s,
+                                        pad, stride, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
+                                        C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"sy_conv_bf16_nhwc_2cta failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+        return y.permute(0, 3, 1, 2)
     rc = lib.sy_conv_bf16_nhwc(C.c_void_p(xs.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, cin, cout, r, s,
                                pad, stride, 0, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
                                C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))

@@ -50,11 +50,14 @@ def main():
         t_cudnn = timeit(lambda: F.conv2d(x, w, stride=stride, padding=pad), 8, flush)
         t_sy = timeit(lambda: gemm.conv_fprop_nhwc(x, w, stride, pad), 8, flush)
         t_sy_stats = timeit(lambda: gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats), 8, flush)
+        t_2cta = None
+        if cout % 128 == 0 and (n * p * p) % 256 == 0:
+            t_2cta = timeit(lambda: gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats, two_cta=True), 8, flush)
         fl = 2.0 * n * p * p * cout * cin * k * k
         byts = 2.0 * (x.numel() + w.numel() + n * p * p * cout)
         roof = max(fl / (peak * 1e12), byts / (hbm * 1e9)) * 1e3
         row = {"cin": cin, "hw": hw, "cout": cout, "k": k, "stride": stride, "fprop_cudnn_ms": round(t_cudnn, 4), "fprop_sy_ms": round(t_sy, 4),
-               "fprop_sy_stats_ms": round(t_sy_stats, 4), "fprop_speedup": round(t_cudnn / t_sy, 3), "fprop_tflops": round(fl / t_sy / 1e9, 1),
+               "fprop_sy_stats_ms": round(t_sy_stats, 4), "fprop_sy_2cta_stats_ms": None if t_2cta is None else round(t_2cta, 4), "fprop_speedup": round(t_cudnn / t_sy, 3), "fprop_tflops": round(fl / t_sy / 1e9, 1),
                "fprop_frac_of_roofline_measured": round(roof / t_sy, 3)}
         dy = torch.randn(n, cout, p, p, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 

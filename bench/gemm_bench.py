@@ -51,11 +51,17 @@ def main():
             if t < best[1]:
                 best = (bn, t)
         t_stats = timeit(lambda: gemm.gemm_tn(a, b, out=out, stats=stats, block_n=best[0]), iters, flush)
+        t_2cta = t_2cta_stats = None
+        if gemm.two_cta_ok(m, n):
+            t_2cta = timeit(lambda: gemm.gemm_tn(a, b, out=out, two_cta=True), iters, flush)
+            t_2cta_stats = timeit(lambda: gemm.gemm_tn(a, b, out=out, stats=stats, two_cta=True), iters, flush)
         fl = 2.0 * m * n * k
         byts = 2.0 * (m * k + n * k + m * n)
         roof_ms = max(fl / (peak * 1e12), byts / (hbm * 1e9)) * 1e3
         rows.append({"m": m, "n": n, "k": k, "cublas_ms": round(t_cublas, 4), "sy_ms": round(best[1], 4), "sy_block_n": best[0],
-                     "sy_stats_ms": round(t_stats, 4), "sy_tflops": round(fl / best[1] / 1e9, 1), "cublas_tflops": round(fl / t_cublas / 1e9, 1),
+                     "sy_stats_ms": round(t_stats, 4), "sy_2cta_ms": None if t_2cta is None else round(t_2cta, 4),
+                     "sy_2cta_stats_ms": None if t_2cta_stats is None else round(t_2cta_stats, 4),
+                     "sy_2cta_tflops": None if t_2cta is None else round(2.0 * m * n * k / t_2cta / 1e9, 1), "sy_tflops": round(fl / best[1] / 1e9, 1), "cublas_tflops": round(fl / t_cublas / 1e9, 1),
                      "roofline_ms": round(roof_ms, 4), "sy_frac_of_roofline_measured": round(roof_ms / best[1], 3),
                      "speedup_vs_cublas": round(t_cublas / best[1], 3)})
         print(json.dumps(rows[-1]), flush=True)

@@ -57,12 +57,23 @@ DEVI void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 DEVI void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Bounded wait: a protocol bug must end in a trap (an error the host sees), never in a box that hangs until it is killed.
 DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  uint32_t ok;
+  uint32_t ok, it = 0;
+  unsigned long long t0 = 0;
   do {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (!ok && ((++it) & 0x3fff) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {
+        printf("shipyard gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, a, parity);
+        asm volatile("trap;");
+      }
+    }
   } while (!ok);
 }
 DEVI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -446,7 +457,9 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-        const int tile = w / splits, sp = w % splits;
+        // K-split-major order: concurrently running CTAs work on the SAME pixel range (K-split) for different output tiles, so
+        // x / dY stream from HBM once and are shared through L2 instead of being re-streamed once per tile
+        const int tile = w % num_mn, sp = w / num_mn;
         const int n_blk = tile / num_m, m_blk = tile % num_m;
         const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
         // slabs that start beyond the matrix edge are not loaded at all: their smem stays stale, which only
@@ -481,7 +494,7 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       constexpr uint32_t idesc = make_idesc<BN, true, true>();
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-        const int sp = w % splits;
+        const int sp = w / num_mn;
         const int kb0 = (int)((long)sp * num_k / splits), kb1 = (int)((long)(sp + 1) * num_k / splits);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -505,7 +518,7 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     const int ew = warp - 4, et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-      const int tile = w / splits;
+      const int tile = w % num_mn;
       const int n_blk = tile / num_m, m_blk = tile % num_m;
       __nv_bfloat16* const out = out_base;
       float* const ws = ws_base;
@@ -924,6 +937,251 @@ gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   epoch_store(comm, ep);
 }
 
+// ===================================================================================================
+// CTA-pair (cta_group::2) variant of the TN GEMM / implicit-GEMM convolution: two SMs of one TPC form a cluster and
+// execute ONE tcgen05.mma of M = 256: each CTA stages its own 128 rows of A and HALF of the B tile (N/2 rows), the
+// leader's single thread issues the MMA for both, and each CTA's TMEM receives its 128 accumulator rows.  Per SM and
+// k-block this moves 16 KB (A) + BN/2 x 128 B (B) for 128 x BN x 64 MACs — a third less L2->SM traffic than the 1-CTA
+// kernel at BN = 256, and half the shared-memory operand reads per MMA (the N = 64 / 128 layers stop being smem-bound).
+//   full_bar   (leader's)  <- TMA complete_tx from BOTH CTAs (cp.async.bulk.tensor...cta_group::2, peer bit cleared)
+//   empty_bar  (each CTA)  <- tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11)
+//   tmem_full  (each CTA)  <- same multicast commit after the last k-block
+//   tmem_empty (leader's)  <- remote mbarrier.arrive from both CTAs' epilogue threads
+// ===================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the even (leader) CTA of the pair
+constexpr uint64_t kCacheHintNormal = 0x1000000000000000ull;
+
+DEVI uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+DEVI void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+DEVI void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(kCacheHintNormal) : "memory");
+}
+DEVI void tma_load_im2col_4d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n),
+                 "h"(off_w), "h"(off_h), "l"(kCacheHintNormal) : "memory");
+}
+DEVI void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+DEVI void umma_commit_2sm(uint64_t* bar) {           // arrives on `bar` in BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+DEVI void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int NCOLS> DEVI void tmem_alloc_2sm(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> DEVI void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BN> struct Cfg2 {
+  static constexpr int kABytes = BM * BK * 2;                 // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * BK * 2;           // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCBytes = BM * kEpiChunk * 2;
+  static constexpr int kBudget = 227 * 1024 - 1024 - 256 - 512;
+  static constexpr int kStages = ((kBudget - 2 * kCBytes) / kStageBytes) > 8 ? 8 : ((kBudget - 2 * kCBytes) / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 + 256;
+};
+
+template <int BN, bool kStats, bool kConv>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, float* __restrict__ stats, const ConvGeom geom) {
+  using C = Cfg2<BN>;
+  constexpr int BM2 = 2 * BM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint8_t* smem_c = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C::kCBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (M + BM2 - 1) / BM2, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
+  const int num_tiles = num_m * num_n;
+  constexpr int kChunks = BN / kEpiChunk;
+  constexpr int kActiveGroups = kChunks < kEpiGroups ? kChunks : kEpiGroups;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_c); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kEpiThreads * kActiveGroups); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();                 // both CTAs' barriers are initialised before any remote arrive / complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier) ====
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int n_blk = t / num_m, m_blk = t % num_m;
+        const int m0 = m_blk * BM2 + (int)rank * BM;
+        int cn = 0, ch = 0, cw = 0;
+        if constexpr (kConv) {
+          const int pq = geom.P * geom.Q;
+          cn = m0 / pq; const int rem = m0 - cn * pq, p0 = rem / geom.Q;
+          ch = geom.lower + geom.stride * p0; cw = geom.lower + geom.stride * (rem - p0 * geom.Q);
+        }
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2u * C::kStageBytes);
+          if constexpr (kConv) {
+            const int tap = kb / geom.cblocks, cb = kb - tap * geom.cblocks, r = tap / geom.S, sx = tap - r * geom.S;
+            tma_load_im2col_4d_2sm(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], cb * 64, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+          } else {
+            tma_load_2d_2sm(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m0);
+          }
+          tma_load_2d_2sm(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only, one thread, M = 256 across the pair =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);             // bytes of BOTH CTAs have landed
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage]);             // frees the stage in both CTAs
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);                 // publishes the accumulator to both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: each CTA drains its own 128 accumulator rows =====================
+    const int grp = (warp - 4) >> 2;
+    if (grp < kChunks) {
+      const int ew = warp & 3, et = threadIdx.x - 128 - grp * 128;
+      const int row = ew * 32 + lane;
+      const bool issuer = et == 0;
+      const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+      uint8_t* cbuf = smem_c + grp * C::kCBytes;
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr int kMyChunks = (kChunks + kEpiGroups - 1) / kEpiGroups;
+      float st[kMyChunks][4];
+#pragma unroll
+      for (int c = 0; c < kMyChunks; ++c) { st[c][0] = st[c][1] = st[c][2] = st[c][3] = 0.f; }
+      int cur_n = -1;
+      auto flush_stats = [&](int n_blk) {
+        if (!kStats || n_blk < 0) return;
+        const int wcol = et & 31;
+#pragma unroll
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = grp + ci * kEpiGroups;
+          if (c < kChunks) {
+            const int col = n_blk * BN + c * kEpiChunk + 2 * wcol;
+            if (col < N) { atomicAdd(&stats[col], st[ci][0]); atomicAdd(&stats[N + col], st[ci][2]); }
+            if (col + 1 < N) { atomicAdd(&stats[col + 1], st[ci][1]); atomicAdd(&stats[N + col + 1], st[ci][3]); }
+          }
+          st[ci][0] = st[ci][1] = st[ci][2] = st[ci][3] = 0.f;
+        }
+      };
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int n_blk = t / num_m, m_blk = t % num_m;
+        const int m0 = m_blk * BM2 + (int)rank * BM;
+        if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+        uint32_t v[2][32];
+        tmem_ld32(tbase + grp * kEpiChunk, v[0]);
+        tmem_ld32(tbase + grp * kEpiChunk + 32, v[1]);
+#pragma unroll
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = grp + ci * kEpiGroups;
+          if (c >= kChunks) break;
+          tmem_ld_wait();
+          const bool last = c + kEpiGroups >= kChunks;
+          if (last) { tc_fence_before(); mbar_arrive_leader(&tmem_empty[acc]); }
+          const int n0 = n_blk * BN + c * kEpiChunk;
+          uint4 w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
+            w[q] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+          if (!last) {
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk, v[0]);
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk + 32, v[1]);
+          }
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_a, kEpiThreads);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w[q];
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, kEpiThreads);
+          if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m0); tma_store_commit(); }
+          if (kStats) {
+            const int wcol = et & 31, rgrp = et >> 5;
+            const int q = wcol >> 2, wi = wcol & 3;
+            const int rows_valid = M - m0;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = rgrp * 32; r < rgrp * 32 + 32; ++r) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(cbuf + r * 128 + ((q ^ (r & 7)) << 4) + wi * 4);
+              const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
+              if (r < rows_valid) { s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); }
+            }
+            st[ci][0] += s0; st[ci][1] += s1; st[ci][2] += q0; st[ci][3] += q1;
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      flush_stats(cur_n);
+      if (issuer) tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                 // the peer's smem / TMEM stay alive until every MMA and epilogue of the pair is done
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_2sm<C::kTmemCols>(tmem_base); }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1078,6 +1336,71 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, bias, stats, max_ctas, s);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// CTA-pair launches.  Requirements on top of the 1-CTA entry points: N %% block_n == 0 (each CTA loads exactly half a B tile).
+template <int BN>
+int launch_2cta(bool conv, const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, float* stats,
+                const ConvGeom& g, const int* im2col /* Nb,H,W,C,R,S,pad,stride or null */, int max_ctas, cudaStream_t s) {
+  using C = Cfg2<BN>;
+  CUtensorMap ta, tb, tc;
+  if (conv) { if (!make_im2col_map(&ta, A, im2col[0], im2col[1], im2col[2], im2col[3], im2col[4], im2col[5], im2col[6], im2col[7], BM)) return 3; }
+  else if (!make_map(&ta, A, K, M, lda, BK, BM)) return 3;
+  if (!make_map(&tb, B, K, N, ldb, BK, BN / 2) || !make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
+  int pairs = tiles < sms / 2 ? tiles : sms / 2;
+  if (max_ctas > 1 && pairs > max_ctas / 2) pairs = max_ctas / 2;
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    kern<<<2 * pairs, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, stats, g);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  if (conv) return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, true>);
+  return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, false>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false>);
+}
+
+extern "C" int sy_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, float* stats,
+                                    int block_n, int max_ctas, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda | ldb | ldc) & 7 || ((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) {
+    snprintf(g_err, sizeof g_err, "alignment: pointers must be 16B aligned and leading dimensions multiples of 8"); return 1;
+  }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
+  if (block_n <= 0) block_n = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0);
+  if (block_n == 0 || N % block_n) { snprintf(g_err, sizeof g_err, "2-CTA GEMM needs N %% block_n == 0 (block_n 128 or 256)"); return 1; }
+  ConvGeom g{};
+  switch (block_n) {
+    case 128: return launch_2cta<128>(false, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
+    case 256: return launch_2cta<256>(false, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 128 or 256");
+  return 1;
+}
+
+// fprop only: out[N,P,Q,Cout] = conv(act[N,H,W,Cin], wgt[Cout,R,S,Cin]) on CTA pairs.  N*P*Q %% 256 == 0, Cout %% block_n == 0.
+extern "C" int sy_conv_bf16_nhwc_2cta(const void* act, const void* wgt, void* out, int Nb, int H, int W, int Cin, int Cout, int R, int S,
+                                      int pad, int stride, float* stats, int block_n, int max_ctas, void* stream) {
+  if (Cin % 64 || ((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out) & 15) { snprintf(g_err, sizeof g_err, "conv: Cin %% 64, aligned tensors"); return 1; }
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (((long)Nb * P * Q) % (2 * BM)) { snprintf(g_err, sizeof g_err, "2-CTA conv: N*P*Q must be a multiple of 256"); return 1; }
+  if (!load_encode() || !load_encode_im2col()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncode* unavailable (no driver?)"); return 6; }
+  if (block_n <= 0) block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 0);
+  if (block_n == 0 || Cout % block_n) { snprintf(g_err, sizeof g_err, "2-CTA conv needs Cout %% block_n == 0 (block_n 128 or 256)"); return 1; }
+  const int M = Nb * P * Q, K = R * S * Cin;
+  ConvGeom g{P, Q, S, R * S, Cin / 64, stride, -pad, 0};
+  const int geo[8] = {Nb, H, W, Cin, R, S, pad, stride};
+  switch (block_n) {
+    case 128: return launch_2cta<128>(true, act, wgt, out, M, Cout, K, 0, K, Cout, stats, g, geo, max_ctas, (cudaStream_t)stream);
+    case 256: return launch_2cta<256>(true, act, wgt, out, M, Cout, K, 0, K, Cout, stats, g, geo, max_ctas, (cudaStream_t)stream);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 128 or 256");
   return 1;
 }
 

@@ -212,3 +212,36 @@ def test_conv_dispatcher_modes_agree_with_reference(mode):
             assert all(v["fprop"] == "cudnn" and v["dgrad"] == "cudnn" and v["wgrad"] == "cudnn" for v in tab.values())
     finally:
         conv.set_mode("auto")
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (512, 256, 256), (4096, 512, 1024), (128 * 7 + 40, 256, 192), (8192, 1024, 512), (50176, 256, 64)])
+@pytest.mark.parametrize("block_n", [0, 128])
+def test_gemm_two_cta_pairs(m, n, k, block_n):
+    """cta_group::2: one M=256 MMA per CTA pair, B split across the pair, multicast commits."""
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(m + n + k + 1)
+    a = (torch.randn(m, k, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(n, k, device="cuda") * 0.5).to(torch.bfloat16)
+    stats = torch.zeros(2 * n, dtype=torch.float32, device="cuda")
+    out = gemm.gemm_tn(a, b, block_n=block_n, two_cta=True, stats=stats)
+    ref = a.float() @ b.float().t()
+    torch.testing.assert_close(out.float(), ref, atol=0.02 * (k ** 0.5) * 0.25 + 0.02, rtol=2e-2)
+    torch.testing.assert_close(stats[:n], out.float().sum(0), atol=1.0, rtol=5e-3)
+    out2 = gemm.gemm_tn(a, b, block_n=block_n, two_cta=True, max_ctas=4)      # persistent pairs: accumulator ping-pong across tiles
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,k,stride", [(8, 64, 16, 16, 128, 3, 1), (4, 128, 16, 16, 256, 3, 1), (16, 256, 8, 8, 256, 3, 1), (16, 128, 16, 16, 128, 3, 2),
+                                                       (16, 256, 16, 16, 512, 1, 2)])
+def test_conv_fprop_two_cta_pairs(n, cin, h, w, cout, k, stride):
+    from batch_shipyard_b200.ops import gemm
+    import torch.nn.functional as F
+    torch.manual_seed(n + cin + cout)
+    pad = k // 2
+    x = (torch.randn(n, cin, h, w, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda") * (1.0 / (cin * k * k) ** 0.5)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    stats = torch.zeros(2 * cout, dtype=torch.float32, device="cuda")
+    y = gemm.conv_fprop_nhwc(x, wt, stride, pad, stats=stats, two_cta=True)
+    ref = F.conv2d(x.float(), wt.float(), stride=stride, padding=pad)
+    torch.testing.assert_close(y.float(), ref, atol=0.03, rtol=2e-2)
+    torch.testing.assert_close(stats[:cout], y.float().sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
