@@ -1,0 +1,8 @@
+#!/bin/bash
+# 1-GPU round: re-check after removing the device printf; full pytest log kept.
+set -x
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_gemm.py -m gpu -q 2>&1 > gpurun_out/pytest_gemm13_full.log; tail -5 gpurun_out/pytest_gemm13_full.log
+timeout 200 python bench/gemm_bench.py 2>&1 | tee gpurun_out/gemm_bench13.log | tail -3
+timeout 300 python bench/conv_bench.py 2>&1 | tee gpurun_out/conv_bench13.log | tail -3
+timeout 200 python bench/wgrad_bench.py 2>&1 | tee gpurun_out/wgrad_bench13.log | tail -3

@@ -70,8 +70,7 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
       else if (t - t0 > 4000000000ull) {
-        printf("shipyard gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, a, parity);
-        asm volatile("trap;");
+        asm volatile("trap;");        // surfaces as a launch failure on the host (no device printf: it costs stack + spills)
       }
     }
   } while (!ok);
@@ -1452,7 +1451,7 @@ extern "C" int sy_conv_bf16_wgrad(const void* x, const void* dy, void* dw, int N
     if (!make_im2col_map(&ta, x, Nb, H, W, Cin, R, S, pad, stride, 64) || !make_map(&tb, dy, J, K, J, 64, BK)) return 3;
     const int tiles = ((I + BM - 1) / BM) * ((J + BN - 1) / BN), num_k = (K + BK - 1) / BK;
     int sp = splits;
-    if (sp <= 0) { sp = (sms + tiles - 1) / tiles; if (sp > num_k / 4) sp = num_k / 4; }
+    if (sp <= 0) { sp = sms / tiles; if (sp > num_k / 4) sp = num_k / 4; }     // floor: tiles * sp <= #SMs, a single wave
     if (sp < 1) sp = 1;
     if (sp > num_k) sp = num_k;
     if (sp > 1 && (!ws || !tickets)) { snprintf(g_err, sizeof g_err, "split-K needs a workspace"); return 2; }
