@@ -185,6 +185,20 @@ struct ConvGeom {
   int flip;          // dgrad: B is W[co][taps-1-tap][ci] read through a 3D map as an MN-major operand
 };
 
+// Tile rasterisation: tiles are numbered in groups of kGroupM row-blocks x all column-blocks, row-block fastest inside a group.
+// The ~148 tiles in flight at any time then touch only ~kGroupM row-blocks of A and ~148/kGroupM column-blocks of B, which
+// fit in the 126 MB L2 — with the plain row-fastest order a large A (or the activations of a wide 1x1 conv) is streamed from
+// HBM once per column-block.
+constexpr int kGroupM = 16;
+DEVI void tile_to_mn(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * num_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int first_m = g * kGroupM;
+  const int gm = (num_m - first_m) < kGroupM ? (num_m - first_m) : kGroupM;
+  m_blk = first_m + r % gm;
+  n_blk = r / gm;
+}
+
 template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
@@ -236,7 +250,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_blk = t / num_m, m_blk = t % num_m;
+        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
         int cn = 0, ch = 0, cw = 0;
         if constexpr (kConv) {               // first output pixel of this M tile -> base-pixel coordinates
           const int pq = geom.P * geom.Q, m0 = m_blk * BM;
@@ -338,7 +352,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_blk = t / num_m, m_blk = t % num_m;
+        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
         if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -1042,7 +1056,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int n_blk = t / num_m, m_blk = t % num_m;
+        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * BM2 + (int)rank * BM;
         int cn = 0, ch = 0, cw = 0;
         if constexpr (kConv) {
@@ -1119,7 +1133,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       };
       for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int n_blk = t / num_m, m_blk = t % num_m;
+        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * BM2 + (int)rank * BM;
         if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
         mbar_wait(&tmem_full[acc], acc_phase);
