@@ -303,6 +303,16 @@ class Communicator:
                                                     grads.numel(), 1 if zero_grads else 0, self._stream(stream)),
                     "fused_allreduce_sgd")
 
+    def fused_allreduce_adam(self, grad, param, m, v, hyper, scale: Optional[float] = None, zero_grad: bool = True, stream=None) -> None:
+        """One launch: gradient all-reduce (x scale, default 1/world) + Adam on this rank's parameter replica.
+        grad/param/m/v: fp32 flat tensors (numel % 4 == 0, <= 256 Ki); hyper: fp32 [lr, beta1, beta2, eps, step] on the device."""
+        assert grad.dtype == param.dtype == m.dtype == v.dtype == torch.float32 and grad.numel() % 4 == 0
+        self.lib.sy_fused_allreduce_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                     C.c_float, C.c_int, C.c_void_p]
+        self._check(self.lib.sy_fused_allreduce_adam(self._h, self._p(grad), self._p(param), self._p(m), self._p(v), self._p(hyper),
+                                                     grad.numel(), float(1.0 / self.world if scale is None else scale),
+                                                     1 if zero_grad else 0, self._stream(stream)), "fused_allreduce_adam")
+
     def all_reduce_fp8(self, inp, out_q, out_scales, scale: float = 1.0, stream=None) -> None:
         assert inp.numel() % 128 == 0 and out_q.numel() == inp.numel() and out_scales.numel() == inp.numel() // 32
         self._check(self.lib.sy_allreduce_fp8_blockscaled(self._h, self._p(inp), _DT[inp.dtype], self._p(out_q),

@@ -391,6 +391,13 @@ extern "C" int sy_fused_allreduce_sgd(sy_comm* c, void* grads, int dt_grad, void
   return k_fused_sgd(c, g_off, dt_grad, p_off, dt_param, master, mom, hyper, count, zero_grads, stream);
 }
 
+extern "C" int sy_fused_allreduce_adam(sy_comm* c, float* grad, float* param, float* m, float* v, float* hyper, size_t count,
+                                       float scale, int zero_grad, sy_stream_t stream) {
+  if (count == 0) return SY_OK;
+  if (is_stub(c)) return stub_fused_adam(c, grad, param, m, v, hyper, count, scale, zero_grad);
+  return k_oneshot_adam(c, grad, param, m, v, hyper, count, scale, zero_grad, stream);
+}
+
 extern "C" int sy_allreduce_fp8_blockscaled(sy_comm* c, const void* in, int dt_in, void* out_q, void* out_scales,
                                             size_t count, float scale, sy_stream_t stream) {
   if (is_stub(c)) return stub_allreduce_fp8(c, in, dt_in, out_q, out_scales, count, scale);

@@ -125,6 +125,8 @@ int k_put_signal(sy_comm* c, const void* src, size_t dst_off, size_t bytes, int 
 int k_wait_signal(sy_comm* c, int sig, uint32_t expected, void* stream);
 int k_halo(sy_comm* c, const void* src, int dt, const sy_halo_desc* descs, int ndesc,
            const int* wait_sig, int nwait, void* stream);
+int k_oneshot_adam(sy_comm* c, float* grad, float* param, float* m, float* v, float* hyper, size_t count, float scale, int zero_grad, void* stream);
+int stub_fused_adam(sy_comm* c, float* grad, float* param, float* m, float* v, float* hyper, size_t count, float scale, int zero_grad);
 int k_fused_sgd(sy_comm* c, size_t grads_off, int dt_grad, size_t params_off, int dt_param,
                 float* master, float* mom, const float* hyper, size_t count, int zero_grads,
                 void* stream);

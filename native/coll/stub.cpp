@@ -8,6 +8,7 @@
 #include <math.h>
 #include <sched.h>
 #include <string.h>
+#include <vector>
 #include <sys/mman.h>
 #include <time.h>
 #include <unistd.h>
@@ -310,6 +311,30 @@ int stub_fused_sgd(sy_comm* c, void* grads, int dt_grad, void* params, int dt_pa
   }
   if ((e = stub_barrier(c))) return e;
   if (zero_grads) memset(grads, 0, count * sy_dtype_size(dt_grad));
+  return stub_barrier(c);
+}
+
+int stub_fused_adam(sy_comm* c, float* grad, float* param, float* m, float* v, float* hyper, size_t count, float scale, int zero_grad) {
+  const void* srcs[SY_MAXR];
+  int e = publish(c, grad, count * sizeof(float), srcs);
+  if (e) return e;
+  if ((e = stub_barrier(c))) return e;
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], t = hyper[4] + 1.0f;
+  const float c1 = 1.0f - powf(b1, t), c2 = 1.0f - powf(b2, t);
+  std::vector<float> g(count);
+  for (size_t i = 0; i < count; ++i) {
+    float a = 0.f;
+    for (int r = 0; r < c->world; ++r) a += ((const float*)srcs[r])[i];
+    g[i] = a * scale;
+  }
+  if ((e = stub_barrier(c))) return e;          // everyone has read every gradient before anyone zeroes it
+  for (size_t i = 0; i < count; ++i) {
+    m[i] = b1 * m[i] + (1.0f - b1) * g[i];
+    v[i] = b2 * v[i] + (1.0f - b2) * g[i] * g[i];
+    param[i] -= (lr / c1) * m[i] / (sqrtf(v[i]) / sqrtf(c2) + eps);
+  }
+  hyper[4] = t;
+  if (zero_grad) memset(grad, 0, count * sizeof(float));
   return stub_barrier(c);
 }
 

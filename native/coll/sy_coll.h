@@ -137,6 +137,12 @@ int sy_fused_allreduce_sgd(sy_comm* c, void* grads, int dt_grad, void* params, i
                            float* master, float* mom, const float* hyper, size_t count,
                            int zero_grads, sy_stream_t stream);
 
+// One-shot gradient all-reduce (averaged by `scale`) fused with the Adam update of every rank's own parameter replica:
+// grad/param/m/v are local fp32 arrays of `count` elements (count % 4 == 0, <= 256 Ki elements), hyper = device floats
+// {lr, beta1, beta2, eps, step}; step is advanced by the kernel.  One launch per training step.
+int sy_fused_allreduce_adam(sy_comm* c, float* grad, float* param, float* m, float* v, float* hyper, size_t count,
+                            float scale, int zero_grad, sy_stream_t stream);
+
 // All-reduce whose output is block-scaled fp8: out_q[i] (e4m3) and one e8m0
 // scale byte per 32 elements (MX format), reduced in fp32 (K11).
 int sy_allreduce_fp8_blockscaled(sy_comm* c, const void* in, int dt_in, void* out_q,

@@ -6,7 +6,7 @@ The reference runs TF-1.2 ``mnist_replica.py`` with one parameter server and N w
 mnist_replica.py:59-80,111-181): 784 -> 100 (ReLU) -> 10 softmax, batch 100, Adam(0.01),
 ``train_steps``, optional ``sync_replicas``.  Same model and flags here; the parameter server is replaced
 by a synchronous all-reduce of the 79,510-parameter gradient (318 KB fp32: the latency-bound regime,
-served by the one-shot push kernel) fused with the 1/N averaging; every replica then applies Adam.
+served by the one-shot push kernel) fused with the 1/N averaging AND the Adam update of every replica (one launch per step).
 TensorFlow is not installed in this image, so the model is PyTorch; data is synthetic MNIST-shaped.
 """
 import argparse
@@ -55,7 +55,10 @@ def main():
         p = flat[off:off + s].view(shape).requires_grad_(True)
         p.grad = grad[off:off + s].view(shape)
         views.append(p); off += s
-    opt = torch.optim.Adam(views, lr=a.learning_rate)
+    # Adam state for the fused kernel: one launch = gradient all-reduce (1/N fused) + Adam on this replica + gradient zeroing
+    adam_m = torch.zeros(npad, dtype=torch.float32, device=dev)
+    adam_v = torch.zeros(npad, dtype=torch.float32, device=dev)
+    hyper = torch.tensor([a.learning_rate, 0.9, 0.999, 1e-8, 0.0], dtype=torch.float32, device=dev)
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.rand(a.batch_size, 784, generator=g).to(dev)
     y = torch.randint(0, 10, (a.batch_size,), generator=g).to(dev)
@@ -63,11 +66,8 @@ def main():
     def step():
         logits = F.linear(torch.relu(F.linear(x, views[0], views[1])), views[2], views[3])
         loss = F.cross_entropy(logits, y)
-        grad.zero_()
-        loss.backward()
-        if a.sync_replicas and world > 1:
-            comm.all_reduce(grad, grad, scale=1.0 / world)    # one-shot push over NVLink, averaging fused in
-        opt.step()
+        loss.backward()                                  # accumulates into `grad` (zeroed by the fused kernel)
+        comm.fused_allreduce_adam(grad, flat, adam_m, adam_v, hyper, scale=(1.0 / world) if a.sync_replicas else 1.0)
         return loss
 
     for _ in range(20):

@@ -226,6 +226,26 @@ def main():
             checks += 1
         comm.barrier(); sync()
         comm.reset_heap()
+    # ---- fused one-shot all-reduce + Adam (every rank updates its own replica) ----
+    n = 4 * 5003
+    w0 = gen(77, n, torch.float32, "cpu", salt=41)
+    param = w0.clone().to(dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    grad = torch.zeros(n, device=dev)
+    lr, b1, b2, eps = 0.01, 0.9, 0.999, 1e-8
+    hyper = torch.tensor([lr, b1, b2, eps, 0.0], dtype=torch.float32, device=dev)
+    ref_p = torch.nn.Parameter(w0.clone().to(torch.float64))
+    ref_opt = torch.optim.Adam([ref_p], lr=lr, betas=(b1, b2), eps=eps)
+    for step in range(4):
+        grad.copy_(gen(R, n, torch.float32, dev, salt=43 + step)); sync()
+        comm.fused_allreduce_adam(grad, param, m, v, hyper)
+        sync()
+        ref_p.grad = ref_sum(W, n, torch.float32, salt=43 + step) / W
+        ref_opt.step()
+        err = (param.cpu().double() - ref_p.detach()).abs().max().item()
+        assert err < 2e-5, f"fused all-reduce + Adam step {step}: max err {err}"
+        assert float(grad.abs().max()) == 0.0 and abs(float(hyper[4]) - (step + 1)) < 1e-6
+        checks += 1
+    comm.barrier(); sync()
     # ---- fp8 block-scaled all-reduce -----------------------------------------
     n = 128 * 41 * W
     xin = comm.alloc(n, torch.bfloat16)
