@@ -143,3 +143,97 @@ def shell(b, config: dict, kind: str, node_name, command) -> dict:
         return ctx
     p = subprocess.run(" ".join(command), shell=True, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return dict(ctx, exit_code=p.returncode, output=p.stdout)
+
+
+# ---- daemon / slurmctld entry points ---------------------------------------------------------------------------------
+def expand_hostlist(spec: str) -> list[str]:
+    """Slurm hostlist expression -> names: ``c-p-pool-[0-2,5],login0`` (what slurmctld passes to Resume/SuspendProgram)."""
+    out, depth, cur = [], 0, ""
+    for ch in spec:
+        if ch == "[":
+            depth += 1
+        elif ch == "]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur); cur = ""
+        else:
+            cur += ch
+    if cur:
+        out.append(cur)
+    names = []
+    for item in out:
+        if "[" not in item:
+            names.append(item); continue
+        prefix, rest = item.split("[", 1)
+        body, suffix = rest.rsplit("]", 1)
+        for part in body.split(","):
+            if "-" in part:
+                lo, hi = part.split("-", 1)
+                width = len(lo)
+                names += [f"{prefix}{str(i).zfill(width)}{suffix}" for i in range(int(lo), int(hi) + 1)]
+            else:
+                names.append(f"{prefix}{part}{suffix}")
+    return names
+
+
+def process_retry_queue(b, config: dict, max_messages: int = 32) -> dict:
+    """One daemon pass: re-drive resumes that failed earlier (bounded by MAX_RESUME_FAILURE_ATTEMPTS)."""
+    cid = S.slurm_options(config)["cluster_id"]
+    q = f"slurm-retry-{cid}"
+    retried, dropped = [], []
+    for msg in b.store.get_messages(q, n=max_messages, visibility_timeout=30.0):
+        body = msg["body"]
+        host = b.store.try_get("slurmhost", cid, body["host"])
+        b.store.delete_message(q, msg["id"], msg.get("pop_receipt"))
+        if host is None or host.get("state") in ("up", "provisioning_error"):
+            dropped.append(body["host"]); continue
+        r = resume(b, config, [body["host"]])
+        (retried if r["resumed"] else dropped).append(body["host"])
+    return {"retried": retried, "dropped": dropped}
+
+
+def daemon(b, config: dict, poll_interval: float = 5.0, max_iterations: int = 0) -> dict:
+    """Long-running companion of slurmctld (reference: `slurm.py daemon`): drains the retry queue every poll interval."""
+    it, total = 0, {"retried": 0, "dropped": 0}
+    while max_iterations <= 0 or it < max_iterations:
+        r = process_retry_queue(b, config)
+        total["retried"] += len(r["retried"]); total["dropped"] += len(r["dropped"])
+        it += 1
+        if max_iterations <= 0 or it < max_iterations:
+            time.sleep(poll_interval)
+    return dict(total, iterations=it)
+
+
+def main(argv=None) -> int:
+    """``python -m batch_shipyard_b200.slurm.cluster <resume|suspend|resume-fail|daemon> --conf slurm.yaml [--hosts LIST]``
+    — the programs a slurm.conf generated by ``slurm_conf`` points ResumeProgram / SuspendProgram / ResumeFailProgram at."""
+    import argparse
+    import json
+    from ..backend.local import LocalBackend
+    from ..config.loader import load_file
+    ap = argparse.ArgumentParser(prog="shipyard-slurm")
+    ap.add_argument("verb", choices=["resume", "suspend", "resume-fail", "daemon"])
+    ap.add_argument("--conf", required=True)
+    ap.add_argument("--hosts", default="")
+    ap.add_argument("--state-dir", default=os.environ.get("SHIPYARD_STATE_DIR"))
+    ap.add_argument("--poll-interval", type=float, default=5.0)
+    ap.add_argument("--iterations", type=int, default=0)
+    a = ap.parse_args(argv)
+    config = load_file(a.conf)
+    b = LocalBackend(state_dir=a.state_dir) if a.state_dir else LocalBackend()
+    hosts = expand_hostlist(a.hosts) if a.hosts else []
+    if a.verb == "resume":
+        out = resume(b, config, hosts)
+    elif a.verb == "suspend":
+        out = suspend(b, config, hosts)
+    elif a.verb == "resume-fail":
+        out = resume_failed(b, config, hosts)
+    else:
+        out = daemon(b, config, a.poll_interval, a.iterations)
+    print(json.dumps(out))
+    return 0 if not out.get("failed") else 1
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

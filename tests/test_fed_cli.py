@@ -167,3 +167,24 @@ def test_cli_surface_and_commands(tmp_path, monkeypatch):
     assert res.exit_code == 1 and "unknown key" in res.output
     res = r.invoke(cli.cli, ["pool", "del", "--configdir", recipe, "-y", "--raw"], obj=cli.CliContext())
     assert json.loads(res.output)["deleted"] is True
+
+
+def test_slurm_hostlist_and_retry_daemon(tmp_path):
+    """slurmctld-facing entry points: hostlist expansion, resume failure -> retry queue -> daemon pass."""
+    from batch_shipyard_b200.backend.local import LocalBackend
+    from batch_shipyard_b200.slurm import cluster as sl
+    assert sl.expand_hostlist("c-p-pool-[0-2,5],login0") == ["c-p-pool-0", "c-p-pool-1", "c-p-pool-2", "c-p-pool-5", "login0"]
+    assert sl.expand_hostlist("n[08-10]") == ["n08", "n09", "n10"]
+    b = LocalBackend(state_dir=str(tmp_path / "st"))
+    cfg = {"slurm": {"cluster_id": "sc", "slurm_options": {"elastic_partitions": {}}}}
+    cid = "sc"
+    b.store.insert("slurmhost", cid, "sc-p-nopool-0", {"state": "suspended", "pool_id": "missing-pool", "resume_failures": 0})
+    r = sl.resume(b, cfg, ["sc-p-nopool-0", "ghost"])
+    assert [f["host"] for f in r["failed"]] == ["sc-p-nopool-0", "ghost"]
+    assert b.store.get("slurmhost", cid, "sc-p-nopool-0")["resume_failures"] == 1
+    assert len(b.store.peek_messages(f"slurm-retry-{cid}")) == 1
+    out = sl.daemon(b, cfg, poll_interval=0.0, max_iterations=1)       # the retry fails again -> a new retry message, count 2
+    assert out["iterations"] == 1 and out["dropped"] == 1
+    assert b.store.get("slurmhost", cid, "sc-p-nopool-0")["resume_failures"] == 2
+    sl.resume_failed(b, cfg, ["sc-p-nopool-0"])
+    assert b.store.get("slurmhost", cid, "sc-p-nopool-0")["state"] == "suspended"
