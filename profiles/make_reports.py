@@ -165,7 +165,8 @@ def main():
     if p:
         step_breakdown(p, os.path.join(P, "step_breakdown.md"))
     coll_tables(os.path.join(P, "coll_sweeps.md"))
-    for name, title in (("gemm_bench.jsonl", "tcgen05 TN GEMM vs cuBLAS"), ("wgrad_bench.jsonl", "split-K MN-major wgrad / MN-major-B dgrad vs cuBLAS")):
+    for name, title in (("gemm_bench.jsonl", "tcgen05 TN GEMM (1-CTA and CTA-pair) vs cuBLAS"), ("wgrad_bench.jsonl", "split-K MN-major wgrad / MN-major-B dgrad vs cuBLAS"),
+                        ("conv_bench.jsonl", "TMA-im2col implicit-GEMM convolution (fprop / dgrad / wgrad) vs cuDNN, ResNet-50 shapes at batch 256")):
         fp = os.path.join(G, name)
         if os.path.exists(fp):
             simple_table(jsonl(fp), os.path.join(P, name.replace(".jsonl", ".md")), title,
@@ -175,6 +176,20 @@ def main():
         simple_table(jsonl(p), os.path.join(P, "bn_bench.md"), "Fused BN(+ReLU) forward / backward bandwidth per ResNet-50 layer shape (batch 256)",
                      "Cold operands (buffer ring > 2x L2). Includes autograd/Python launch overhead, which dominates the small layers (in the model the step is a CUDA graph).")
     bench_lines(os.path.join(P, "bench_history.md"))
+    cp = os.path.join(G, "conv_plan.json")
+    if os.path.exists(cp):
+        tab = json.load(open(cp))
+        rows = [dict({"shape n x cin x h x w x cout x k x stride": k}, fprop=v["fprop"], fused_bn_stats=v["stats"], dgrad=v["dgrad"], wgrad=v["wgrad"],
+                     **{kk: vv for kk, vv in (v.get("timings_us") or {}).items()}) for k, v in tab.items()]
+        keys = []
+        for r in rows:
+            for k in r:
+                if k not in keys:
+                    keys.append(k)
+        rows = [{k: r.get(k, "") for k in keys} for r in rows]
+        simple_table(rows, os.path.join(P, "conv_dispatch_plan.md"), "Convolution dispatcher: measured per-pass choice per layer shape (us)",
+                     "`ops/conv.py` times the tcgen05 implicit-GEMM kernels against cuDNN the first time a shape is seen and keeps the faster per pass; "
+                     "fprop timings include the separate BN-statistics pass when the epilogue does not produce them.")
     for name in ("k10_bench_n8.log", "hpcg7_n1.log", "hpcg6_n1.log"):
         fp = os.path.join(G, name)
         if os.path.exists(fp):
