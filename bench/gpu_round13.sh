@@ -6,3 +6,5 @@ timeout 400 python -m pytest tests/test_gpu_gemm.py -m gpu -q 2>&1 > gpurun_out/
 timeout 200 python bench/gemm_bench.py 2>&1 | tee gpurun_out/gemm_bench13.log | tail -3
 timeout 300 python bench/conv_bench.py 2>&1 | tee gpurun_out/conv_bench13.log | tail -3
 timeout 200 python bench/wgrad_bench.py 2>&1 | tee gpurun_out/wgrad_bench13.log | tail -3
+SHIPYARD_CONV_PLAN_DUMP=1 timeout 300 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench13_n1_auto.log
+SHIPYARD_CONV_IMPL=tc timeout 300 python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench13_n1_tc.log
