@@ -10,3 +10,9 @@ for r in $(seq 0 $((NG-1))); do timeout 300 python tests/_k10_worker.py --rank $
 tail -2 gpurun_out/k10v2_r0.log | tee gpurun_out/k10v2_bench_n$NG.log
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29571 recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --n 256 --t 6 2>&1 | tail -2 | tee gpurun_out/hpcg11_n$NG.log
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus $NG --steps 15 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench11_n$NG.log
+# whole stack on GPUs: pool add (probe, node prep, cascade) + jobs add (native task runner -> MPI face -> device kernels)
+export SHIPYARD_STATE_DIR=$PWD/gpurun_out/state11_$$
+sed "s/dedicated: 2/dedicated: $NG/" recipes/mpiBench-OpenMPI/config/pool.yaml > /tmp/pool11.yaml
+timeout 200 ./shipyard pool add --configdir recipes/mpiBench-OpenMPI/config --pool /tmp/pool11.yaml -y 2>&1 | tail -5 | tee gpurun_out/recipe11_pool.log
+timeout 300 ./shipyard jobs add --configdir recipes/mpiBench-OpenMPI/config --pool /tmp/pool11.yaml --jobs recipes/mpiBench-OpenMPI/config/jobs-gpu.yaml --tail stdout.txt 2>&1 | tail -45 | tee gpurun_out/recipe11_mpibench.log
+rm -rf $SHIPYARD_STATE_DIR
