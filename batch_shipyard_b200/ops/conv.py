@@ -25,7 +25,7 @@ _HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics
 
 @dataclass
 class ConvPlan:
-    fprop: str = "cudnn"      # "tc" | "cudnn"
+    fprop: str = "cudnn"      # "tc" (1-CTA tcgen05) | "tc2" (CTA-pair, cta_group::2) | "cudnn"
     dgrad: str = "cudnn"
     wgrad: str = "cudnn"
     stats: bool = False       # fprop produces the BatchNorm statistics in its epilogue
@@ -98,22 +98,32 @@ def _time(fn, iters: int = 5, reps: int = 4) -> float:
 
 
 # ---- the individual passes ---------------------------------------------------------------------------------------------
-def _fprop_tc(x, w, stride, pad, stats):
+def _fprop_tc(x, w, stride, pad, stats, two_cta=False):
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
-        y2 = _gemm.gemm_tn(x.permute(0, 2, 3, 1).reshape(n * h * wd, cin), w.permute(0, 2, 3, 1).reshape(cout, cin), stats=stats)
+        y2 = _gemm.gemm_tn(x.permute(0, 2, 3, 1).reshape(n * h * wd, cin), w.permute(0, 2, 3, 1).reshape(cout, cin), stats=stats, two_cta=two_cta)
         return y2.view(n, h, wd, cout).permute(0, 3, 1, 2)
-    return _gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats)
+    return _gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats, two_cta=two_cta)
 
 
-def _dgrad_tc(dy, x, w, stride, pad):
+def _dgrad_tc(dy, x, w, stride, pad, two_cta=False):
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
         dy2 = dy.permute(0, 2, 3, 1).reshape(n * h * wd, cout)
-        return _gemm.gemm_nn(dy2, w.permute(0, 2, 3, 1).reshape(cout, cin)).view(n, h, wd, cin).permute(0, 3, 1, 2)
-    return _gemm.conv_dgrad_nhwc(dy, w, pad)
+        return _gemm.gemm_nn(dy2, w.permute(0, 2, 3, 1).reshape(cout, cin), two_cta=two_cta).view(n, h, wd, cin).permute(0, 3, 1, 2)
+    return _gemm.conv_dgrad_nhwc(dy, w, pad, two_cta=two_cta)
+
+
+def _two_cta_caps(x, w, stride) -> dict:
+    """CTA-pair variants: M (pixels) multiple of 256, output channels multiple of 128."""
+    n, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    pad = k // 2
+    p, q = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
+    m_ok = (n * p * q) % 256 == 0
+    return {"fprop": m_ok and cout % 128 == 0, "dgrad": m_ok and cin % 128 == 0 and stride == 1}
 
 
 def _wgrad_tc(dy, x, w, stride, pad, out_view, accumulate):
@@ -156,7 +166,9 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
     if _MODE == "cudnn" or not any(caps.values()):
         return plan
     if _MODE == "tc":
-        return ConvPlan("tc" if caps["fprop"] else "cudnn", "tc" if caps["dgrad"] else "cudnn", "tc" if caps["wgrad"] else "cudnn",
+        c2 = _two_cta_caps(x, w, stride)
+        return ConvPlan(("tc2" if c2["fprop"] else "tc") if caps["fprop"] else "cudnn",
+                        ("tc2" if c2["dgrad"] else "tc") if caps["dgrad"] else "cudnn", "tc" if caps["wgrad"] else "cudnn",
                         stats=caps["fprop"] and (k > 1 or stride > 1 or cin >= 256), timings_us={})
     t = plan.timings_us
     with torch.no_grad():
@@ -164,18 +176,27 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
         y = F.conv2d(xd, wd_, None, stride, pad)
         t_stats_pass = y.numel() * 2 / _HBM_BPS * 1e6 + 3.0            # the separate statistics kernel a non-fused fprop needs
         t["fprop_cudnn"] = _time(lambda: F.conv2d(xd, wd_, None, stride, pad)) + t_stats_pass
+        caps2 = _two_cta_caps(x, w, stride)
         if caps["fprop"]:
             st = torch.zeros(2 * cout, dtype=torch.float32, device=x.device)
             t["fprop_tc_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st))
             t["fprop_tc"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None)) + t_stats_pass
-            best = min(("fprop_cudnn", "fprop_tc_stats", "fprop_tc"), key=lambda k_: t[k_])
-            plan.fprop = "cudnn" if best == "fprop_cudnn" else "tc"
-            plan.stats = best == "fprop_tc_stats"
+            cands = ["fprop_cudnn", "fprop_tc_stats", "fprop_tc"]
+            if caps2["fprop"]:
+                t["fprop_tc2_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st, True))
+                t["fprop_tc2"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None, True)) + t_stats_pass
+                cands += ["fprop_tc2_stats", "fprop_tc2"]
+            best = min(cands, key=lambda k_: t[k_])
+            plan.fprop = "cudnn" if best == "fprop_cudnn" else ("tc2" if "tc2" in best else "tc")
+            plan.stats = best.endswith("_stats")
         dy = torch.randn_like(y)
         t["dgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, True, False))
         if caps["dgrad"]:
             t["dgrad_tc"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad))
-            plan.dgrad = "tc" if t["dgrad_tc"] < t["dgrad_cudnn"] else "cudnn"
+            if caps2["dgrad"]:
+                t["dgrad_tc2"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad, True))
+            best = min([k_ for k_ in ("dgrad_cudnn", "dgrad_tc", "dgrad_tc2") if k_ in t], key=lambda k_: t[k_])
+            plan.dgrad = {"dgrad_cudnn": "cudnn", "dgrad_tc": "tc", "dgrad_tc2": "tc2"}[best]
         t_accum = w.numel() * 6 / 4e12 * 1e6 + 3.0                     # AccumulateGrad add the library path pays
         t["wgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, False, True)) + t_accum
         if caps["wgrad"]:
@@ -202,10 +223,10 @@ class _Conv(torch.autograd.Function):
         k = w.shape[2]
         pad = k // 2
         stats = None
-        if plan.fprop == "tc":
+        if plan.fprop in ("tc", "tc2"):
             if plan.stats:
                 stats = torch.zeros(2 * w.shape[0], dtype=torch.float32, device=x.device)
-            y = _fprop_tc(x, w, stride, pad, stats)
+            y = _fprop_tc(x, w, stride, pad, stats, plan.fprop == "tc2")
         else:
             y = F.conv2d(x, w, None, stride, pad)
         ctx.save_for_backward(x, w)
@@ -222,12 +243,12 @@ class _Conv(torch.autograd.Function):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = dw = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        lib_dx = need_dx and plan.dgrad != "tc"
+        lib_dx = need_dx and plan.dgrad not in ("tc", "tc2")
         lib_dw = need_dw and plan.wgrad != "tc"
         if lib_dx or lib_dw:
             dx, dw = _cudnn_bwd(dy, x, w, stride, pad, lib_dx, lib_dw)
-        if need_dx and plan.dgrad == "tc":
-            dx = _dgrad_tc(dy, x, w, stride, pad)
+        if need_dx and plan.dgrad in ("tc", "tc2"):
+            dx = _dgrad_tc(dy, x, w, stride, pad, plan.dgrad == "tc2")
         if need_dw and plan.wgrad == "tc":
             dw = _wgrad_tc(dy, x, w, stride, pad, _grad_view(ctx.w_ref), True)     # None when written into .grad in place
         return dx, dw, None, None

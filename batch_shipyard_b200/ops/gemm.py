@@ -42,8 +42,8 @@ def load() -> C.CDLL:
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_gemm_bf16_tn_rsag.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
-        lib.sy_gemm_bf16_tn_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-        lib.sy_conv_bf16_nhwc_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_tn_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_conv_bf16_nhwc_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
@@ -97,7 +97,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         assert bias is None and two_cta_ok(m, n, block_n), "2-CTA GEMM: no bias, N % block_n == 0"
         rc = lib.sy_gemm_bf16_tn_2cta(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
                                       a.stride(0), b.stride(0), out.stride(0), C.c_void_p(stats.data_ptr() if stats is not None else 0),
-                                      block_n, max_ctas, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+                                      block_n, max_ctas, 0, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"sy_gemm_bf16_tn_2cta failed ({rc}): {lib.sy_gemm_last_error().decode()}")
         return out
@@ -110,7 +110,8 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     return out
 
 
-def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
+            two_cta: bool = False) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[K,N] with b row-major (N contiguous): the dgrad shape dX = dY @ W.  The kernel reads b as an
     MN-major tcgen05 operand, so no transposed copy of the weight is made."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[1] == b.shape[0]
@@ -128,6 +129,14 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         out = buf[:, :n] if ldc != n else buf
     assert out.shape == (m, n) and out.dtype == torch.bfloat16 and _rows_ok(out)
     lib = load()
+    if two_cta:
+        assert two_cta_ok(m, n, block_n), "2-CTA GEMM: N % block_n == 0"
+        rc = lib.sy_gemm_bf16_tn_2cta(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
+                                      a.stride(0), b.stride(0), out.stride(0), None, block_n, max_ctas, 1,
+                                      C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"sy_gemm_bf16_tn_2cta (MN-major B) failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+        return out
     rc = lib.sy_gemm_bf16_nn(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), m, n, k,
                              a.stride(0), b.stride(0), out.stride(0), block_n, max_ctas,
                              C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
@@ -356,7 +365,7 @@ def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int 
     lib = load()
     if two_cta:
         rc = lib.sy_conv_bf16_nhwc_2cta(C.c_void_p(xs.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, cin, cout, r, s,
-                                        pad, stride, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
+                                        pad, stride, 0, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, max_ctas,
                                         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"sy_conv_bf16_nhwc_2cta failed ({rc}): {lib.sy_gemm_last_error().decode()}")
@@ -369,7 +378,11 @@ def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int 
     return y.permute(0, 3, 1, 2)
 
 
-def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, pad: int = 1, block_n: int = 0) -> torch.Tensor:
+def conv_two_cta_ok(n: int, p: int, q: int, c_out: int) -> bool:
+    return (n * p * q) % 256 == 0 and c_out % 128 == 0
+
+
+def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, pad: int = 1, block_n: int = 0, two_cta: bool = False) -> torch.Tensor:
     """dx of a stride-1 'same' convolution: implicit GEMM over dY with the weights read in place (rotated by tap index,
     transposed by reading them as an MN-major operand)."""
     n, cout, p, q = dy.shape
@@ -377,6 +390,12 @@ def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, pad: int = 1, block_n: in
     dys, ws = _nhwc_storage(dy), _nhwc_storage(w)
     dx = torch.empty((n, p, q, cin), dtype=torch.bfloat16, device=dy.device)
     lib = load()
+    if two_cta:
+        rc = lib.sy_conv_bf16_nhwc_2cta(C.c_void_p(dys.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(dx.data_ptr()), n, p, q, cout, cin, r, s,
+                                        pad, 1, 1, None, block_n, 0, C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"sy_conv_bf16_nhwc_2cta dgrad failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+        return dx.permute(0, 3, 1, 2)
     rc = lib.sy_conv_bf16_nhwc(C.c_void_p(dys.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_void_p(dx.data_ptr()), n, p, q, cout, cin, r, s,
                                pad, 1, 1, None, block_n, 0, C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
     if rc != 0:

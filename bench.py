@@ -220,7 +220,8 @@ def _conv_summary():
         tab = _conv.plan_table()
         out = {"mode": _conv._MODE, "shapes": len(tab)}
         for pas in ("fprop", "dgrad", "wgrad"):
-            out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] == "tc")
+            out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] in ("tc", "tc2"))
+            out[pas + "_tc_2cta"] = sum(1 for v in tab.values() if v[pas] == "tc2")
         out["fprop_fused_bn_stats"] = sum(1 for v in tab.values() if v["stats"])
         if os.environ.get("SHIPYARD_CONV_PLAN_DUMP"):
             os.makedirs("gpurun_out", exist_ok=True)

@@ -199,6 +199,21 @@ DEVI void tile_to_mn(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
   n_blk = r / gm;
 }
 
+// Kernels that accumulate per-column statistics want every CTA to stay on ONE column-block (the partial sums live in registers
+// and are flushed with atomics when the column-block changes): tiles are numbered column-block fastest and the persistent
+// stride is rounded down to a multiple of num_n, so CTA c always works on column-block c % num_n while the CTAs running
+// concurrently still share their A row-blocks through L2.
+template <bool kColumnSticky> DEVI void map_tile(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  if constexpr (kColumnSticky) { m_blk = t / num_n; n_blk = t - m_blk * num_n; }
+  else tile_to_mn(t, num_m, num_n, m_blk, n_blk);
+}
+template <bool kColumnSticky> DEVI void tile_walk(int cta, int ncta, int num_n, int num_tiles, int& t_first, int& t_stride) {
+  t_stride = ncta; t_first = cta;
+  if constexpr (kColumnSticky) {
+    if (ncta >= num_n) { t_stride = ncta - ncta % num_n; if (cta >= t_stride) t_first = num_tiles; }
+  }
+}
+
 template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
@@ -231,6 +246,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
   const int num_tiles = num_m * num_n;
+  int t_first, t_stride;
+  tile_walk<kStats>(blockIdx.x, gridDim.x, num_n, num_tiles, t_first, t_stride);
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_c); }
   if (warp == 1 && lane == 0) {
@@ -249,8 +266,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
+      for (int t = t_first; t < num_tiles; t += t_stride) {
+        int m_blk, n_blk; map_tile<kStats>(t, num_m, num_n, m_blk, n_blk);
         int cn = 0, ch = 0, cw = 0;
         if constexpr (kConv) {               // first output pixel of this M tile -> base-pixel coordinates
           const int pq = geom.P * geom.Q, m0 = m_blk * BM;
@@ -294,7 +311,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc = make_idesc<BN, false, kBMN>();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = t_first; t < num_tiles; t += t_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -351,8 +368,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           st[ci][0] = st[ci][1] = st[ci][2] = st[ci][3] = 0.f;
         }
       };
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
+      for (int t = t_first; t < num_tiles; t += t_stride) {
+        int m_blk, n_blk; map_tile<kStats>(t, num_m, num_n, m_blk, n_blk);
         if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -979,6 +996,10 @@ DEVI void tma_load_im2col_4d_2sm(void* smem_dst, const void* tmap, uint64_t* lea
                ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n),
                  "h"(off_w), "h"(off_h), "l"(kCacheHintNormal) : "memory");
 }
+DEVI void tma_load_3d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(kCacheHintNormal) : "memory");
+}
 DEVI void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const uint32_t z = 0;
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -1012,7 +1033,7 @@ template <int BN> struct Cfg2 {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 + 256;
 };
 
-template <int BN, bool kStats, bool kConv>
+template <int BN, bool kStats, bool kConv, bool kBMN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, float* __restrict__ stats, const ConvGeom geom) {
@@ -1036,6 +1057,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_m = (M + BM2 - 1) / BM2, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
   const int num_tiles = num_m * num_n;
+  int t_first, t_stride;
+  tile_walk<kStats>(pair, num_pairs, num_n, num_tiles, t_first, t_stride);
   constexpr int kChunks = BN / kEpiChunk;
   constexpr int kActiveGroups = kChunks < kEpiGroups ? kChunks : kEpiGroups;
 
@@ -1055,8 +1078,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier) ====
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
+      for (int t = t_first; t < num_tiles; t += t_stride) {
+        int m_blk, n_blk; map_tile<kStats>(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * BM2 + (int)rank * BM;
         int cn = 0, ch = 0, cw = 0;
         if constexpr (kConv) {
@@ -1073,7 +1096,22 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else {
             tma_load_2d_2sm(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m0);
           }
-          tma_load_2d_2sm(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if constexpr (kBMN) {
+            // B = W[K, N] row-major (dgrad): this CTA's half of the N range as 64-wide MN-major slabs
+            const int nb0 = n_blk * BN + (int)rank * (BN / 2);
+#pragma unroll
+            for (int sl = 0; sl < BN / 128; ++sl) {
+              if constexpr (kConv) {
+                const int tap = kb / geom.cblocks, cb = kb - tap * geom.cblocks;
+                tma_load_3d_2sm(smem_b + stage * C::kBBytes + sl * kSlabBytes, &tmap_b, &full_bar[stage], nb0 + sl * 64,
+                                geom.flip ? geom.taps - 1 - tap : tap, cb * 64);
+              } else {
+                tma_load_2d_2sm(smem_b + stage * C::kBBytes + sl * kSlabBytes, &tmap_b, &full_bar[stage], nb0 + sl * 64, kb * BK);
+              }
+            }
+          } else {
+            tma_load_2d_2sm(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -1081,10 +1119,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA only, one thread, M = 256 across the pair =====================
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kBMN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int t = t_first; t < num_tiles; t += t_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -1092,10 +1130,12 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_wait(&full_bar[stage], phase);             // bytes of BOTH CTAs have landed
           tc_fence_after();
           const uint64_t adesc = make_kmajor_sw128_desc(smem_a + stage * C::kABytes);
-          const uint64_t bdesc = make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+          const uint64_t bdesc = kBMN ? make_mnmajor_sw128_desc(smem_b + stage * C::kBBytes, kSlabBytes)
+                                      : make_kmajor_sw128_desc(smem_b + stage * C::kBBytes);
+          constexpr uint64_t kBStep = kBMN ? (UK * 128 >> 4) : (UK * 2 >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k)
-            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * UK * 2 >> 4), bdesc + (uint64_t)k * kBStep, idesc, (kb | k) != 0);
           umma_commit_2sm(&empty_bar[stage]);             // frees the stage in both CTAs
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -1132,8 +1172,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           st[ci][0] = st[ci][1] = st[ci][2] = st[ci][3] = 0.f;
         }
       };
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        int m_blk, n_blk; tile_to_mn(t, num_m, num_n, m_blk, n_blk);
+      for (int t = t_first; t < num_tiles; t += t_stride) {
+        int m_blk, n_blk; map_tile<kStats>(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * BM2 + (int)rank * BM;
         if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -1353,14 +1393,19 @@ extern "C" int sy_gemm_bf16_tn(const void* A, const void* B, void* C, int M, int
 }
 
 // CTA-pair launches.  Requirements on top of the 1-CTA entry points: N %% block_n == 0 (each CTA loads exactly half a B tile).
+// mode 0: B K-major [N, K]; mode 1: B = W[K, N] row-major (MN-major operand, dgrad of a 1x1 conv / Linear);
+// mode 2: conv dgrad, B = W[Cout][taps][Cin] through the 3-D map.
 template <int BN>
-int launch_2cta(bool conv, const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, float* stats,
+int launch_2cta(bool conv, int bmode, const void* A, const void* B, void* Cc, int M, int N, int K, int lda, int ldb, int ldc, float* stats,
                 const ConvGeom& g, const int* im2col /* Nb,H,W,C,R,S,pad,stride or null */, int max_ctas, cudaStream_t s) {
   using C = Cfg2<BN>;
   CUtensorMap ta, tb, tc;
   if (conv) { if (!make_im2col_map(&ta, A, im2col[0], im2col[1], im2col[2], im2col[3], im2col[4], im2col[5], im2col[6], im2col[7], BM)) return 3; }
   else if (!make_map(&ta, A, K, M, lda, BK, BM)) return 3;
-  if (!make_map(&tb, B, K, N, ldb, BK, BN / 2) || !make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
+  if (bmode == 0) { if (!make_map(&tb, B, K, N, ldb, BK, BN / 2)) return 3; }
+  else if (bmode == 1) { if (!make_map(&tb, B, N, K, ldb, 64, BK)) return 3; }
+  else if (!make_w3d_map(&tb, B, im2col[3], im2col[4] * im2col[5], N)) return 3;       // W[Co = act channels][taps][Ci = N]
+  if (!make_map(&tc, Cc, N, M, ldc, kEpiChunk, BM)) return 3;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
@@ -1375,12 +1420,16 @@ int launch_2cta(bool conv, const void* A, const void* B, void* Cc, int M, int N,
     g_launches.fetch_add(1);
     return 0;
   };
+  if (bmode != 0) {
+    if (stats) { snprintf(g_err, sizeof g_err, "2-CTA dgrad: no fused statistics"); return 2; }
+    return conv ? go(gemm_bf16_tn_2cta_kernel<BN, false, true, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false, true>);
+  }
   if (conv) return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, true>);
   return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, false>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false>);
 }
 
 extern "C" int sy_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, float* stats,
-                                    int block_n, int max_ctas, void* stream) {
+                                    int block_n, int max_ctas, int b_mn, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda | ldb | ldc) & 7 || ((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) {
     snprintf(g_err, sizeof g_err, "alignment: pointers must be 16B aligned and leading dimensions multiples of 8"); return 1;
@@ -1390,28 +1439,33 @@ extern "C" int sy_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int M
   if (block_n == 0 || N % block_n) { snprintf(g_err, sizeof g_err, "2-CTA GEMM needs N %% block_n == 0 (block_n 128 or 256)"); return 1; }
   ConvGeom g{};
   switch (block_n) {
-    case 128: return launch_2cta<128>(false, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
-    case 256: return launch_2cta<256>(false, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
+    case 128: return launch_2cta<128>(false, b_mn ? 1 : 0, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
+    case 256: return launch_2cta<256>(false, b_mn ? 1 : 0, A, B, C, M, N, K, lda, ldb, ldc, stats, g, nullptr, max_ctas, (cudaStream_t)stream);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 128 or 256");
   return 1;
 }
 
-// fprop only: out[N,P,Q,Cout] = conv(act[N,H,W,Cin], wgt[Cout,R,S,Cin]) on CTA pairs.  N*P*Q %% 256 == 0, Cout %% block_n == 0.
-extern "C" int sy_conv_bf16_nhwc_2cta(const void* act, const void* wgt, void* out, int Nb, int H, int W, int Cin, int Cout, int R, int S,
-                                      int pad, int stride, float* stats, int block_n, int max_ctas, void* stream) {
-  if (Cin % 64 || ((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out) & 15) { snprintf(g_err, sizeof g_err, "conv: Cin %% 64, aligned tensors"); return 1; }
+// CTA-pair convolution.  dgrad == 0: out[N,P,Q,c_out] = conv(act[N,H,W,c_act], wgt[c_out,R,S,c_act]) (+BN statistics);
+// dgrad == 1 (stride 1, 'same'): out[N,H,W,c_out] from act = dY[N,H,W,c_act], wgt = W[c_act,R,S,c_out] read in place.
+// N*P*Q %% 256 == 0, c_out %% block_n == 0, c_act %% 64 == 0.
+extern "C" int sy_conv_bf16_nhwc_2cta(const void* act, const void* wgt, void* out, int Nb, int H, int W, int c_act, int c_out, int R, int S,
+                                      int pad, int stride, int dgrad, float* stats, int block_n, int max_ctas, void* stream) {
+  if (c_act % 64 || ((uintptr_t)act | (uintptr_t)wgt | (uintptr_t)out) & 15) { snprintf(g_err, sizeof g_err, "conv: act channels %% 64, aligned tensors"); return 1; }
+  if (dgrad && (stride != 1 || stats)) { snprintf(g_err, sizeof g_err, "conv dgrad: stride 1, no stats"); return 1; }
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   if (((long)Nb * P * Q) % (2 * BM)) { snprintf(g_err, sizeof g_err, "2-CTA conv: N*P*Q must be a multiple of 256"); return 1; }
+  if (dgrad && (P != H || Q != W)) { snprintf(g_err, sizeof g_err, "conv dgrad: 'same' padding only"); return 1; }
   if (!load_encode() || !load_encode_im2col()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncode* unavailable (no driver?)"); return 6; }
-  if (block_n <= 0) block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 0);
-  if (block_n == 0 || Cout % block_n) { snprintf(g_err, sizeof g_err, "2-CTA conv needs Cout %% block_n == 0 (block_n 128 or 256)"); return 1; }
-  const int M = Nb * P * Q, K = R * S * Cin;
-  ConvGeom g{P, Q, S, R * S, Cin / 64, stride, -pad, 0};
-  const int geo[8] = {Nb, H, W, Cin, R, S, pad, stride};
+  if (block_n <= 0) block_n = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 0);
+  if (block_n == 0 || c_out % block_n) { snprintf(g_err, sizeof g_err, "2-CTA conv needs out channels %% block_n == 0 (block_n 128 or 256)"); return 1; }
+  const int M = Nb * P * Q, K = R * S * c_act;
+  ConvGeom g{P, Q, S, R * S, c_act / 64, stride, -pad, dgrad ? 1 : 0};
+  const int geo[8] = {Nb, H, W, c_act, R, S, pad, stride};
+  const int bmode = dgrad ? 2 : 0;
   switch (block_n) {
-    case 128: return launch_2cta<128>(true, act, wgt, out, M, Cout, K, 0, K, Cout, stats, g, geo, max_ctas, (cudaStream_t)stream);
-    case 256: return launch_2cta<256>(true, act, wgt, out, M, Cout, K, 0, K, Cout, stats, g, geo, max_ctas, (cudaStream_t)stream);
+    case 128: return launch_2cta<128>(true, bmode, act, wgt, out, M, c_out, K, 0, K, c_out, stats, g, geo, max_ctas, (cudaStream_t)stream);
+    case 256: return launch_2cta<256>(true, bmode, act, wgt, out, M, c_out, K, 0, K, c_out, stats, g, geo, max_ctas, (cudaStream_t)stream);
   }
   snprintf(g_err, sizeof g_err, "block_n must be 128 or 256");
   return 1;

@@ -207,7 +207,7 @@ def test_conv_dispatcher_modes_agree_with_reference(mode):
         tab = conv.plan_table()
         assert len(tab) == 4
         if mode == "tc":
-            assert all(v["fprop"] == "tc" and v["wgrad"] == "tc" for v in tab.values())
+            assert all(v["fprop"] in ("tc", "tc2") and v["wgrad"] == "tc" for v in tab.values())
         if mode == "cudnn":
             assert all(v["fprop"] == "cudnn" and v["dgrad"] == "cudnn" and v["wgrad"] == "cudnn" for v in tab.values())
     finally:
@@ -245,3 +245,25 @@ def test_conv_fprop_two_cta_pairs(n, cin, h, w, cout, k, stride):
     ref = F.conv2d(x.float(), wt.float(), stride=stride, padding=pad)
     torch.testing.assert_close(y.float(), ref, atol=0.03, rtol=2e-2)
     torch.testing.assert_close(stats[:cout], y.float().sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
+
+
+@pytest.mark.parametrize("m,n,k", [(512, 256, 64), (4096, 128, 512), (1024, 512, 2048), (50176, 256, 64)])
+def test_gemm_nn_two_cta(m, n, k):
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(m + n + k + 2)
+    a = (torch.randn(m, k, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(k, n, device="cuda") * 0.5).to(torch.bfloat16)
+    out = gemm.gemm_nn(a, b, two_cta=True)
+    torch.testing.assert_close(out.float(), a.float() @ b.float(), atol=0.02 * (k ** 0.5) * 0.25 + 0.02, rtol=2e-2)
+
+
+@pytest.mark.parametrize("n,c,h,w,k", [(8, 128, 16, 16, 3), (4, 256, 16, 16, 3), (16, 128, 8, 8, 3)])
+def test_conv_dgrad_two_cta(n, c, h, w, k):
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(n + c + h)
+    cout = 128
+    wt = (torch.randn(cout, c, k, k, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = (torch.randn(n, cout, h, w, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = gemm.conv_dgrad_nhwc(dy, wt, k // 2, two_cta=True)
+    ref = torch.nn.grad.conv2d_input((n, c, h, w), wt.float(), dy.float(), stride=1, padding=k // 2)
+    torch.testing.assert_close(dx.float(), ref, atol=0.05, rtol=2e-2)
