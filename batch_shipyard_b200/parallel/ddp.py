@@ -139,6 +139,23 @@ class FusedDataParallelTrainer:
 
     def prepare(self, warmup: int = 3) -> None:
         """Eager warm-up (also lets cuDNN pick algorithms), then capture the step."""
+        # the first eager step autotunes every conv shape (ops.conv) and cuDNN searches its algorithms: ranks can drift apart
+        # by seconds, so the collective watchdog is relaxed until the step has been captured
+        old_timeout = None
+        try:
+            old_timeout = self.comm.get_tuning("timeout_ms")
+            self.comm.set_tuning(timeout_ms=180000)
+        except Exception:  # noqa: BLE001
+            old_timeout = None
+        def restore():
+            if old_timeout:
+                self.comm.set_tuning(timeout_ms=int(old_timeout))
+        try:
+            self._prepare(warmup, restore)
+        finally:
+            restore()
+
+    def _prepare(self, warmup: int, before_capture=lambda: None) -> None:
         if not self.use_graph:
             before = self._count_own_launches()
             self._step_body()
@@ -153,6 +170,7 @@ class FusedDataParallelTrainer:
                 self._step_body()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        before_capture()                       # the captured collective carries the normal watchdog, not the relaxed one
         self.graph = torch.cuda.CUDAGraph()
         before = self._count_own_launches()
         with torch.cuda.graph(self.graph):

@@ -11,6 +11,11 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+def _need_multi():
+    if _ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs on the box")
+
+
 def test_single_gpu_collectives():
     ok, outs = run_ranks("_coll_worker.py", 1, extra=["--quick"], gpu=True, timeout=300)
     assert ok, "\n".join(o[-3000:] for o in outs)
@@ -20,6 +25,7 @@ def test_single_gpu_collectives():
 @pytest.mark.multigpu
 @pytest.mark.parametrize("transport", ["auto", "p2p"])
 def test_multi_gpu_collectives(transport):
+    _need_multi()
     world = min(_ngpu(), 8)
     import os
     extra = ["--transport", transport] + (["--quick"] if os.environ.get("SHIPYARD_TEST_QUICK") else [])
@@ -30,6 +36,7 @@ def test_multi_gpu_collectives(transport):
 @pytest.mark.multigpu
 def test_nccl_preload_shim_under_torch_distributed():
     """LD_PRELOAD the shim under a torchrun NCCL job: results stay correct and the collectives ran on our kernels."""
+    _need_multi()
     import os
     import subprocess
     import sys
@@ -51,6 +58,7 @@ def test_nccl_preload_shim_under_torch_distributed():
 @pytest.mark.multigpu
 @pytest.mark.parametrize("transport", ["auto", "p2p"])
 def test_k10_gemm_allreduce_fused(transport):
+    _need_multi()
     world = min(_ngpu(), 8)
     ok, outs = run_ranks("_k10_worker.py", world, extra=["--transport", transport], gpu=True, timeout=600)
     assert ok, "\n".join(o[-3000:] for o in outs)
