@@ -234,11 +234,17 @@ class HPCG:
             self._sync()
             done = 2
             self._graph = torch.cuda.CUDAGraph()
+            self._graph_parity = [L.parity for L in self.levels]      # ghost-buffer parity every level has when a replay starts
             l0 = self._launches()
             with torch.cuda.graph(self._graph):
                 self._cg_step(x, True); self._cg_step(x, True)
             self._graph_launches = self._launches() - l0        # our kernels inside one replay (2 iterations)
             self._graph_key = key
+        # the captured exchanges have their ghost-buffer parity baked in: consecutive exchanges must alternate buffers (a push
+        # may not land in a plane the neighbour is still reading), so re-align each level's parity with one extra exchange
+        for li, L in enumerate(self.levels):
+            if self.world > 1 and L.parity != self._graph_parity[li]:
+                self.exchange(li, L.x)
         while done < iters:
             self._graph.replay(); done += 2
             self._replays = getattr(self, "_replays", 0) + 1
