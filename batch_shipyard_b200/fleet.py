@@ -384,6 +384,15 @@ def action_jobs_add(ctx: Context, recreate=False, tail=None, wait=False, dry_run
                 out[jid]["tail"] = f.read()
         except OSError as e:
             out[jid]["tail"] = f"<{e}>"
+        try:                                   # a failed task: say so and show why (stderr tail), instead of an empty tail
+            t = ctx.b.get_task(jid, tid)
+            out[jid]["task_state"] = t.get("state")
+            if t.get("exit_code") not in (None, 0):
+                out[jid]["exit_code"] = t.get("exit_code")
+                with open(ctx.b.task_file_path(jid, tid, "stderr.txt")) as f:
+                    out[jid]["stderr_tail"] = f.read()[-2000:]
+        except (OSError, BackendError, KeyError):
+            pass
     return out
 
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# 2-GPU round: HPCG over the halo path, mpiBench recipe through the CLI on device buffers (with stderr), N=2 bench.
+set -x
+mkdir -p gpurun_out
+NG=$(nvidia-smi -L | wc -l)
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29571 recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --size 256 --seconds 6 2>&1 | tail -2 | tee gpurun_out/hpcg16_n$NG.log
+export SHIPYARD_STATE_DIR=$PWD/gpurun_out/state16_$$
+sed "s/dedicated: 2/dedicated: $NG/" recipes/mpiBench-OpenMPI/config/pool.yaml > /tmp/pool16.yaml
+timeout 200 ./shipyard pool add --configdir recipes/mpiBench-OpenMPI/config --pool /tmp/pool16.yaml -y 2>&1 | tail -3 | tee gpurun_out/recipe16_pool.log
+timeout 300 ./shipyard jobs add --configdir recipes/mpiBench-OpenMPI/config --pool /tmp/pool16.yaml --jobs recipes/mpiBench-OpenMPI/config/jobs-gpu.yaml --tail stdout.txt 2>&1 | tail -60 | tee gpurun_out/recipe16_mpibench.log
+find $SHIPYARD_STATE_DIR -name "stderr*.txt" -o -name "result.json" | head -5 | while read f; do echo "== $f"; tail -15 $f; done 2>&1 | tee gpurun_out/recipe16_stderr.log
+rm -rf $SHIPYARD_STATE_DIR
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus $NG --steps 15 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench16_n$NG.log

@@ -20,8 +20,8 @@ from batch_shipyard_b200.ops.coll import Communicator  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=256, help="local grid edge (nx=ny=nz)")
-    ap.add_argument("--t", type=float, default=30.0, help="timed seconds")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="local grid edge (nx=ny=nz); --size for launchers that abbreviate-match --n")
+    ap.add_argument("--t", "--seconds", dest="t", type=float, default=30.0, help="timed seconds")
     ap.add_argument("--levels", type=int, default=4)
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
