@@ -806,26 +806,34 @@ DEVI void mc_st_v4(void* mc, const uint4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+struct InboxMaps { CUtensorMap m[SY_MAXR]; };     // one 2-D map per owner rank over ITS inbox (peer-mapped virtual addresses)
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CommDev comm, size_t inbox_off, size_t out_off, int M, int N, int K, int rows_per_rank) {
+                         const __grid_constant__ InboxMaps inbox_maps, const __grid_constant__ CommDev comm, size_t inbox_off,
+                         size_t out_off, int M, int N, int K, int rows_per_rank) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + 2 * C::kCBytes);
+  uint8_t* smem_c = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C::kCBytes);
   uint64_t* full_bar = bars; uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages; uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
   const int num_tiles = num_m * num_n;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b);
+    for (int p = 0; p < comm.world; ++p) tma_prefetch_desc(&inbox_maps.m[p]);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads); }
+    constexpr int kActiveGroups = (BN / kEpiChunk) < kEpiGroups ? (BN / kEpiChunk) : kEpiGroups;
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads * kActiveGroups); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
@@ -888,43 +896,62 @@ gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
-    const int row = ew * 32 + lane;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < virt_tiles; t += gridDim.x) {
-      int m_blk, n_blk; tile_coords(t, m_blk, n_blk);
-      if (m_blk >= num_m) continue;
-      const int owner = m_blk / m_per_rank;
-      const int grow = m_blk * BM + row;
-      // inbox on the owner: [src rank][local row][N] bf16
-      __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(comm.heap[owner] + inbox_off) +
-                               ((size_t)comm.rank * rows_per_rank + (size_t)(grow - owner * rows_per_rank)) * N;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / kEpiChunk; ++c) {
+    // epilogue: two warpgroups drain alternate 64-column chunks; each chunk goes TMEM -> bf16 -> swizzled staging tile -> ONE
+    // bulk TMA store into the owner's inbox (peer memory over NVLink, or local HBM for tiles this rank owns)
+    constexpr int kChunks = BN / kEpiChunk;
+    const int grp = (warp - 4) >> 2;
+    if (grp < kChunks) {
+      const int ew = warp & 3, et = threadIdx.x - 128 - grp * 128;
+      const int row = ew * 32 + lane;
+      const bool issuer = et == 0;
+      const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+      uint8_t* cbuf = smem_c + grp * C::kCBytes;
+      constexpr int kMyChunks = (kChunks + kEpiGroups - 1) / kEpiGroups;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < virt_tiles; t += gridDim.x) {
+        int m_blk, n_blk; tile_coords(t, m_blk, n_blk);
+        if (m_blk >= num_m) continue;
+        const int owner = m_blk / m_per_rank;
+        const int inbox_row0 = comm.rank * rows_per_rank + (m_blk * BM - owner * rows_per_rank);   // [src rank][local row] on the owner
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
         uint32_t v[2][32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * kEpiChunk);
-        tmem_ld32(taddr, v[0]);
-        tmem_ld32(taddr + 32, v[1]);
-        tmem_ld_wait();
-        if (c == BN / kEpiChunk - 1) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
-        const int n0 = n_blk * BN + c * kEpiChunk;
-        if (grow < M) {
+        tmem_ld32(tbase + grp * kEpiChunk, v[0]);
+        tmem_ld32(tbase + grp * kEpiChunk + 32, v[1]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {          // 8 x 16 B = one full 128 B line of this thread's row
-            if (n0 + q * 8 < N) {
-              float f[8];
+        for (int ci = 0; ci < kMyChunks; ++ci) {
+          const int c = grp + ci * kEpiGroups;
+          if (c >= kChunks) break;
+          tmem_ld_wait();
+          const bool last = c + kEpiGroups >= kChunks;
+          if (last) { tc_fence_before(); mbar_arrive(&tmem_empty[acc]); }
+          uint4 w[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
-              st_global_v4(dst_row + n0 + q * 8, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
-            }
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(q * 8 + i) >> 5][(q * 8 + i) & 31]);
+            w[q] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
+          if (!last) {
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk, v[0]);
+            tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk + 32, v[1]);
+          }
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_a, kEpiThreads);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w[q];
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, kEpiThreads);
+          if (issuer) { tma_store_2d(&inbox_maps.m[owner], cbuf, n_blk * BN + c * kEpiChunk, inbox_row0); tma_store_commit(); }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (issuer) tma_store_wait_all();         // every bulk store of this group has been performed (not just read from smem)
+      __threadfence_system();
     }
-    __threadfence_system();
   }
   tc_fence_before();
   __syncthreads();
@@ -940,7 +967,7 @@ gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int vec_per_row = N / 8;
   const long total = (long)my_rows * vec_per_row;
   const __nv_bfloat16* inbox = reinterpret_cast<const __nv_bfloat16*>(comm.heap[comm.rank] + inbox_off);
-  for (long idx = (long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long)gridDim.x * kThreads) {
+  for (long idx = (long)blockIdx.x * kThreadsTN + threadIdx.x; idx < total; idx += (long)gridDim.x * kThreadsTN) {
     const int r = (int)(idx / vec_per_row), c8 = (int)(idx % vec_per_row);
     float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint4 in[SY_MAXR];
@@ -1570,7 +1597,11 @@ extern "C" int sy_gemm_bf16_tn_rsag(const void* comm_view, size_t comm_view_byte
     if (grid > SY_MAX_BLOCKS) grid = SY_MAX_BLOCKS;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreads, smem, s>>>(ta, tb, cd, inbox_off, out_off, M, N, K, rpr);
+    InboxMaps im;
+    memset(&im, 0, sizeof im);
+    for (int p = 0; p < cd.world; ++p)
+      if (!make_map(&im.m[p], cd.heap[p] + inbox_off, (uint64_t)N, (uint64_t)cd.world * rpr, (uint64_t)N, kEpiChunk, BM)) return 3;
+    kern<<<grid, kThreadsTN, smem, s>>>(ta, tb, im, cd, inbox_off, out_off, M, N, K, rpr);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
