@@ -3,6 +3,9 @@
 set -x
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
+S=k10bench$$
+for r in $(seq 0 $((NG-1))); do timeout 200 python tests/_k10_worker.py --rank $r --world $NG --session $S --device $r --bench > gpurun_out/k10v3_r$r.log 2>&1 & done; wait
+tail -3 gpurun_out/k10v3_r0.log | tee gpurun_out/k10v3_bench_n$NG.log
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29571 recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --size 256 --seconds 6 2>&1 | tail -2 | tee gpurun_out/hpcg16_n$NG.log
 export SHIPYARD_STATE_DIR=$PWD/gpurun_out/state16_$$
 sed "s/dedicated: 2/dedicated: $NG/" recipes/mpiBench-OpenMPI/config/pool.yaml > /tmp/pool16.yaml

@@ -45,7 +45,9 @@ def ncu_table(csv_path, out_md, title, note=""):
             ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
             ("launch__registers_per_thread", "registers/thread"), ("launch__grid_size", "grid"), ("launch__waves_per_multiprocessor", "waves/SM"),
             ("launch__occupancy_limit_registers", "blocks/SM (register limit)"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
-            ("sm__inst_executed_pipe_tensor_op_hmma.sum", "HMMA-pipe instructions"), ("sm__pipe_tensor_subpipe_mma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+            ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
+            ("l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "L2 -> SM read bandwidth"), ("launch__cluster_size", "cluster size"),
+            ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "TMEM pipe %"),
             ("smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "stall: long scoreboard %")]
     with open(out_md, "w") as f:
         f.write(f"# {title}\n\n{note}\n\nSource: `ncu --set full --clock-control none --import-source on` (raw page exported with `ncu -i ... --page raw --csv`).\n"
@@ -160,7 +162,11 @@ def main():
             ncu_hot_lines(rep, ["k_bn_stats", "k_bn_apply_fwd", "k_bn_bwd_reduce", "k_bn_bwd_apply"], os.path.join(P, "ncu_bn_kernels.md"))
     p = latest("ncu_gemm*_raw.csv")
     if p:
-        ncu_table(p, os.path.join(P, "ncu_gemm_kernels.md"), "tcgen05 GEMM kernels", "Conv-as-GEMM shapes of ResNet-50.")
+        ncu_table(p, os.path.join(P, "ncu_gemm_kernels.md"), "tcgen05 kernels: 8192^3 GEMM (CTA pair and 1-CTA) and 256-channel 3x3 convolution at 28x28, batch 256 (fprop+stats, dgrad on CTA pairs; split-K wgrad)",
+                  "Captured back to back from one script (`bench/gpu_round15.sh`).")
+        rep = p.replace("_raw.csv", ".ncu-rep")
+        if os.path.exists(rep):
+            ncu_hot_lines(rep, ["gemm_bf16_tn_2cta_kernel", "gemm_bf16_tn_kernel", "gemm_bf16_nt_splitk_kernel"], os.path.join(P, "ncu_gemm_kernels.md"))
     p = latest("launches_shipyard*.csv")
     if p:
         step_breakdown(p, os.path.join(P, "step_breakdown.md"))
