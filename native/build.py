@@ -125,12 +125,14 @@ def build_target(name: str, force: bool = False) -> str:
     deplink = []
     for d in DEPS.get(name, []):
         deplink += ["-L", OUT, "-l" + TARGETS[d][1][3:-3]]
+    tmp = out + ".tmp%d" % os.getpid()          # link to a temp name, then rename: readers never see a half-written artefact
     if kind == "nvcc-shared":
-        _run([NVCC] + GENCODE + ["-shared", "-o", out] + objs + deplink + rpath + ldflags)
+        _run([NVCC] + GENCODE + ["-shared", "-o", tmp] + objs + deplink + rpath + ldflags)
     elif kind == "nvcc-exe":
-        _run([NVCC] + GENCODE + ["-o", out] + objs + deplink + rpath + ldflags)
+        _run([NVCC] + GENCODE + ["-o", tmp] + objs + deplink + rpath + ldflags)
     else:
-        _run([CXX, "-o", out] + objs + deplink + rpath + ldflags)
+        _run([CXX, "-o", tmp] + objs + deplink + rpath + ldflags)
+    os.replace(tmp, out)
     return f"{name}: built {os.path.relpath(out, ROOT)}"
 
 

@@ -564,13 +564,16 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         const int j0 = n_blk * BN + c * 32;
         if (i < I) {
           if (splits == 1) {              // whole K in this CTA: write the gradient directly (a warp covers 64 contiguous bytes)
-            float prev[32];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)          // all read-modify-write loads first: one memory round trip, not 32
-              prev[jj] = (accumulate && j0 + jj < J) ? __bfloat162float(out[(size_t)(j0 + jj) * ldo + i]) : 0.f;
+            for (int jb = 0; jb < 32; jb += 8) {      // read-modify-write loads in batches of 8: 4 memory round trips, not 32
+              float prev[8];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (j0 + jj < J) out[(size_t)(j0 + jj) * ldo + i] = __float2bfloat16_rn(__uint_as_float(v[jj]) + prev[jj]);
+              for (int jj = 0; jj < 8; ++jj)
+                prev[jj] = (accumulate && j0 + jb + jj < J) ? __bfloat162float(out[(size_t)(j0 + jb + jj) * ldo + i]) : 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                if (j0 + jb + jj < J) out[(size_t)(j0 + jb + jj) * ldo + i] = __float2bfloat16_rn(__uint_as_float(v[jb + jj]) + prev[jj]);
+            }
           } else {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj)
@@ -587,7 +590,7 @@ gemm_bf16_nt_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           __threadfence();
           // thread -> 4 consecutive i (16 B of fp32) x every 4th column; kFin loads in flight per thread so the
           // L2 round trips overlap instead of serialising (I % 8 == 0, so a 4-wide group is all-in or all-out)
-          constexpr int kFin = 8;
+          constexpr int kFin = 4;
           const int ii = m_blk * BM + (et & 31) * 4, jsub = et >> 5;
           if (ii < I) {
             for (int jb = 0; jb < BN / 4; jb += kFin) {
