@@ -45,6 +45,7 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->threads = (long)env_sz("SHIPYARD_COLL_THREADS", 512);
   c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 4096);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
+  c->mailbox_max_bytes = (long)env_sz("SHIPYARD_COLL_MAILBOX_MAX", 128 << 10);
   c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);
   c->nvls_min_world = (long)env_sz("SHIPYARD_COLL_NVLS_MIN_WORLD", 4);
   if (heap_bytes == 0) heap_bytes = env_sz("SHIPYARD_COLL_HEAP", transport == SY_TRANSPORT_STUB ? (256ul << 20) : (1ul << 30));
@@ -123,6 +124,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "threads")) c->threads = v < 32 ? 32 : (v > 512 ? 512 : v / 32 * 32);
   else if (!strcmp(k, "ll_max_bytes")) c->ll_max_bytes = v > (long)SY_LL_MAX_PAYLOAD ? (long)SY_LL_MAX_PAYLOAD : v;
   else if (!strcmp(k, "oneshot_max_bytes")) c->oneshot_max_bytes = v > (long)SY_OS_SLOT ? (long)SY_OS_SLOT : v;
+  else if (!strcmp(k, "mailbox_max_bytes")) c->mailbox_max_bytes = v > (long)SY_OS_SLOT ? (long)SY_OS_SLOT : v;
   else if (!strcmp(k, "nvls_min_bytes")) c->nvls_min_bytes = v;
   else if (!strcmp(k, "timeout_ms")) c->timeout_ms = v;
   else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
@@ -135,6 +137,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "threads")) return c->threads;
   if (!strcmp(k, "ll_max_bytes")) return c->ll_max_bytes;
   if (!strcmp(k, "oneshot_max_bytes")) return c->oneshot_max_bytes;
+  if (!strcmp(k, "mailbox_max_bytes")) return c->mailbox_max_bytes;
   if (!strcmp(k, "nvls_min_bytes")) return c->nvls_min_bytes;
   if (!strcmp(k, "timeout_ms")) return c->timeout_ms;
   if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
@@ -255,12 +258,19 @@ static int out_target(sy_comm* c, void* out, size_t bytes, OutStage* t) {
   return SY_OK;
 }
 
+// small / medium byte movers go through the one-shot mailboxes: any device pointers, no staging copy, no barriers
+static bool mailbox_ok(const sy_comm* c, const void* in, const void* out, size_t bytes) {
+  return bytes <= (size_t)c->mailbox_max_bytes && bytes <= SY_OS_SLOT && bytes % 16 == 0 &&
+         ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0 && !getenv("SHIPYARD_COLL_NO_MAILBOX");
+}
+
 extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count, int dt, sy_stream_t stream) {
   if (count == 0) return SY_OK;
   if (is_stub(c)) return stub_allgather(c, in, out, count, dt);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 0, 0, stream);
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
   rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
   if (rc) return rc;
@@ -275,6 +285,7 @@ extern "C" int sy_broadcast(sy_comm* c, const void* in, void* out, size_t count,
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (mailbox_ok(c, c->rank == root ? in : out, out, bytes)) return k_mailbox(c, c->rank == root ? in : out, out, bytes, 2, root, stream);
   OutStage t; int rc = out_target(c, out, bytes, &t); if (rc) return rc;
   rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)c->nvls_min_bytes, stream);
   if (rc) return rc;
@@ -288,6 +299,7 @@ extern "C" int sy_alltoall(sy_comm* c, const void* in, void* out, size_t count, 
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 1, 0, stream);
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
   rc = k_alltoall(c, in, t.off, bytes, stream);
   if (rc) return rc;

@@ -58,6 +58,7 @@ struct sy_comm {
   // tuning
   long max_blocks = 128, threads = 512;
   long ll_max_bytes = 4096, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;
+  long mailbox_max_bytes = 128 << 10;   // per-writer payload up to which all-gather / all-to-all / broadcast use the mailbox kernel
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
   long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
@@ -112,6 +113,7 @@ int k_allreduce(sy_comm* c, const void* in, void* out, size_t in_off, size_t out
                 void* stream);
 int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_in, int dt_out,
                      float scale, int op, bool nvls, void* stream);
+int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream);
 int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt, bool nvls,
                 void* stream);
 int k_broadcast(sy_comm* c, const void* in, size_t out_off, size_t bytes, int root, bool nvls,

@@ -808,6 +808,71 @@ k_scatter_k(const __grid_constant__ CommDev c, size_t in_off, void* out, size_t 
   epoch_store(c, ep);
 }
 
+// Mailbox byte movers for small / medium messages (<= 1 MB per writer): the sender pushes straight into its slot of the
+// receiver's parity-double-buffered one-shot mailbox and raises one flag per block; the receiver waits for the flags of
+// the writers it needs and copies the payload out of its own HBM.  No start barrier (nobody's `out` is touched remotely)
+// and no end barrier (the next mailbox operation uses the other parity), so the cost is one NVLink store latency + a
+// local copy instead of two cross-GPU barriers.
+//   mode 0 all-gather : my `bytes` -> slot[me] on every rank; out[r*bytes ..] <- slot[r]
+//   mode 1 all-to-all : in[p*bytes ..] -> slot[me] on rank p;  out[r*bytes ..] <- slot[r]
+//   mode 2 broadcast  : root's `bytes` -> slot[root] on every rank; out <- slot[root]
+__global__ void __launch_bounds__(512)
+k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char* __restrict__ out, size_t bytes, int mode, int root) {
+  const uint32_t seq = c.seq[0] + 1, parity = seq & 1;
+  const size_t units = bytes / 16;
+  const size_t per_block = (units + gridDim.x - 1) / gridDim.x;
+  const size_t u0 = (size_t)blockIdx.x * per_block, u1 = (u0 + per_block < units) ? u0 + per_block : units;
+  const bool writer = mode != 2 || c.rank == root;
+  if (writer) {
+    for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+      if (mode == 1) {
+#pragma unroll
+        for (int j = 0; j < SY_MAXR; ++j)
+          if (j < c.world) {
+            int p = c.rank + j; if (p >= c.world) p -= c.world;
+            st16(os_slot(c, p, parity, c.rank) + u * 16, ld16(in + (size_t)p * bytes + u * 16));
+          }
+      } else {
+        const V16 v = ld16(in + u * 16);
+#pragma unroll
+        for (int j = 0; j < SY_MAXR; ++j)
+          if (j < c.world) {
+            int p = c.rank + j; if (p >= c.world) p -= c.world;
+            st16(os_slot(c, p, parity, c.rank) + u * 16, v);
+          }
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < c.world) {
+    const int p = threadIdx.x;
+    // flags: writers tell every receiver "my block-b payload has landed".  In a broadcast the non-root ranks also flag the
+    // root (no payload): the root may not run two mailbox generations ahead of a receiver that is still copying out.
+    if (writer || p == root) {
+      uint32_t* remote = reinterpret_cast<uint32_t*>(c.heap[p] + SY_OSFLAGS_OFF) + ((parity * SY_MAX_BLOCKS + blockIdx.x) * SY_MAXR + c.rank);
+      __threadfence_system();
+      st_release_sys(remote, seq);
+    }
+    if (mode != 2 || p == root || c.rank == root) {
+      const uint32_t* local = reinterpret_cast<const uint32_t*>(c.heap[c.rank] + SY_OSFLAGS_OFF) + ((parity * SY_MAX_BLOCKS + blockIdx.x) * SY_MAXR + p);
+      spin_until_ge(local, seq, c);
+    }
+  }
+  __syncthreads();
+  if (mode == 2) {
+    for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) st16(out + u * 16, ld16(os_slot(c, c.rank, parity, root) + u * 16));
+  } else {
+    for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+      V16 v[SY_MAXR];
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) v[r] = ld16(os_slot(c, c.rank, parity, r) + u * 16);
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) st16(out + (size_t)r * bytes + u * 16, v[r]);
+    }
+  }
+  seq_finish(c, 0);
+}
+
 __global__ void k_barrier_k(const __grid_constant__ CommDev c) {
   uint32_t ep = epoch_load(c);
   block_barrier(c, ep);
@@ -1213,6 +1278,13 @@ int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_
   }
 }
 
+// in/out: any device pointers (out is this rank's own buffer); bytes per writer, multiple of 16, <= SY_OS_SLOT
+int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream) {
+  int g = grid_for(c, bytes / 16 + 1, 256);
+  k_mailbox_k<<<g, 256, 0, (cudaStream_t)stream>>>(devof(c), (const char*)in, (char*)out, bytes, mode, root);
+  LAUNCH_CHECK(c);
+  return SY_OK;
+}
 int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt, bool nvls, void* stream) {
   size_t bytes = count * sy_dtype_size(dt);
   int g = grid_for(c, bytes / 16 + 1, (int)c->threads, 4);
