@@ -3,6 +3,9 @@
 set -x
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
+export SHIPYARD_TEST_QUICK=1
+timeout 600 python -m pytest tests/test_gpu_coll.py -m gpu -q -x -k "multi_gpu_collectives or single" 2>&1 | tail -8 | tee gpurun_out/pytest_coll16.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29573 bench/coll_sweep.py --min-bytes 1K --max-bytes 4M --step 4 --ops allgather,alltoall,broadcast --out gpurun_out/coll_sweep16_small_n$NG.jsonl 2>&1 | grep -v Warning | tail -24 | tee gpurun_out/sweep16_small_n$NG.log
 S=k10bench$$
 for r in $(seq 0 $((NG-1))); do timeout 200 python tests/_k10_worker.py --rank $r --world $NG --session $S --device $r --bench > gpurun_out/k10v3_r$r.log 2>&1 & done; wait
 tail -3 gpurun_out/k10v3_r0.log | tee gpurun_out/k10v3_bench_n$NG.log
