@@ -231,7 +231,19 @@ extern "C" int sy_reduce_scatter(sy_comm* c, const void* in, void* out, size_t c
   size_t in_off;
   const size_t total = count * si * c->world;
   if (!sym_off(c, in, &in_off)) {
-    if (total > c->stage_bytes / 2) { sy_set_error("reduce_scatter: input larger than staging; use a symmetric buffer"); return SY_ERR_NOMEM; }
+    if (total > c->stage_bytes / 2) {
+      // chunk along the per-rank count: stage [world x nc] columns of the input per round
+      const size_t so_ = sy_dtype_size(dt_out);
+      const size_t nc_max = (c->stage_bytes / 2 / c->world / si) / 64 * 64;
+      if (nc_max == 0) { sy_set_error("reduce_scatter: no staging space"); return SY_ERR_NOMEM; }
+      for (size_t b = 0; b < count; b += nc_max) {
+        const size_t nc = count - b < nc_max ? count - b : nc_max;
+        CUDA_TRY(cudaMemcpy2DAsync(stage_half(c, 0), nc * si, (const char*)in + b * si, count * si, nc * si, c->world, cudaMemcpyDeviceToDevice, s));
+        int rc2 = sy_reduce_scatter(c, stage_half(c, 0), (char*)out + b * so_, nc, dt_in, dt_out, scale, op, stream);
+        if (rc2) return rc2;
+      }
+      return SY_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(stage_half(c, 0), in, total, cudaMemcpyDeviceToDevice, s));
     in_off = stage_half_off(c, 0);
   }
@@ -271,6 +283,17 @@ extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 0, 0, stream);
+  { size_t o_; if (!sym_off(c, out, &o_) && bytes * c->world > c->stage_bytes / 2) {
+      // plain (non-symmetric) output larger than the staging half: gather it in column chunks through the staging buffer
+      const size_t piece = (c->stage_bytes / 2 / c->world) & ~(size_t)255;
+      for (size_t off = 0; off < bytes; off += piece) {
+        const size_t n = bytes - off < piece ? bytes - off : piece;
+        int rc2 = k_allgather(c, (const char*)in + off, stage_half_off(c, 1), n, SY_U8, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world, stream);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)out + off, bytes, stage_half(c, 1), n, n, c->world, cudaMemcpyDeviceToDevice, s));
+      }
+      return SY_OK;
+  } }
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
   rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
   if (rc) return rc;
@@ -286,6 +309,17 @@ extern "C" int sy_broadcast(sy_comm* c, const void* in, void* out, size_t count,
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   if (mailbox_ok(c, c->rank == root ? in : out, out, bytes)) return k_mailbox(c, c->rank == root ? in : out, out, bytes, 2, root, stream);
+  { size_t o_; if (!sym_off(c, out, &o_) && bytes > c->stage_bytes / 2) {
+      const size_t piece = (c->stage_bytes / 2) & ~(size_t)255;
+      for (size_t off = 0; off < bytes; off += piece) {
+        const size_t n = bytes - off < piece ? bytes - off : piece;
+        int rc2 = k_broadcast(c, c->rank == root ? (const char*)in + off : nullptr, stage_half_off(c, 1), n, root,
+                              c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world, stream);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaMemcpyAsync((char*)out + off, stage_half(c, 1), n, cudaMemcpyDeviceToDevice, s));
+      }
+      return SY_OK;
+  } }
   OutStage t; int rc = out_target(c, out, bytes, &t); if (rc) return rc;
   rc = k_broadcast(c, c->rank == root ? in : nullptr, t.off, bytes, root, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)c->nvls_min_bytes, stream);
   if (rc) return rc;
@@ -300,6 +334,18 @@ extern "C" int sy_alltoall(sy_comm* c, const void* in, void* out, size_t count, 
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 1, 0, stream);
+  { size_t o_; if (!sym_off(c, out, &o_) && bytes * c->world > c->stage_bytes / 2) {
+      // column chunks: stage [world x n] of the input, exchange, scatter the [world x n] result back with a strided copy
+      const size_t piece = (c->stage_bytes / 2 / c->world) & ~(size_t)255;
+      for (size_t off = 0; off < bytes; off += piece) {
+        const size_t n = bytes - off < piece ? bytes - off : piece;
+        CUDA_TRY(cudaMemcpy2DAsync(stage_half(c, 0), n, (const char*)in + off, bytes, n, c->world, cudaMemcpyDeviceToDevice, s));
+        int rc2 = k_alltoall(c, stage_half(c, 0), stage_half_off(c, 1), n, stream);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)out + off, bytes, stage_half(c, 1), n, n, c->world, cudaMemcpyDeviceToDevice, s));
+      }
+      return SY_OK;
+  } }
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
   rc = k_alltoall(c, in, t.off, bytes, stream);
   if (rc) return rc;

@@ -168,6 +168,29 @@ def main():
                 sync()
                 assert torch.equal(sc_out.cpu(), gen(root, cnt * W, dtype, "cpu", salt=17)[R * cnt:(R + 1) * cnt]), "scatter"
             checks += 6
+    # ---- plain (non-symmetric) buffers larger than the staging half: chunked through staging with strided copies ----
+    if 1 < W <= 4 and dev.type == "cuda":
+        big = 20 * (1 << 20) + 64                     # fp32 elements per rank: 80 MB -> W * 80 MB of output
+        g_in = gen(R, big, torch.float32, dev, salt=51)
+        g_out = torch.empty(big * W, dtype=torch.float32, device=dev)
+        comm.all_gather(g_in, g_out); sync()
+        for r in range(W):
+            assert torch.equal(g_out[r * big:(r + 1) * big].cpu(), gen(r, big, torch.float32, "cpu", salt=51)), f"chunked all_gather from {r}"
+        a_in = torch.cat([g_in + float(p) for p in range(W)])            # block p = my data + p
+        a_out = torch.empty_like(a_in)
+        comm.all_to_all(a_in, a_out); sync()
+        for r in range(W):
+            assert torch.equal(a_out[r * big:(r + 1) * big].cpu(), gen(r, big, torch.float32, "cpu", salt=51) + float(R)), f"chunked all_to_all from {r}"
+        b = g_in.clone() if R == W - 1 else torch.zeros_like(g_in)
+        comm.broadcast(b, root=W - 1); sync()
+        assert torch.equal(b.cpu(), gen(W - 1, big, torch.float32, "cpu", salt=51)), "chunked broadcast"
+        rs_out = torch.empty(big, dtype=torch.float32, device=dev)
+        comm.reduce_scatter(a_in, rs_out); sync()
+        ref = sum(gen(r, big, torch.float32, "cpu", salt=51).double() + float(R) for r in range(W))
+        close(rs_out, ref, torch.float32, W, "chunked reduce_scatter")
+        del g_in, g_out, a_in, a_out, b, rs_out
+        torch.cuda.empty_cache()
+        checks += 4
     # symmetric-output variants (zero-copy paths incl. NVLS broadcast/all-gather)
     cnt = 1 << 18
     so = comm.alloc(cnt * W, torch.float32)
