@@ -196,11 +196,20 @@ def main():
         simple_table(rows, os.path.join(P, "conv_dispatch_plan.md"), "Convolution dispatcher: measured per-pass choice per layer shape (us)",
                      "`ops/conv.py` times the tcgen05 implicit-GEMM kernels against cuDNN the first time a shape is seen and keeps the faster per pass; "
                      "fprop timings include the separate BN-statistics pass when the epilogue does not produce them.")
-    for name in ("k10_bench_n8.log", "hpcg7_n1.log", "hpcg6_n1.log"):
-        fp = os.path.join(G, name)
-        if os.path.exists(fp):
-            with open(os.path.join(P, name.replace(".log", ".txt")), "w") as f:
-                f.write(open(fp).read())
+    # K10 / HPCG one-line results: keep every N, latest run per N
+    with open(os.path.join(P, "k10_hpcg_results.md"), "w") as f:
+        f.write("# Fused GEMM + collective (K10) and HPCG results\n\nOne line per run, straight from the benchmark programs (`tests/_k10_worker.py --bench`, "
+                "`recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py`).  K10: m = n = 8192, K split across ranks, times are device-timed max over ranks.\n\n")
+        for pat in ("k10*bench_n*.log", "hpcg*_n*.log"):
+            for path in sorted(glob.glob(os.path.join(G, pat)), key=os.path.getmtime):
+                txt = [l.strip() for l in open(path) if ("bench m=n" in l or l.startswith("{"))]
+                if txt:
+                    f.write(f"* `{os.path.basename(path)}`: {txt[-1]}\n")
+    for old in ("k10_bench_n8.txt", "hpcg6_n1.txt", "hpcg7_n1.txt"):
+        try:
+            os.remove(os.path.join(P, old))
+        except OSError:
+            pass
 
 
 if __name__ == "__main__":
