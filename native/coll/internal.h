@@ -138,7 +138,7 @@ int k_reduce_rooted(sy_comm* c, size_t in_off, void* out, size_t count, int dt, 
                     void* stream);
 int k_local_cast(sy_comm* c, const void* in, void* out, size_t count, int dt_in, int dt_out,
                  float scale, void* stream);
-#define SY_SEQ_WORDS (16 + SY_NSIG)   // [0]=one-shot seq [1]=LL seq [8..10]=done counters [16..]=signal expects
+#define SY_SEQ_WORDS (16 + SY_NSIG + 32)   // [0]=one-shot seq [1]=LL seq [8..10]=done counters [16..]=signal expects [16+NSIG..]=halo block counters
 
 static inline size_t sy_dtype_size(int dt) {
   switch (dt) {

@@ -933,22 +933,49 @@ struct HaloArgs {
 // field array and store it into the neighbour's ghost buffer over NVLink (no
 // pack buffer, no separate copy), then signal; finally wait for my own
 // neighbours' signals.  expected counts live in device memory (graph-safe).
+// kHaloBPD blocks share one descriptor (a 512 KB face pushed by a single block is latency-bound at ~50 us); the last block
+// of a descriptor to finish (device counter) raises the neighbour's signal.  Rows that are contiguous and 16-byte aligned
+// move as 16-byte vectors.
+constexpr int kHaloBPD = 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_halo_k(const __grid_constant__ CommDev c, const T* __restrict__ src, const __grid_constant__ HaloArgs a,
-         uint32_t* expect) {
-  for (int di = blockIdx.x; di < a.ndesc; di += gridDim.x) {
+         uint32_t* expect, uint32_t* done) {
+  const int di = blockIdx.x / kHaloBPD, part = blockIdx.x % kHaloBPD;
+  if (di < a.ndesc) {
     const sy_halo_desc& d = a.d[di];
     T* dst = reinterpret_cast<T*>(c.heap[d.peer] + d.dst_off);
     const long n = (long)d.nx * d.ny * d.nz;
-    for (long i = threadIdx.x; i < n; i += blockDim.x) {
-      long x = i % d.nx, y = (i / d.nx) % d.ny, z = i / ((long)d.nx * d.ny);
-      dst[i] = src[d.src_elem_off + x * d.sx + y * d.sy + z * d.sz];
+    const long per = (n + kHaloBPD - 1) / kHaloBPD;
+    const long i0 = (long)part * per, i1 = i0 + per < n ? i0 + per : n;
+    constexpr int VE = 16 / sizeof(T);
+    const bool contiguous = d.sx == 1 && (d.ny == 1 || d.sy == d.nx) && (d.nz == 1 || d.sz == (long)d.nx * d.ny);
+    const bool vec_ok = contiguous && (((uintptr_t)(src + d.src_elem_off) | (uintptr_t)dst) & 15) == 0 && (per % VE) == 0;
+    if (vec_ok) {
+      const V16* s16 = reinterpret_cast<const V16*>(src + d.src_elem_off);
+      V16* d16 = reinterpret_cast<V16*>(dst);
+      const long v0 = i0 / VE, v1 = i1 / VE;
+      long v = v0 + threadIdx.x;
+      for (; v + 3 * (long)blockDim.x < v1; v += 4 * (long)blockDim.x) {        // four 16 B loads in flight per thread
+        const V16 q0 = s16[v], q1 = s16[v + blockDim.x], q2 = s16[v + 2 * blockDim.x], q3 = s16[v + 3 * blockDim.x];
+        d16[v] = q0; d16[v + blockDim.x] = q1; d16[v + 2 * blockDim.x] = q2; d16[v + 3 * blockDim.x] = q3;
+      }
+      for (; v < v1; v += blockDim.x) d16[v] = s16[v];
+      for (long i = v1 * VE + threadIdx.x; i < i1; i += blockDim.x) dst[i] = src[d.src_elem_off + i];   // tail of the last part
+    } else {
+      for (long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        long x = i % d.nx, y = (i / d.nx) % d.ny, z = i / ((long)d.nx * d.ny);
+        dst[i] = src[d.src_elem_off + x * d.sx + y * d.sy + z * d.sz];
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
-      red_add_release_sys(reinterpret_cast<uint32_t*>(c.heap[d.peer] + SY_SIG_OFF) + d.sig_idx, 1u);
+      if (atomicAdd(&done[di], 1u) == kHaloBPD - 1) {      // every part of this face has been pushed and fenced
+        done[di] = 0;
+        __threadfence_system();
+        red_add_release_sys(reinterpret_cast<uint32_t*>(c.heap[d.peer] + SY_SIG_OFF) + d.sig_idx, 1u);
+      }
     }
   }
   // waits: block 0 only; one thread per expected signal
@@ -1370,13 +1397,14 @@ int k_halo(sy_comm* c, const void* src, int dt, const sy_halo_desc* descs, int n
   for (int i = 0; i < ndesc; ++i) a.d[i] = descs[i];
   for (int i = 0; i < nwait; ++i) a.wait_sig[i] = wait_sig[i];
   uint32_t* expect = c->dev.seq + 16;  // SY_NSIG expected counters follow the sequence words
-  int g = ndesc > 0 ? ndesc : 1;
+  uint32_t* done = c->dev.seq + 16 + SY_NSIG;   // per-descriptor block counters (self-resetting)
+  int g = ndesc > 0 ? ndesc * kHaloBPD : 1;
   CommDev d = devof(c);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dt) {
-    case SY_F64: k_halo_k<double><<<g, 256, 0, s>>>(d, (const double*)src, a, expect); break;
-    case SY_F32: k_halo_k<float><<<g, 256, 0, s>>>(d, (const float*)src, a, expect); break;
-    case SY_BF16: case SY_F16: k_halo_k<uint16_t><<<g, 256, 0, s>>>(d, (const uint16_t*)src, a, expect); break;
+    case SY_F64: k_halo_k<double><<<g, 256, 0, s>>>(d, (const double*)src, a, expect, done); break;
+    case SY_F32: k_halo_k<float><<<g, 256, 0, s>>>(d, (const float*)src, a, expect, done); break;
+    case SY_BF16: case SY_F16: k_halo_k<uint16_t><<<g, 256, 0, s>>>(d, (const uint16_t*)src, a, expect, done); break;
     default: return SY_ERR_UNSUPPORTED;
   }
   LAUNCH_CHECK(c);
