@@ -45,7 +45,7 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->threads = (long)env_sz("SHIPYARD_COLL_THREADS", 512);
   c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 4096);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
-  c->mailbox_max_bytes = (long)env_sz("SHIPYARD_COLL_MAILBOX_MAX", 128 << 10);
+  c->mailbox_max_bytes = (long)env_sz("SHIPYARD_COLL_MAILBOX_MAX", 1 << 20);
   c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);
   c->nvls_min_world = (long)env_sz("SHIPYARD_COLL_NVLS_MIN_WORLD", 4);
   if (heap_bytes == 0) heap_bytes = env_sz("SHIPYARD_COLL_HEAP", transport == SY_TRANSPORT_STUB ? (256ul << 20) : (1ul << 30));

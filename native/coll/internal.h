@@ -58,7 +58,7 @@ struct sy_comm {
   // tuning
   long max_blocks = 128, threads = 512;
   long ll_max_bytes = 4096, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;
-  long mailbox_max_bytes = 128 << 10;   // per-writer payload up to which all-gather / all-to-all / broadcast use the mailbox kernel
+  long mailbox_max_bytes = 1 << 20;     // per-writer payload up to which all-gather / all-to-all / broadcast use the mailbox kernel
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
   long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
