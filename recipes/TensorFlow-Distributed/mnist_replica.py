@@ -73,16 +73,29 @@ def main():
     for _ in range(20):
         step()
     sync = (lambda: torch.cuda.synchronize()) if use_cuda else (lambda: None)
+    graph = None
+    static_loss = torch.zeros((), device=dev)
+    if use_cuda and (a.cuda_graph or os.environ.get("SHIPYARD_TF_GRAPH", "1") != "0"):
+        # forward + backward + ONE fused all-reduce/Adam kernel captured as a CUDA graph: a training step is one launch
+        sync()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss.copy_(step().detach())
     sync(); comm.barrier(); sync()
     t0 = time.time()
     for i in range(a.train_steps):
-        loss = step()
+        if graph is not None:
+            graph.replay()
+        else:
+            loss = step()
+    if graph is not None:
+        loss = static_loss
     sync()
     dt = time.time() - t0
     comm.check_status()
     if rank == 0:
         print(json.dumps({"steps_per_sec": round(a.train_steps / dt, 1), "training_elapsed_s": round(dt, 3), "world": world,
-                          "final_loss": round(float(loss), 4), "gradient_bytes": n * 4, "transport": comm.transport}), flush=True)
+                          "final_loss": round(float(loss), 4), "gradient_bytes": n * 4, "transport": comm.transport, "cuda_graph": graph is not None}), flush=True)
     comm.close()
 
 
