@@ -72,13 +72,15 @@ def main():
             e1.record(); e1.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / iters
         else:
-            tot = 0.0
+            ts = []
             for _ in range(iters):
                 flush.fill_(1)
+                dist.barrier()                 # ranks enter together: a barrier-free collective would otherwise be charged the host skew
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); fn(); e1.record(); e1.synchronize()
-                tot += e0.elapsed_time(e1) * 1e3
-            us = tot / iters
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.sort()
+            us = ts[len(ts) // 2]              # median: one host hiccup in ten iterations must not decide the row
         t = torch.tensor([us], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
