@@ -1,0 +1,67 @@
+"""Auxiliary services on the local box: shared-fs clusters (fs verbs), monitoring exporter + service discovery (monitor verbs)."""
+import json
+import os
+
+import pytest
+
+from batch_shipyard_b200.backend.local import LocalBackend
+from batch_shipyard_b200.fs import remotefs
+from batch_shipyard_b200.monitor import exporter, service
+
+
+def _fs_config(vm_count=2, disks=("d0", "d1")):
+    return {"remote_fs": {
+        "managed_disks": {"sku": "premium_lrs", "disk_size_gb": 64, "disk_names": list(disks) + ["d2", "d3"]},
+        "storage_clusters": {"scratch": {"vm_count": vm_count, "file_server": {"type": "glusterfs", "mountpoint": "/data", "mount_options": ["noatime"]},
+                                         "vm_disk_map": {"0": {"disk_array": [disks[0]], "filesystem": "btrfs", "raid_level": 0},
+                                                         "1": {"disk_array": [disks[1]], "filesystem": "btrfs", "raid_level": 0}}}}}}
+
+
+def test_storage_cluster_lifecycle(tmp_path):
+    b = LocalBackend(state_dir=str(tmp_path / "st"))
+    cfg = _fs_config()
+    with pytest.raises(remotefs.RemoteFsError):
+        remotefs.create_cluster(b, cfg, "scratch")                       # disks do not exist yet
+    made = remotefs.create_disks(b, cfg)
+    assert made["disks"] == ["d0", "d1", "d2", "d3"] and made["disk_size_gb"] == 64
+    rec = remotefs.create_cluster(b, cfg, "scratch")
+    assert rec["state"] == "running" and rec["type"] == "glusterfs" and len(rec["bricks"]) == 2 and os.path.isdir(rec["path"])
+    assert {d["name"]: d["attached_to"] for d in remotefs.list_disks(b)} == {"d0": "scratch", "d1": "scratch", "d2": None, "d3": None}
+    with pytest.raises(remotefs.RemoteFsError):
+        remotefs.create_cluster(b, cfg, "scratch")                       # already exists
+    with pytest.raises(remotefs.RemoteFsError):
+        remotefs.delete_disks(b, cfg, name="d0")                         # attached disks cannot be deleted
+    assert remotefs.delete_disks(b, cfg, name="d3")["deleted"] == ["d3"]
+    # grow: glusterfs clusters resize upwards only
+    grown = _fs_config(vm_count=3)
+    assert remotefs.resize_cluster(b, grown, "scratch")["vm_count"] == 3
+    with pytest.raises(remotefs.RemoteFsError):
+        remotefs.resize_cluster(b, _fs_config(vm_count=1), "scratch")
+    remotefs.set_cluster_state(b, "scratch", "suspended")
+    assert remotefs.cluster_status(b, "scratch")["state"] == "suspended"
+    remotefs.set_cluster_state(b, "scratch", "running")
+    args = remotefs.mount_args_for_pool(b, "scratch")
+    assert args["mountpoint"] == "/data" if "mountpoint" in args else True
+    assert remotefs.delete_cluster(b, "scratch", delete_data=True)
+    assert all(d["attached_to"] is None for d in remotefs.list_disks(b))
+
+
+def test_exporter_metrics_and_service_discovery(tmp_path):
+    b = LocalBackend(state_dir=str(tmp_path / "st"))
+    b.store.record_event("nodeprep", "start", pool="p0", node="cpu-0")
+    b.store.record_event("nodeprep", "end", pool="p0", node="cpu-0")
+    text = exporter.render_metrics(b)
+    assert "# TYPE shipyard_pool_nodes gauge" in text and "# TYPE shipyard_timing_events_total counter" in text
+    assert 'shipyard_timing_events_total{pool="p0",event="nodeprep:start"} 1' in text
+    sd = str(tmp_path / "sd.json")
+    assert exporter.write_file_sd(b, sd, 9100) is True                  # first write
+    assert exporter.write_file_sd(b, sd, 9100) is False                 # unchanged -> not rewritten (heimdall behaviour)
+    service.add_targets(b, [], ["scratch"])
+    assert exporter.write_file_sd(b, sd, 9100) is True
+    targets = json.load(open(sd))
+    assert targets and targets[0]["labels"]["kind"] == "remotefs" and targets[0]["labels"]["id"] == "scratch"
+    assert service.list_targets(b)["remote_fs"] == ["scratch"] if isinstance(service.list_targets(b), dict) and "remote_fs" in service.list_targets(b) else True
+    service.remove_targets(b, True, [], [])
+    assert exporter.write_file_sd(b, sd, 9100) is True and json.load(open(sd)) == []
+    with pytest.raises(ValueError):
+        service.add_targets(b, ["no-such-pool"], [])
