@@ -15,7 +15,7 @@ import os
 import shutil
 import signal
 import time
-from typing import Any, Iterable, Optional
+from typing import Iterable, Optional
 
 from .. import __version__
 from ..config import settings as S

@@ -14,7 +14,6 @@ import os
 import shlex
 import sys
 import zlib
-from typing import Optional
 
 from .._build import native_dir
 

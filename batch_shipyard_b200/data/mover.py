@@ -18,7 +18,7 @@ import shutil
 import sys
 import time
 import urllib.parse
-from typing import Iterable, Optional
+from typing import Iterable
 
 
 def _match(rel: str, include: Iterable[str], exclude: Iterable[str]) -> bool:

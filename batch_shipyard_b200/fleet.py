@@ -18,7 +18,7 @@ import subprocess
 import sys
 import time
 from dataclasses import dataclass, field
-from typing import Any, Optional
+from typing import Optional
 
 from . import __version__
 from .backend.agent import NodeAgent, spawn_detached_agent

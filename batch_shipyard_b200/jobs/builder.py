@@ -19,7 +19,7 @@ from __future__ import annotations
 import re
 import shlex
 from dataclasses import asdict, dataclass, field
-from typing import Any, Optional
+from typing import Optional
 
 from ..config import settings as S
 from ..utils import util

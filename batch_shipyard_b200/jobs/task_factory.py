@@ -21,7 +21,7 @@ import importlib
 import itertools
 import os
 import random as _random
-from typing import Any, Iterator
+from typing import Iterator
 
 
 def _tmpl(task: dict) -> dict:

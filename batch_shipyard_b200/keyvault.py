@@ -11,7 +11,7 @@ import base64
 import json
 import os
 import zlib
-from typing import Any, Optional
+from typing import Any
 
 import yaml
 

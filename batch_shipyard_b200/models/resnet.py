@@ -11,7 +11,7 @@ single launch.
 from __future__ import annotations
 
 import math
-from typing import Callable, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn

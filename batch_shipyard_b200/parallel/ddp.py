@@ -21,7 +21,6 @@ whatever the container's framework does.
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 

@@ -23,7 +23,7 @@ import threading
 import time
 import uuid
 from contextlib import contextmanager
-from typing import Any, Iterable, Optional
+from typing import Any, Optional
 
 
 class EntityExists(Exception):
