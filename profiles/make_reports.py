@@ -198,9 +198,9 @@ def main():
                      "fprop timings include the separate BN-statistics pass when the epilogue does not produce them.")
     # K10 / HPCG one-line results: keep every N, latest run per N
     with open(os.path.join(P, "k10_hpcg_results.md"), "w") as f:
-        f.write("# Fused GEMM + collective (K10) and HPCG results\n\nOne line per run, straight from the benchmark programs (`tests/_k10_worker.py --bench`, "
+        f.write("# Fused GEMM + collective (K10), HPCG and TensorFlow-Distributed recipe results\n\nOne line per run, straight from the benchmark programs (`tests/_k10_worker.py --bench`, "
                 "`recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py`).  K10: m = n = 8192, K split across ranks, times are device-timed max over ranks.\n\n")
-        for pat in ("k10*bench_n*.log", "hpcg*_n*.log"):
+        for pat in ("k10*bench_n*.log", "hpcg*_n*.log", "tfdist*_n*.log"):
             for path in sorted(glob.glob(os.path.join(G, pat)), key=os.path.getmtime):
                 txt = [l.strip() for l in open(path) if ("bench m=n" in l or l.startswith("{"))]
                 if txt:
