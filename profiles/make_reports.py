@@ -103,10 +103,14 @@ def step_breakdown(csv_path, out_md, steps_hint=None):
             continue
         v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
-        k = re.sub(r"<.*|\(.*", "", row["Kernel Name"])[:80]
+        k = re.sub(r"\(.*", "", row["Kernel Name"])
+        k = re.sub(r"^void ", "", k).replace("<unnamed>::", "")
+        if not k.startswith(("gemm_bf16", "k_")):
+            k = re.sub(r"<.*", "", k)                  # library kernels: drop the template noise
+        k = k[:80]
         agg[k][0] += 1; agg[k][1] += v; tot += v
     with open(out_md, "w") as f:
-        f.write("# ResNet-50 training step: kernel time by kernel name\n\nSource: `ncu --metrics gpu__time_duration.sum --clock-control none` over a short "
+        f.write("# ResNet-50 training step: kernel time by kernel name (all convolution passes forced onto the tcgen05 kernels)\n\nSource: `ncu --metrics gpu__time_duration.sum --clock-control none` over a short "
                 f"`bench.py` run (`{os.path.basename(csv_path)}`; warm-up + timed steps, eager mode so every kernel is visible). Numbers under a profiler are for "
                 "attribution only, never bench values.\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
@@ -167,7 +171,9 @@ def main():
         rep = p.replace("_raw.csv", ".ncu-rep")
         if os.path.exists(rep):
             ncu_hot_lines(rep, ["gemm_bf16_tn_2cta_kernel", "gemm_bf16_tn_kernel", "gemm_bf16_nt_splitk_kernel"], os.path.join(P, "ncu_gemm_kernels.md"))
-    p = latest("launches_shipyard*.csv")
+    p = os.path.join(G, "launches9_conv1_notc0.csv")          # SHIPYARD_CONV_IMPL=tc: every conv pass on our kernels
+    if not os.path.exists(p):
+        p = latest("launches_shipyard*.csv")
     if p:
         step_breakdown(p, os.path.join(P, "step_breakdown.md"))
     coll_tables(os.path.join(P, "coll_sweeps.md"))
