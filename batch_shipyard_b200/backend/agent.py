@@ -4,7 +4,7 @@ The part of Azure Batch the reference never had to write: picking runnable tasks
 (dependencies, job state, priority), placing them on node slots (pack / spread,
 multi-instance tasks need N nodes at once), job preparation / release tasks,
 retries, exit-condition actions, auto-complete, job schedules (recurrence, the
-reference's ``cargo/recurrent_job_manager.py:56-253``), autoscale evaluation and
+reference's /root/reference/cargo/recurrent_job_manager.py:56-253), autoscale evaluation and
 recovery of tasks orphaned by an agent crash.  Execution itself is delegated to
 ``shipyard-taskrun`` (one process per task), so the agent only polls.
 

@@ -1,4 +1,10 @@
-"""ctypes binding for ``libshipyard_ops`` (fused elementwise / normalisation kernels)."""
+"""ctypes binding for ``libshipyard_ops`` (fused elementwise / normalisation kernels).
+
+No counterpart in the reference: its recipes run framework containers (e.g. MNIST on PyTorch,
+/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8); these kernels are the memory-bound half of the
+retargeted ResNet-50 recipe (BN(+residual)(+ReLU) forward / backward, max-pool, uint8 -> bf16 input conversion)
+and of the HPCG retarget (``sy_hpcg_*``, /root/reference/recipes/HPCG-Infiniband-IntelMPI/config/docker/jobs.yaml:5-20).
+"""
 from __future__ import annotations
 
 import ctypes as C

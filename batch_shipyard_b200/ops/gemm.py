@@ -1,4 +1,8 @@
-"""ctypes binding + autograd wrappers for ``libshipyard_gemm`` (tcgen05/TMEM/TMA bf16 GEMM).
+"""ctypes binding + autograd wrappers for ``libshipyard_gemm`` (tcgen05/TMEM/TMA bf16 GEMM and implicit-GEMM convolution).
+
+The reference ships no compute kernels (its GPU recipes launch framework containers, e.g.
+/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8 and /root/reference/recipes/CNTK-GPU-OpenMPI/docker/run_cntk.sh:66-78);
+these are the tensor-core half of the retargeted recipes.
 
 ``gemm_tn(a, b)`` computes ``a @ b.T`` for row-major bf16 ``a[M,K]``, ``b[N,K]`` — the shape of a
 ``Linear`` and of a 1x1 convolution on NHWC activations (``X[M=N*H*W, Cin] @ W[Cout, Cin]^T``).

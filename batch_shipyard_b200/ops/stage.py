@@ -2,8 +2,8 @@
 
 ``Stager(device=None)`` is the host-only mode used on CPU boxes; with a device index the
 arena is cudaHostAlloc'd and copies run on per-worker CUDA copy streams.  Used by the
-image/artefact pre-loader (cascade equivalent), ``shipyard data ingress`` and the recipes'
-input pipelines.
+image/artefact pre-loader (cascade equivalent: /root/reference/cascade/cascade.py:500-646 pulls images with
+bounded concurrency), ``shipyard data ingress`` (/root/reference/convoy/data.py:492-876) and the recipes' input pipelines.
 """
 from __future__ import annotations
 

@@ -1,7 +1,8 @@
 // Host shared-memory transport: same API as the GPU transports, CPU reductions.
 // Lets `shipyard jobs add` multi-instance tasks, the MPI face and every
 // collective run on a box with no GPU (BASELINE.json config #1: world_size=2
-// dry-run with the stub collectives shim).
+// dry-run with the stub collectives shim).  Stands in for the MPI / NCCL libraries the reference's recipe
+// images bring along (e.g. /root/reference/recipes/mpiBench-OpenMPI/docker/Dockerfile:21-35).
 #include <atomic>
 #include <errno.h>
 #include <fcntl.h>

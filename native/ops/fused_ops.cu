@@ -1,6 +1,7 @@
 // Fused elementwise / normalisation kernels for the recipe workloads (sm_100a).
 // All are HBM-bandwidth bound: 16-byte vector accesses, one pass over the data,
-// statistics accumulated in fp32.
+// statistics accumulated in fp32.  The reference has no kernels; these serve the retargeted
+// PyTorch-GPU recipe (/root/reference/recipes/PyTorch-GPU/config/jobs.yaml:1-8) and the HPCG retarget.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
