@@ -188,3 +188,22 @@ def test_slurm_hostlist_and_retry_daemon(tmp_path):
     assert b.store.get("slurmhost", cid, "sc-p-nopool-0")["resume_failures"] == 2
     sl.resume_failed(b, cfg, ["sc-p-nopool-0"])
     assert b.store.get("slurmhost", cid, "sc-p-nopool-0")["state"] == "suspended"
+
+
+def test_federation_leader_failover(tmp_path, monkeypatch):
+    """Two proxy daemons share the store: one leads; when it stops renewing, the lease expires and the other takes over."""
+    import time
+    from batch_shipyard_b200.backend.local import LocalBackend
+    from batch_shipyard_b200.fed import daemon as fd
+    monkeypatch.setattr(fd, "LEADER_LEASE_S", 0.3)
+    monkeypatch.setattr(fd, "LEADER_RENEW_S", 0.05)
+    b = LocalBackend(state_dir=str(tmp_path / "st"))
+    a, c = fd.FederationProcessor(b, holder="proxy-a"), fd.FederationProcessor(b, holder="proxy-b")
+    assert a.is_leader() and not c.is_leader()
+    for _ in range(4):                        # a keeps renewing: b never gets in
+        time.sleep(0.1)
+        assert a.is_leader() and not c.is_leader()
+    time.sleep(0.45)                          # a "crashes" (stops renewing): the lease runs out
+    assert c.is_leader()
+    assert not a.is_leader()                  # and the old leader cannot reclaim it while b renews
+    assert b.store.lease_holder("federation-leader") == "proxy-b"
