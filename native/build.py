@@ -154,7 +154,29 @@ def artifact(name: str) -> str:
     return p
 
 
+def build_sanitizers() -> dict:
+    """Sanitizer builds of the host-side native code: the multi-threaded staging library under
+    ThreadSanitizer with a concurrent driver, the task runner under Address+UndefinedBehaviour sanitizers.
+    Outputs go to build/san/ (never shipped).  Returns {name: path}."""
+    san = os.path.join(ROOT, "build", "san")
+    os.makedirs(san, exist_ok=True)
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    out = {"stage_tsan": os.path.join(san, "stage_tsan"), "taskrun_asan": os.path.join(san, "shipyard-taskrun-asan")}
+    # the sanitizer runtimes ship with the distribution compiler, not necessarily with $CXX
+    cxx = os.environ.get("CXX_SAN") or next((c for c in ("/usr/bin/g++", "/usr/bin/clang++") if os.path.exists(c)), CXX)
+    _run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-I", cuda_inc,
+          os.path.join(NATIVE, "tests", "tsan_stage.cpp"), os.path.join(NATIVE, "stage", "stage.cpp"),
+          "-o", out["stage_tsan"], "-L", cuda_lib, "-lcudart", "-Wl,-rpath," + cuda_lib], os.path.join(san, "stage_tsan.log"))
+    _run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-pthread",
+          os.path.join(NATIVE, "runner", "taskrun.cpp"), "-o", out["taskrun_asan"]], os.path.join(san, "taskrun_asan.log"))
+    return out
+
+
 if __name__ == "__main__":
+    if "--sanitizers" in sys.argv:
+        for k, v in build_sanitizers().items():
+            print(f"{k}: built {os.path.relpath(v, ROOT)}")
+        sys.exit(0)
     args = [a for a in sys.argv[1:] if not a.startswith("-")]
     if "--clean" in sys.argv:
         shutil.rmtree(OBJ, ignore_errors=True)
