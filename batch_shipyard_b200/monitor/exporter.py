@@ -79,6 +79,32 @@ def render_metrics(b: LocalBackend, pools: Optional[list] = None) -> str:
         k = (e["pool"] or "", f"{e['source']}:{e['event']}")
         ev[k] = ev.get(k, 0) + 1
     m("shipyard_timing_events_total", "Timing events recorded", "counter", [({"pool": k[0], "event": k[1]}, c) for k, c in sorted(ev.items())])
+    # per-collective latency histograms written by traced communicators (SHIPYARD_TRACE, ops/coll.py)
+    agg: dict = {}
+    mdir = os.path.join(b.root, "metrics")
+    if os.path.isdir(mdir):
+        for fn in sorted(os.listdir(mdir)):
+            if not (fn.startswith("coll-") and fn.endswith(".json")):
+                continue
+            try:
+                with open(os.path.join(mdir, fn)) as f:
+                    doc = json.load(f)
+            except (OSError, ValueError):
+                continue
+            for op, h in (doc.get("ops") or {}).items():
+                a = agg.setdefault(op, {"count": 0, "sum_us": 0.0, "buckets": [0] * len(h["buckets"]), "edges": doc.get("buckets_us") or []})
+                a["count"] += h["count"]; a["sum_us"] += h["sum_us"]
+                a["buckets"] = [x + y for x, y in zip(a["buckets"], h["buckets"])]
+    bucket_s, count_s, sum_s = [], [], []
+    for op, a in sorted(agg.items()):
+        run = 0
+        for edge, c in zip(list(a["edges"]) + ["+Inf"], a["buckets"]):
+            run += c
+            bucket_s.append(({"op": op, "le": edge}, run))
+        count_s.append(({"op": op}, a["count"])); sum_s.append(({"op": op}, round(a["sum_us"], 2)))
+    m("shipyard_collective_latency_us_bucket", "Device-side latency of collective calls (cumulative histogram)", "histogram", bucket_s)
+    m("shipyard_collective_latency_us_count", "Collective calls observed", "counter", count_s)
+    m("shipyard_collective_latency_us_sum", "Summed device-side latency in microseconds", "counter", sum_s)
     return "\n".join(L) + "\n"
 
 

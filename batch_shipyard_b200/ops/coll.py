@@ -138,6 +138,9 @@ class Communicator:
         self.heap_bytes = self.lib.sy_heap_bytes(h)
         self.torch_device = torch.device("cpu") if self.is_stub else torch.device("cuda", self.device_index)
         self._keep = []
+        self._trace = None
+        if os.environ.get("SHIPYARD_TRACE"):
+            self._install_tracing(os.environ["SHIPYARD_TRACE"])
 
     # -- lifecycle ---------------------------------------------------------
     @classmethod
@@ -149,9 +152,98 @@ class Communicator:
         return cls(rank, world, default_session(tag), device, **kw)
 
     def close(self) -> None:
+        if getattr(self, "_trace", None) is not None:
+            try:
+                self.flush_trace(final=True)
+            except Exception:  # noqa: BLE001 - tracing must never break teardown
+                pass
         if getattr(self, "_h", None) is not None:
             self.lib.sy_comm_destroy(self._h)
             self._h = None
+
+    # -- tracing (JSONL trace per rank, device-side timings per collective, NVTX ranges) -------------
+    _TRACED = ("all_reduce", "reduce_scatter", "all_gather", "broadcast", "all_to_all", "reduce", "gather", "scatter", "barrier",
+               "halo_exchange", "fused_allreduce_sgd", "fused_allreduce_adam", "all_reduce_fp8")
+    _BUCKETS_US = (5, 10, 20, 50, 100, 200, 500, 1000, 5000, 20000, 100000)
+
+    def _install_tracing(self, path: str) -> None:
+        """SHIPYARD_TRACE=<prefix>: every collective call is bracketed by CUDA events on its stream (time.perf_counter on the
+        stub transport) and an NVTX range; records go to <prefix>.rank<r>.jsonl without ever synchronising the stream (events
+        are harvested when they have completed, the rest at close()).  A latency histogram per operation is written next to
+        the trace and, when SHIPYARD_STATE_DIR is set, under <state>/metrics/ for the Prometheus exporter."""
+        self._trace = {"path": f"{path}.rank{self.rank}.jsonl", "pending": [], "hist": {}, "records": 0}
+        for name in self._TRACED:
+            fn = getattr(self, name, None)
+            if fn is not None:
+                setattr(self, name, self._traced(name, fn))
+
+    def _traced(self, name, fn):
+        import time as _time
+
+        def wrapper(*a, **kw):
+            tr = self._trace
+            first = next((x for x in a if isinstance(x, torch.Tensor)), None)
+            nbytes = 0 if first is None else first.numel() * first.element_size()
+            cuda = self.torch_device.type == "cuda"
+            if cuda and torch.cuda.is_current_stream_capturing():
+                return fn(*a, **kw)                                  # inside a graph capture: nothing to time per call
+            ts = _time.time()
+            if cuda:
+                stream = kw.get("stream") or torch.cuda.current_stream(self.torch_device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.nvtx.range_push(f"shipyard:{name}:{nbytes}B")
+                e0.record(stream)
+                try:
+                    return fn(*a, **kw)
+                finally:
+                    e1.record(stream)
+                    torch.cuda.nvtx.range_pop()
+                    tr["pending"].append((ts, name, nbytes, e0, e1))
+                    if len(tr["pending"]) >= 256:
+                        self.flush_trace()
+            else:
+                t0 = _time.perf_counter()
+                try:
+                    return fn(*a, **kw)
+                finally:
+                    self._trace_emit(ts, name, nbytes, (_time.perf_counter() - t0) * 1e6)
+        wrapper.__name__ = name
+        return wrapper
+
+    def _trace_emit(self, ts: float, name: str, nbytes: int, us: float) -> None:
+        import json as _json
+        tr = self._trace
+        with open(tr["path"], "a") as f:
+            f.write(_json.dumps({"ts": round(ts, 6), "rank": self.rank, "world": self.world, "event": f"coll:{name}", "bytes": nbytes,
+                                 "device_us": round(us, 2), "transport": self.transport}) + "\n")
+        h = tr["hist"].setdefault(name, {"count": 0, "sum_us": 0.0, "buckets": [0] * (len(self._BUCKETS_US) + 1)})
+        h["count"] += 1; h["sum_us"] += us
+        h["buckets"][next((i for i, b in enumerate(self._BUCKETS_US) if us <= b), len(self._BUCKETS_US))] += 1
+        tr["records"] += 1
+
+    def flush_trace(self, final: bool = False) -> None:
+        import json as _json
+        tr = self._trace
+        if tr is None:
+            return
+        keep = []
+        for (ts, name, nbytes, e0, e1) in tr["pending"]:
+            if final:
+                e1.synchronize()
+            if e1.query():
+                self._trace_emit(ts, name, nbytes, e0.elapsed_time(e1) * 1e3)
+            else:
+                keep.append((ts, name, nbytes, e0, e1))
+        tr["pending"] = keep
+        if final:
+            summary = {"rank": self.rank, "world": self.world, "transport": self.transport, "buckets_us": list(self._BUCKETS_US), "ops": tr["hist"]}
+            with open(tr["path"].replace(".jsonl", ".hist.json"), "w") as f:
+                _json.dump(summary, f)
+            sd = os.environ.get("SHIPYARD_STATE_DIR")
+            if sd:
+                os.makedirs(os.path.join(sd, "metrics"), exist_ok=True)
+                with open(os.path.join(sd, "metrics", f"coll-{os.getpid()}-rank{self.rank}.json"), "w") as f:
+                    _json.dump(summary, f)
 
     def __del__(self):  # pragma: no cover - best effort
         try:

@@ -65,3 +65,28 @@ def test_exporter_metrics_and_service_discovery(tmp_path):
     assert exporter.write_file_sd(b, sd, 9100) is True and json.load(open(sd)) == []
     with pytest.raises(ValueError):
         service.add_targets(b, ["no-such-pool"], [])
+
+
+def test_collective_trace_and_latency_histogram(tmp_path, monkeypatch):
+    """SHIPYARD_TRACE: JSONL trace per rank + latency histogram picked up by the exporter."""
+    import torch
+    from batch_shipyard_b200.ops.coll import Communicator
+    state = tmp_path / "st"
+    monkeypatch.setenv("SHIPYARD_TRACE", str(tmp_path / "trace"))
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(state))
+    comm = Communicator(0, 1, device=None, heap_bytes=16 << 20)
+    x = torch.arange(1024, dtype=torch.float32)
+    out = torch.empty_like(x)
+    for _ in range(3):
+        comm.all_reduce(x, out)
+    comm.barrier()
+    comm.close()
+    lines = [json.loads(l) for l in open(str(tmp_path / "trace") + ".rank0.jsonl")]
+    assert [l["event"] for l in lines] == ["coll:all_reduce"] * 3 + ["coll:barrier"]
+    assert lines[0]["bytes"] == 4096 and lines[0]["device_us"] >= 0 and lines[0]["transport"] == "stub"
+    hist = json.load(open(str(tmp_path / "trace") + ".rank0.hist.json"))
+    assert hist["ops"]["all_reduce"]["count"] == 3 and sum(hist["ops"]["all_reduce"]["buckets"]) == 3
+    b = LocalBackend(state_dir=str(state))
+    text = exporter.render_metrics(b)
+    assert 'shipyard_collective_latency_us_count{op="all_reduce"} 3' in text
+    assert 'shipyard_collective_latency_us_bucket{op="all_reduce",le="+Inf"} 3' in text
