@@ -43,6 +43,33 @@ def gpu_metrics() -> list[dict]:
     return rows
 
 
+def parse_nvlink_counters(text: str) -> list[dict]:
+    """`nvidia-smi nvlink -gt d` -> [{gpu, link, tx_bytes, rx_bytes}] (KiB counters; tolerant of layout differences)."""
+    import re
+    rows: dict = {}
+    gpu = None
+    for line in text.splitlines():
+        mg = re.match(r"\s*GPU\s+(\d+)\s*:", line)
+        if mg:
+            gpu = int(mg.group(1)); continue
+        ml = re.match(r"\s*Link\s+(\d+)\s*:\s*(?:Data\s+)?(Tx|Rx)\s*:\s*([0-9.]+)\s*(KiB|MiB|GiB|B)?", line, re.I)
+        if ml and gpu is not None:
+            mult = {"b": 1, "kib": 1 << 10, "mib": 1 << 20, "gib": 1 << 30}[(ml.group(4) or "KiB").lower()]
+            r = rows.setdefault((gpu, int(ml.group(1))), {"gpu": gpu, "link": int(ml.group(1)), "tx_bytes": 0.0, "rx_bytes": 0.0})
+            r["tx_bytes" if ml.group(2).lower() == "tx" else "rx_bytes"] = float(ml.group(3)) * mult
+    return [rows[k] for k in sorted(rows)]
+
+
+def nvlink_metrics() -> list[dict]:
+    if not shutil.which("nvidia-smi"):
+        return []
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+    except Exception:  # noqa: BLE001
+        return []
+    return parse_nvlink_counters(out)
+
+
 def render_metrics(b: LocalBackend, pools: Optional[list] = None) -> str:
     L = []
 
@@ -58,6 +85,9 @@ def render_metrics(b: LocalBackend, pools: Optional[list] = None) -> str:
     m("shipyard_gpu_memory_used_bytes", "GPU memory in use", "gauge", [({"gpu": r["index"]}, r["mem_used"]) for r in g])
     m("shipyard_gpu_power_watts", "GPU power draw", "gauge", [({"gpu": r["index"]}, r["power"]) for r in g])
     m("shipyard_gpu_sm_clock_mhz", "GPU SM clock", "gauge", [({"gpu": r["index"]}, r["sm_mhz"]) for r in g])
+    nv = nvlink_metrics()
+    m("shipyard_nvlink_tx_bytes_total", "NVLink bytes transmitted per GPU link", "counter", [({"gpu": r["gpu"], "link": r["link"]}, int(r["tx_bytes"])) for r in nv])
+    m("shipyard_nvlink_rx_bytes_total", "NVLink bytes received per GPU link", "counter", [({"gpu": r["gpu"], "link": r["link"]}, int(r["rx_bytes"])) for r in nv])
     node_s, task_s, slot_s = [], [], []
     for p in b.list_pools():
         if pools and p["id"] not in pools:

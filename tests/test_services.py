@@ -90,3 +90,19 @@ def test_collective_trace_and_latency_histogram(tmp_path, monkeypatch):
     text = exporter.render_metrics(b)
     assert 'shipyard_collective_latency_us_count{op="all_reduce"} 3' in text
     assert 'shipyard_collective_latency_us_bucket{op="all_reduce",le="+Inf"} 3' in text
+
+
+def test_nvlink_counter_parser():
+    sample = """GPU 0: NVIDIA B200 (UUID: GPU-aaaa)
+\t Link 0: Data Tx: 1024 KiB
+\t Link 0: Data Rx: 2048 KiB
+\t Link 1: Data Tx: 3 MiB
+\t Link 1: Data Rx: 0 KiB
+GPU 1: NVIDIA B200 (UUID: GPU-bbbb)
+\t Link 0: Data Tx: 5 KiB
+\t Link 0: Data Rx: 7 KiB
+"""
+    rows = exporter.parse_nvlink_counters(sample)
+    assert rows[0] == {"gpu": 0, "link": 0, "tx_bytes": 1024 * 1024.0, "rx_bytes": 2048 * 1024.0}
+    assert rows[1]["tx_bytes"] == 3 * (1 << 20) and rows[2] == {"gpu": 1, "link": 0, "tx_bytes": 5 * 1024.0, "rx_bytes": 7 * 1024.0}
+    assert exporter.parse_nvlink_counters("nothing useful") == []
