@@ -22,16 +22,32 @@ def test_all_reference_target_recipes_present():
 
 @pytest.mark.parametrize("recipe", RECIPES)
 def test_recipe_config_validates(recipe):
+    """Every config file of every recipe passes the strict schema validation; job commands point at files that exist."""
     cfg = loader.load_configs(configdir=os.path.join(ROOT, "recipes", recipe, "config"))
-    assert S.pool_id(cfg)
-    jobs = cfg["job_specifications"]
-    assert jobs and jobs[0]["tasks"][0]["multi_instance"]["num_instances"] == "pool_current_dedicated"
-    cmd = jobs[0]["tasks"][0]["command"]
-    # the command points at something that exists in this tree
-    for tok in cmd.split():
-        if tok.startswith("$SHIPYARD_HOME/"):
-            rel = tok[len("$SHIPYARD_HOME/"):]
-            assert os.path.exists(os.path.join(ROOT, rel)) or rel.startswith("batch_shipyard_b200/_native/"), rel
+    if "pool_specification" in cfg:
+        assert S.pool_id(cfg)
+    for job in cfg.get("job_specifications") or []:
+        for task in job["tasks"]:
+            mi = task.get("multi_instance")
+            if mi is not None:
+                assert mi["num_instances"] == "pool_current_dedicated" and mi["mpi"]["runtime"] in ("openmpi", "mpich", "mvapich", "intelmpi", "intelmpi-ofa")
+            for tok in task["command"].split():
+                if tok.startswith("$SHIPYARD_HOME/"):
+                    rel = tok[len("$SHIPYARD_HOME/"):]
+                    assert os.path.exists(os.path.join(ROOT, rel)) or rel.startswith("batch_shipyard_b200/_native/"), rel
+    if "remote_fs" in cfg:
+        assert S.remotefs_storage_clusters(cfg)["mystoragecluster"].vm_count >= 1
+    if "slurm" in cfg:
+        assert S.slurm_options(cfg)["cluster_id"] == "myslurmcluster"
+
+
+def test_recipe_catalogue_covers_the_reference():
+    """One directory per reference recipe (Windows-only recipes excluded)."""
+    ref = "/root/reference/recipes"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted")
+    want = {d for d in os.listdir(ref) if os.path.isdir(os.path.join(ref, d)) and "Windows" not in d}
+    assert want <= set(RECIPES), sorted(want - set(RECIPES))
 
 
 def _run_world(script, args, world=2, timeout=300):
