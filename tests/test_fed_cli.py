@@ -207,3 +207,16 @@ def test_federation_leader_failover(tmp_path, monkeypatch):
     assert c.is_leader()
     assert not a.is_leader()                  # and the old leader cannot reclaim it while b renews
     assert b.store.lease_holder("federation-leader") == "proxy-b"
+
+
+def test_generated_docs_are_current():
+    """docs/cli.md lists every leaf command; regenerate with `python docs/gen_docs.py` after changing the CLI."""
+    import os
+    from batch_shipyard_b200 import cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "docs", "cli.md")).read()
+    missing = [c for c in cli.leaf_commands() if f"### `shipyard {c}`" not in text]
+    assert not missing, missing
+    cfg = open(os.path.join(root, "docs", "configuration.md")).read()
+    for section in ("config.yaml", "credentials.yaml", "pool.yaml", "jobs.yaml", "fs.yaml", "federation.yaml", "monitor.yaml", "slurm.yaml"):
+        assert f"## {section}" in cfg
