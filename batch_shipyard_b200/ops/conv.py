@@ -6,6 +6,10 @@ The reference has no compute path at all (its recipes run third-party framework 
 
 ``SHIPYARD_CONV_IMPL`` = ``auto`` (default: measure, keep the faster), ``tc`` (always our kernels where the shape is
 supported) or ``cudnn`` (library only).  The chosen table is available from ``plan_table()`` and is printed by bench.py.
+
+``SHIPYARD_CONV_HALO=1`` adds the halo-load 3x3 kernels (``th`` / ``th2``, native/gemm/conv_halo.inc: one TMA box per tile and
+channel block instead of nine im2col boxes) to the candidates.  Every halo candidate is first compared against the cuDNN
+result of the same call; a mismatch disables the halo kernels for the process (``halo_state()``) instead of training on them.
 """
 from __future__ import annotations
 
@@ -20,12 +24,14 @@ from . import gemm as _gemm
 
 _MODE = os.environ.get("SHIPYARD_CONV_IMPL", "auto").lower()
 _PLANS: dict = {}
+_HALO = os.environ.get("SHIPYARD_CONV_HALO", "0") not in ("0", "", "off", "false")
+_HALO_STATE = {"enabled": _HALO, "checked": 0, "failed": []}
 _HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics pass (profiles/ncu_bn_kernels.md)
 
 
 @dataclass
 class ConvPlan:
-    fprop: str = "cudnn"      # "tc" (1-CTA tcgen05) | "tc2" (CTA-pair, cta_group::2) | "cudnn"
+    fprop: str = "cudnn"      # "tc" (1-CTA tcgen05 im2col) | "tc2" (CTA pair) | "th" (halo load) | "th2" (halo, CTA pair) | "cudnn"
     dgrad: str = "cudnn"
     wgrad: str = "cudnn"
     stats: bool = False       # fprop produces the BatchNorm statistics in its epilogue
@@ -37,6 +43,16 @@ def set_mode(mode: str) -> None:
     assert mode in ("auto", "tc", "cudnn")
     _MODE = mode
     _PLANS.clear()
+
+
+def set_halo(on: bool) -> None:
+    """Enable / disable the halo-load 3x3 candidates (clears the plan table)."""
+    _HALO_STATE.update(enabled=bool(on), checked=0, failed=[])
+    _PLANS.clear()
+
+
+def halo_state() -> dict:
+    return dict(_HALO_STATE)
 
 
 def plan_table() -> dict:
@@ -98,7 +114,9 @@ def _time(fn, iters: int = 5, reps: int = 4) -> float:
 
 
 # ---- the individual passes ---------------------------------------------------------------------------------------------
-def _fprop_tc(x, w, stride, pad, stats, two_cta=False):
+def _fprop_tc(x, w, stride, pad, stats, two_cta=False, impl=None):
+    if impl in ("th", "th2"):
+        return _gemm.conv3x3_halo(x, w, False, stats=stats, pair=impl == "th2")
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -107,7 +125,9 @@ def _fprop_tc(x, w, stride, pad, stats, two_cta=False):
     return _gemm.conv_fprop_nhwc(x, w, stride, pad, stats=stats, two_cta=two_cta)
 
 
-def _dgrad_tc(dy, x, w, stride, pad, two_cta=False):
+def _dgrad_tc(dy, x, w, stride, pad, two_cta=False, impl=None):
+    if impl in ("th", "th2"):
+        return _gemm.conv3x3_halo(dy, w, True, pair=impl == "th2")
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -124,6 +144,34 @@ def _two_cta_caps(x, w, stride) -> dict:
     p, q = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
     m_ok = (n * p * q) % 256 == 0
     return {"fprop": m_ok and cout % 128 == 0, "dgrad": m_ok and cin % 128 == 0 and stride == 1}
+
+
+def _halo_caps(x, w, stride) -> dict:
+    """Halo-load kernels: 3x3, stride 1, whole image rows per 128-row tile (ops.gemm.halo_ok)."""
+    off = {"fprop": False, "fprop2": False, "dgrad": False, "dgrad2": False}
+    if not _HALO_STATE["enabled"] or not (x.is_cuda and x.dtype == torch.bfloat16):
+        return off
+    n, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    a = (n, h, wd)
+    return {"fprop": _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2), "fprop2": _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2, pair=True),
+            "dgrad": _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, dgrad=True),
+            "dgrad2": _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, pair=True, dgrad=True)}
+
+
+def _close(a: torch.Tensor, ref: torch.Tensor) -> bool:
+    a, ref = a.float(), ref.float()
+    return bool(torch.isfinite(a).all()) and float((a - ref).abs().max()) <= 0.02 * float(ref.abs().max()) + 1e-3
+
+
+def _halo_check(tag: str, key, got: torch.Tensor, ref: torch.Tensor) -> bool:
+    """A halo candidate only enters the race if it reproduces the library result on this very call."""
+    _HALO_STATE["checked"] += 1
+    if _close(got, ref):
+        return True
+    _HALO_STATE["failed"].append(f"{tag}:{'x'.join(map(str, key))}")
+    _HALO_STATE["enabled"] = False              # one wrong answer: stop using the kernels in this process
+    return False
 
 
 def _wgrad_tc(dy, x, w, stride, pad, out_view, accumulate):
@@ -165,10 +213,16 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
     plan = ConvPlan(timings_us={})
     if _MODE == "cudnn" or not any(caps.values()):
         return plan
+    hc = _halo_caps(x, w, stride)
     if _MODE == "tc":
         c2 = _two_cta_caps(x, w, stride)
-        return ConvPlan(("tc2" if c2["fprop"] else "tc") if caps["fprop"] else "cudnn",
-                        ("tc2" if c2["dgrad"] else "tc") if caps["dgrad"] else "cudnn", "tc" if caps["wgrad"] else "cudnn",
+        fp = ("tc2" if c2["fprop"] else "tc") if caps["fprop"] else "cudnn"
+        dg = ("tc2" if c2["dgrad"] else "tc") if caps["dgrad"] else "cudnn"
+        if hc["fprop"]:
+            fp = "th2" if hc["fprop2"] else "th"
+        if hc["dgrad"]:
+            dg = "th2" if hc["dgrad2"] else "th"
+        return ConvPlan(fp, dg, "tc" if caps["wgrad"] else "cudnn",
                         stats=caps["fprop"] and (k > 1 or stride > 1 or cin >= 256), timings_us={})
     t = plan.timings_us
     with torch.no_grad():
@@ -186,17 +240,27 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
                 t["fprop_tc2_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st, True))
                 t["fprop_tc2"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None, True)) + t_stats_pass
                 cands += ["fprop_tc2_stats", "fprop_tc2"]
+            for impl, cap in (("th", "fprop"), ("th2", "fprop2")):
+                if hc[cap] and _HALO_STATE["enabled"] and _halo_check("fprop_" + impl, _key(x, w, stride), _fprop_tc(xd, wd_, stride, pad, None, impl=impl), y):
+                    t[f"fprop_{impl}_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st, impl=impl))
+                    t[f"fprop_{impl}"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None, impl=impl)) + t_stats_pass
+                    cands += [f"fprop_{impl}_stats", f"fprop_{impl}"]
             best = min(cands, key=lambda k_: t[k_])
-            plan.fprop = "cudnn" if best == "fprop_cudnn" else ("tc2" if "tc2" in best else "tc")
+            plan.fprop = best.split("_")[1]
             plan.stats = best.endswith("_stats")
-        dy = torch.randn_like(y)
+        dy = torch.randn_like(y).contiguous(memory_format=torch.channels_last)
         t["dgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, True, False))
         if caps["dgrad"]:
             t["dgrad_tc"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad))
             if caps2["dgrad"]:
                 t["dgrad_tc2"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad, True))
-            best = min([k_ for k_ in ("dgrad_cudnn", "dgrad_tc", "dgrad_tc2") if k_ in t], key=lambda k_: t[k_])
-            plan.dgrad = {"dgrad_cudnn": "cudnn", "dgrad_tc": "tc", "dgrad_tc2": "tc2"}[best]
+            if hc["dgrad"] and _HALO_STATE["enabled"]:
+                dx_ref = _cudnn_bwd(dy, xd, wd_, stride, pad, True, False)[0]
+                for impl, cap in (("th", "dgrad"), ("th2", "dgrad2")):
+                    if hc[cap] and _HALO_STATE["enabled"] and _halo_check("dgrad_" + impl, _key(x, w, stride), _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl), dx_ref):
+                        t[f"dgrad_{impl}"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl))
+            best = min([k_ for k_ in t if k_.startswith("dgrad_")], key=lambda k_: t[k_])
+            plan.dgrad = best.split("_")[1]
         t_accum = w.numel() * 6 / 4e12 * 1e6 + 3.0                     # AccumulateGrad add the library path pays
         t["wgrad_cudnn"] = _time(lambda: _cudnn_bwd(dy, xd, wd_, stride, pad, False, True)) + t_accum
         if caps["wgrad"]:
@@ -223,10 +287,10 @@ class _Conv(torch.autograd.Function):
         k = w.shape[2]
         pad = k // 2
         stats = None
-        if plan.fprop in ("tc", "tc2"):
+        if plan.fprop != "cudnn":
             if plan.stats:
                 stats = torch.zeros(2 * w.shape[0], dtype=torch.float32, device=x.device)
-            y = _fprop_tc(x, w, stride, pad, stats, plan.fprop == "tc2")
+            y = _fprop_tc(x, w, stride, pad, stats, plan.fprop == "tc2", impl=plan.fprop)
         else:
             y = F.conv2d(x, w, None, stride, pad)
         ctx.save_for_backward(x, w)
@@ -243,12 +307,12 @@ class _Conv(torch.autograd.Function):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = dw = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        lib_dx = need_dx and plan.dgrad not in ("tc", "tc2")
+        lib_dx = need_dx and plan.dgrad == "cudnn"
         lib_dw = need_dw and plan.wgrad != "tc"
         if lib_dx or lib_dw:
             dx, dw = _cudnn_bwd(dy, x, w, stride, pad, lib_dx, lib_dw)
-        if need_dx and plan.dgrad in ("tc", "tc2"):
-            dx = _dgrad_tc(dy, x, w, stride, pad, plan.dgrad == "tc2")
+        if need_dx and plan.dgrad != "cudnn":
+            dx = _dgrad_tc(dy, x, w, stride, pad, plan.dgrad == "tc2", impl=plan.dgrad)
         if need_dw and plan.wgrad == "tc":
             dw = _wgrad_tc(dy, x, w, stride, pad, _grad_view(ctx.w_ref), True)     # None when written into .grad in place
         return dx, dw, None, None

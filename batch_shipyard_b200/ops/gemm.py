@@ -50,6 +50,8 @@ def load() -> C.CDLL:
         lib.sy_conv_bf16_nhwc_2cta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_conv3x3_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        lib.sy_conv3x3_halo_rows.argtypes = [C.c_int, C.c_int]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -379,6 +381,52 @@ def conv_fprop_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int 
                                C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
     if rc != 0:
         raise RuntimeError(f"sy_conv_bf16_nhwc fprop failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return y.permute(0, 3, 1, 2)
+
+
+def halo_rows(h: int, w: int) -> int:
+    """Image rows per M tile of the halo-load 3x3 kernel: the largest divisor R of H with R*(W+2) <= 128 (0 = unsupported).
+    Pure-Python mirror of ``halo_rows`` in native/gemm/conv_halo.inc so the dispatcher can filter shapes without a GPU."""
+    wp, best = w + 2, 0
+    for r in range(1, h + 1):
+        if h % r == 0 and r * wp <= 128 and (r + 2) * wp <= 256 and wp <= 256:
+            best = r
+    return best
+
+
+def halo_ok(n: int, h: int, w: int, c_act: int, c_out: int, r: int, s: int, stride: int, pad: int, pair: bool = False,
+            dgrad: bool = False) -> bool:
+    """Shapes the halo-load kernel accepts: 3x3, stride 1, pad 1, activation channels % 64, whole image rows per tile."""
+    if (r, s, stride, pad) != (3, 3, 1, 1) or c_act % 64 or c_out % (64 if dgrad else 8):
+        return False
+    rows = halo_rows(h, w)
+    if rows == 0:
+        return False
+    if pair:
+        return c_out % 128 == 0 and (n * (h // rows)) % 2 == 0
+    return True
+
+
+_HALO_BASE_MODE = int(os.environ.get("SHIPYARD_HALO_BASE_MODE", "1"))
+
+
+def conv3x3_halo(act: torch.Tensor, w: torch.Tensor, dgrad: bool = False, stats: Optional[torch.Tensor] = None, block_n: int = 0,
+                 pair: bool = False, base_mode: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution through the halo-load kernel (native/gemm/conv_halo.inc).
+
+    fprop: ``act`` = x[N,Cin,H,W], ``w`` = W[Cout,Cin,3,3] -> y[N,Cout,H,W] (optionally the BN statistics of y in ``stats``);
+    dgrad: ``act`` = dY[N,Cout,H,W], same ``w`` -> dX[N,Cin,H,W].  channels_last bf16 in and out."""
+    n, ca, h, wd = act.shape
+    cn = w.shape[1] if dgrad else w.shape[0]
+    a_s, w_s = _nhwc_storage(act), _nhwc_storage(w)
+    y = torch.empty((n, h, wd, cn), dtype=torch.bfloat16, device=act.device)
+    lib = load()
+    rc = lib.sy_conv3x3_halo(C.c_void_p(a_s.data_ptr()), C.c_void_p(w_s.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, ca, cn,
+                             1 if dgrad else 0, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, 1 if pair else 0,
+                             _HALO_BASE_MODE if base_mode is None else base_mode, max_ctas,
+                             C.c_void_p(torch.cuda.current_stream(act.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_conv3x3_halo failed ({rc}): {lib.sy_gemm_last_error().decode()}")
     return y.permute(0, 3, 1, 2)
 
 

@@ -220,9 +220,11 @@ def _conv_summary():
         tab = _conv.plan_table()
         out = {"mode": _conv._MODE, "shapes": len(tab)}
         for pas in ("fprop", "dgrad", "wgrad"):
-            out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] in ("tc", "tc2"))
-            out[pas + "_tc_2cta"] = sum(1 for v in tab.values() if v[pas] == "tc2")
+            out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] != "cudnn")
+            out[pas + "_tc_2cta"] = sum(1 for v in tab.values() if v[pas] in ("tc2", "th2"))
+            out[pas + "_halo"] = sum(1 for v in tab.values() if v[pas] in ("th", "th2"))
         out["fprop_fused_bn_stats"] = sum(1 for v in tab.values() if v["stats"])
+        out["halo"] = _conv.halo_state()
         if os.environ.get("SHIPYARD_CONV_PLAN_DUMP"):
             os.makedirs("gpurun_out", exist_ok=True)
             with open(os.path.join("gpurun_out", "conv_plan.json"), "w") as f:

@@ -74,7 +74,7 @@ def _newer(out: str, deps: list[str]) -> bool:
 def _headers() -> list[str]:
     hs = []
     for d, _, fs in os.walk(NATIVE):
-        hs += [os.path.join(d, f) for f in fs if f.endswith((".h", ".cuh", ".hpp"))]
+        hs += [os.path.join(d, f) for f in fs if f.endswith((".h", ".cuh", ".hpp", ".inc"))]
     return hs
 
 

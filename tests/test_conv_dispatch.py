@@ -28,3 +28,24 @@ def test_capabilities_table():
     assert caps == {"fprop": False, "dgrad": False, "wgrad": False}      # CPU tensors: never on the tcgen05 kernels
     plan = conv.ConvPlan()
     assert (plan.fprop, plan.dgrad, plan.wgrad, plan.stats) == ("cudnn", "cudnn", "cudnn", False)
+
+
+def test_halo_candidates_are_gated_and_self_checked():
+    """The halo-load kernels are opt-in, never offered for CPU tensors, and one wrong answer disables them for the process."""
+    x = torch.empty(256, 64, 56, 56, dtype=torch.bfloat16)
+    w3 = torch.empty(64, 64, 3, 3, dtype=torch.bfloat16)
+    conv.set_halo(True)
+    try:
+        assert conv._halo_caps(x, w3, 1) == {"fprop": False, "fprop2": False, "dgrad": False, "dgrad2": False}   # CPU tensor
+        ref = torch.randn(4, 8, 6, 6)
+        assert conv._halo_check("fprop_th", (1, 2, 3), ref + 1e-4, ref)
+        assert conv.halo_state()["enabled"] and conv.halo_state()["checked"] == 1
+        bad = ref.clone(); bad[0, 0, 0, 0] += 10.0
+        assert not conv._halo_check("fprop_th", (1, 2, 3), bad, ref)
+        st = conv.halo_state()
+        assert not st["enabled"] and st["failed"] == ["fprop_th:1x2x3"]
+        nan = ref.clone(); nan[1, 1, 1, 1] = float("nan")
+        assert not conv._close(nan, ref)
+    finally:
+        conv.set_halo(False)
+    assert conv.halo_state() == {"enabled": False, "checked": 0, "failed": []}
