@@ -402,8 +402,27 @@ extern "C" int sy_barrier(sy_comm* c, sy_stream_t stream) {
   return k_barrier(c, stream);
 }
 
+// Fault injection for the flag protocol (tests only): SHIPYARD_FAULT_INJECT=drop_signal:<rank>:<n> makes rank <rank>'s n-th
+// (1-based) put_signal deliver the payload but never raise the flag, so the peer's bounded wait must end in SY_ERR_TIMEOUT
+// (the watchdog) instead of a hang.  (The task runner interprets the kill_rank:... form of the same variable.)
+static bool fault_drop_signal(const sy_comm* c) {
+  static int target = -2, nth = 0, calls = 0;
+  if (target == -2) {
+    target = -1;
+    const char* fi = getenv("SHIPYARD_FAULT_INJECT");
+    int r = 0, n = 0;
+    if (fi && sscanf(fi, "drop_signal:%d:%d", &r, &n) == 2) { target = r; nth = n; }
+  }
+  return target == c->rank && ++calls == nth;
+}
+
 extern "C" int sy_put_signal(sy_comm* c, const void* src, size_t dst_off, size_t bytes, int peer, int sig, sy_stream_t stream) {
   if (peer < 0 || peer >= c->world || sig < 0 || sig >= SY_NSIG || dst_off + bytes > c->heap_bytes) return SY_ERR_ARG;
+  if (fault_drop_signal(c)) {
+    if (is_stub(c)) { memcpy(c->dev.heap[peer] + dst_off, src, bytes); return SY_OK; }
+    CUDA_TRY(cudaMemcpyAsync(c->dev.heap[peer] + dst_off, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SY_OK;
+  }
   if (is_stub(c)) return stub_put_signal(c, src, dst_off, bytes, peer, sig);
   return k_put_signal(c, src, dst_off, bytes, peer, sig, stream);
 }

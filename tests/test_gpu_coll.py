@@ -62,3 +62,12 @@ def test_k10_gemm_allreduce_fused(transport):
     world = min(_ngpu(), 8)
     ok, outs = run_ranks("_k10_worker.py", world, extra=["--transport", transport], gpu=True, timeout=600)
     assert ok, "\n".join(o[-3000:] for o in outs)
+
+
+@pytest.mark.multigpu
+def test_flag_protocol_litmus_over_nvlink():
+    """Message-passing litmus on P2P-mapped flags (payload stores, release flag / acquire flag, payload loads), 500 ping-pong rounds."""
+    _need_multi()
+    ok, outs = run_ranks("_litmus_worker.py", 2, extra=["--rounds", "500"], gpu=True, timeout=300)
+    assert ok, "\n".join(o[-3000:] for o in outs)
+    assert all("transport=gpu" in o for o in outs)
