@@ -22,6 +22,16 @@ from ..ops import fused as _fused
 from ..ops import gemm as _gemm
 
 
+import os as _os0
+
+_BN_DUAL = [_os0.environ.get("SHIPYARD_BN_DUAL", "0") not in ("0", "", "off", "false")]
+
+
+def set_bn_dual(on: bool) -> None:
+    """Residual-gradient fusion (two-handle block outputs) on / off; read at forward time."""
+    _BN_DUAL[0] = bool(on)
+
+
 class ConvBN(nn.Module):
     """conv (no bias) + train-mode BatchNorm (+ residual add) (+ ReLU)."""
 
@@ -38,7 +48,7 @@ class ConvBN(nn.Module):
         import os as _os
         self.use_tc_gemm = not _os.environ.get("SHIPYARD_NO_TC_GEMM")     # off: plain cuDNN path, no dispatcher
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, dual: bool = False):
         fast = x.is_cuda and self.training and x.dtype == torch.bfloat16
         stats = None
         if fast and self.k in (1, 3) and self.use_tc_gemm:
@@ -54,7 +64,7 @@ class ConvBN(nn.Module):
             # one fused stats + apply(+residual)(+ReLU) pair instead of BN / add / ReLU kernels;
             # no eager fallback on GPU: a missing extension must fail loudly
             return _fused.fused_bn_act(y, self.gamma, self.beta, residual, self.running_mean, self.running_var,
-                                       self.relu, self.eps, self.momentum, stats=stats)
+                                       self.relu, self.eps, self.momentum, stats=stats, dual=dual)
         y = F.batch_norm(y.float(), self.running_mean, self.running_var, self.gamma.float(), self.beta.float(),
                          self.training, self.momentum, self.eps).to(y.dtype)
         if residual is not None:
@@ -74,8 +84,12 @@ class Bottleneck(nn.Module):
         self.down = ConvBN(cin, cout, 1, stride, relu=False) if (stride != 1 or cin != cout) else None
 
     def forward(self, x):
-        idt = x if self.down is None else self.down(x)
-        return self.c3(self.c2(self.c1(x)), residual=idt)
+        # SHIPYARD_BN_DUAL: the block output travels as two handles of one tensor (ops.fused.fused_bn_act(dual=True)); the next
+        # block gives one to its first convolution and one to its residual input, so the two gradients meet inside the BN
+        # backward kernels of THIS block instead of in a separate add kernel (12 of the 16 blocks of ResNet-50).
+        xm, xa = x if isinstance(x, tuple) else (x, x)
+        idt = xa if self.down is None else self.down(xm)
+        return self.c3(self.c2(self.c1(xm)), residual=idt, dual=_BN_DUAL[0])
 
 
 class ResNet(nn.Module):
@@ -103,6 +117,8 @@ class ResNet(nn.Module):
         fast = x.is_cuda and x.dtype == torch.bfloat16 and self.training
         x = _fused.maxpool3x3s2(x) if (fast and x.shape[1] % 8 == 0) else F.max_pool2d(x, 3, 2, 1)
         x = self.blocks(x)
+        if isinstance(x, tuple):
+            x = x[0]
         x = x.mean(dim=(2, 3))
         if fast and self.use_tc_gemm:
             return _gemm.linear(x, self.fc_weight, self.fc_bias)          # FC on the tcgen05 kernel (bias fused)

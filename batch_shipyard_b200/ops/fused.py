@@ -71,6 +71,7 @@ def _bind_bn(lib):
     lib.sy_ops_bn_apply_only.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float,
                                          C.c_float, C.c_int, vp, vp]
     lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.sy_ops_bn_bwd_dual.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.sy_ops_maxpool3x3s2_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.sy_ops_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.sy_ops_u8_to_s2d_norm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
@@ -94,8 +95,9 @@ class _FusedBNAct(torch.autograd.Function):
     """y = act(BN_train(x) [+ residual]) with saved (x, y, mean, invstd) for the fused backward."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats, dual=False):
         lib = load(); _bind_bn(lib)
+        ctx.set_materialize_grads(False)                # an unused second output must arrive as None, not as a zeros tensor
         assert x.is_cuda and x.dtype == torch.bfloat16 and _is_nhwc(x), "fused BN wants NHWC bf16"
         n, c, h, w = x.shape
         m = n * h * w
@@ -121,17 +123,31 @@ class _FusedBNAct(torch.autograd.Function):
         ctx.has_mask = mask is not None
         ctx.relu, ctx.has_res = bool(relu), residual is not None
         ctx.beta_ref = beta if isinstance(beta, torch.nn.Parameter) else None
+        ctx.dual = bool(dual)
+        if dual:
+            # the same activation twice: consumers that use the two handles (next block's first conv / its residual input)
+            # send their gradients back separately, and the backward kernels add them in registers (no add kernel)
+            return out, out.view_as(out)
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dout2=None):
         lib = load(); _bind_bn(lib)
         x, mask, mean, invstd, gamma = ctx.saved_tensors
         mask = mask if ctx.has_mask else None
         n, c, h, w = x.shape
         m = n * h * w
+        nres = 11
+        if dout is None:
+            dout, dout2 = dout2, None
+        if dout is None:
+            return (None,) * nres
         if not _is_nhwc(dout):
             dout = dout.contiguous(memory_format=torch.channels_last)
+        if dout2 is not None and not _is_nhwc(dout2):
+            dout2 = dout2.contiguous(memory_format=torch.channels_last)
+        if dout2 is not None and ctx.relu and mask is None:
+            dout, dout2 = dout + dout2, None            # the two-gradient kernels gate with the bit mask only
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         # write dgamma/dbeta straight into the parameters' .grad views when they exist (flat gradient buffer):
@@ -145,20 +161,28 @@ class _FusedBNAct(torch.autograd.Function):
             dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
             dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
         ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
-        rc = lib.sy_ops_bn_bwd(_ptr(dout), None, _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
-                               _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
-                               1 if direct else 0, _ptr(mask), _stream(x))
+        if dout2 is not None:
+            rc = lib.sy_ops_bn_bwd_dual(_ptr(dout), _ptr(dout2), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
+                                        _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
+                                        1 if direct else 0, _ptr(mask), _stream(x))
+        else:
+            rc = lib.sy_ops_bn_bwd(_ptr(dout), None, _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
+                                   _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,
+                                   1 if direct else 0, _ptr(mask), _stream(x))
         if rc != 0:
             raise RuntimeError(f"fused BN backward failed (rc={rc})")
         if direct:
-            return dx, None, None, dres, None, None, None, None, None, None
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+            return (dx, None, None, dres) + (None,) * (nres - 4)
+        return (dx, dgamma, dbeta, dres) + (None,) * (nres - 4)
 
 
 def fused_bn_act(x, gamma, beta, residual=None, running_mean=None, running_var=None, relu=True, eps=1e-5,
-                 momentum=0.1, stats=None):
-    """Train-mode BN + optional residual + optional ReLU in two passes (NHWC bf16, CUDA only)."""
-    return _FusedBNAct.apply(x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats)
+                 momentum=0.1, stats=None, dual=False):
+    """Train-mode BN + optional residual + optional ReLU in two passes (NHWC bf16, CUDA only).
+
+    ``dual=True`` returns the output twice ``(y, y_alias)`` (same storage): give one handle to each of two consumers and
+    their gradients are summed inside the backward kernels instead of by a separate autograd add kernel."""
+    return _FusedBNAct.apply(x, gamma, beta, residual, running_mean, running_var, relu, eps, momentum, stats, dual)
 
 
 def bn_act_reference(x, gamma, beta, residual=None, relu=True, eps=1e-5):

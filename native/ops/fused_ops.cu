@@ -224,43 +224,56 @@ DEVI void relu_gate(float* d, bool relu, bool has_mask, uint32_t bits, const V16
 }
 
 // s1[c] = sum dz, s2[c] = sum dz * xhat, dz = relu ? dout * (out > 0) : dout
+// kDual: the incoming gradient is the SUM of two tensors (a block output that feeds both the next block's first convolution
+// and its residual connection): reading both here removes the separate add kernel autograd would run (read 2, write 1) and
+// the re-read of its result.  The dual variant needs the saved ReLU bit mask (no `out` re-read), which keeps it at 111
+// registers with the same 4-deep unroll (two resident blocks, like the single-gradient kernel).
+template <bool kDual>
 __global__ void __launch_bounds__(256)
-k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2, const __nv_bfloat16* __restrict__ out,
                 const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                 const float* __restrict__ invstd, float* __restrict__ sums, long M, int C, int relu,
                 const uint8_t* __restrict__ mask) {
+  constexpr int U = kU;
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float mu[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) mu[i] = mean[cg * 8 + i];
   float acc[2][8] = {};
   const long stride = (long)gridDim.x * rpi;
-  const bool use_out = relu && !mask;
-  auto body = [&](const V16& vd, const V16& vx, uint32_t bits, const V16& vo) {
+  const bool use_out = !kDual && relu && !mask;
+  auto body = [&](const V16& vd, const V16& vd2, const V16& vx, uint32_t bits, const V16& vo) {
     float d[8], xv[8];
     unpack8(vd, d); unpack8(vx, xv);
-    relu_gate(d, relu, mask != nullptr, bits, vo);
+    if constexpr (kDual) {
+      float e[8]; unpack8(vd2, e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] += e[i];
+    }
+    relu_gate(d, relu, kDual || mask != nullptr, bits, vo);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[0][i] += d[i]; acc[1][i] = fmaf(d[i], xv[i] - mu[i], acc[1][i]); }
   };
   long r = (long)blockIdx.x * rpi + rl;
-  for (; r + (kU - 1) * stride < M; r += kU * stride) {
-    V16 vd[kU], vx[kU], vo[kU]; uint32_t mb[kU];
+  for (; r + (U - 1) * stride < M; r += U * stride) {
+    V16 vd[U], vd2[U], vx[U], vo[U]; uint32_t mb[U];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long rr = r + u * stride;
       const size_t off = (size_t)rr * C + cg * 8;
       vd[u] = ldg16(dout + off); vx[u] = ldg16(x + off);
+      if constexpr (kDual) vd2[u] = ldg16(dout2 + off);
       mb[u] = (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu;
       if (use_out) vo[u] = ldg16(out + off);
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) body(vd[u], vx[u], mb[u], vo[u]);
+    for (int u = 0; u < U; ++u) body(vd[u], vd2[u], vx[u], mb[u], vo[u]);
   }
   for (; r < M; r += stride) {
     const size_t off = (size_t)r * C + cg * 8;
-    V16 vo{}; if (use_out) vo = ldg16(out + off);
-    body(ldg16(dout + off), ldg16(x + off), (relu && mask) ? mask[(size_t)r * G + cg] : 0xffu, vo);
+    V16 vo{}, v2{}; if (use_out) vo = ldg16(out + off);
+    if constexpr (kDual) v2 = ldg16(dout2 + off);
+    body(ldg16(dout + off), v2, ldg16(x + off), (relu && mask) ? mask[(size_t)r * G + cg] : 0xffu, vo);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[1][i] *= invstd[cg * 8 + i];       // xhat = (x - mean) * invstd, factored out of the loop
@@ -268,13 +281,15 @@ k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __r
 }
 
 // dx = gamma*invstd*(dz - s1/M - xhat*s2/M); dres = dz; block 0 writes dgamma/dbeta (bf16)
+template <bool kDual>
 __global__ void __launch_bounds__(256)
-k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ dout2, const __nv_bfloat16* __restrict__ out,
                const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ gamma,
                const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
                __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dgamma,
                __nv_bfloat16* __restrict__ dbeta, long M, int C, int relu, int accum, const uint8_t* __restrict__ mask) {
+  constexpr int U = kU;
   const int G = C / 8, rpi = 256 / G, cg = threadIdx.x % G, rl = threadIdx.x / G;
   float k0[8], k1[8], k2[8];
   const float invM = 1.f / (float)M;
@@ -294,12 +309,17 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
     }
   }
   const long stride = (long)gridDim.x * rpi;
-  const bool use_out = relu && !mask;
-  auto body = [&](long rr, const V16& vd, const V16& vx, uint32_t bits, const V16& vo) {
+  const bool use_out = !kDual && relu && !mask;
+  auto body = [&](long rr, const V16& vd, const V16& vd2, const V16& vx, uint32_t bits, const V16& vo) {
     const size_t off = (size_t)rr * C + cg * 8;
     float d[8], xv[8];
     unpack8(vd, d); unpack8(vx, xv);
-    relu_gate(d, relu, mask != nullptr, bits, vo);
+    if constexpr (kDual) {
+      float e[8]; unpack8(vd2, e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] += e[i];
+    }
+    relu_gate(d, relu, kDual || mask != nullptr, bits, vo);
     if (dres) stg16(dres + off, pack8(d));
     float g[8];
 #pragma unroll
@@ -308,24 +328,26 @@ k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
   };
   // reversed row order: the reduce pass that ran just before ended on the last rows, so they are the ones in L2
   long r = (long)blockIdx.x * rpi + rl;
-  for (; r + (kU - 1) * stride < M; r += kU * stride) {
-    V16 vd[kU], vx[kU], vo[kU]; uint32_t mb[kU];
+  for (; r + (U - 1) * stride < M; r += U * stride) {
+    V16 vd[U], vd2[U], vx[U], vo[U]; uint32_t mb[U];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long rr = M - 1 - (r + u * stride);
       const size_t off = (size_t)rr * C + cg * 8;
       vd[u] = ldg16(dout + off); vx[u] = ldg16(x + off);
+      if constexpr (kDual) vd2[u] = ldg16(dout2 + off);
       mb[u] = (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu;
       if (use_out) vo[u] = ldg16(out + off);
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) body(M - 1 - (r + u * stride), vd[u], vx[u], mb[u], vo[u]);
+    for (int u = 0; u < U; ++u) body(M - 1 - (r + u * stride), vd[u], vd2[u], vx[u], mb[u], vo[u]);
   }
   for (; r < M; r += stride) {
     const long rr = M - 1 - r;
     const size_t off = (size_t)rr * C + cg * 8;
-    V16 vo{}; if (use_out) vo = ldg16(out + off);
-    body(rr, ldg16(dout + off), ldg16(x + off), (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu, vo);
+    V16 vo{}, v2{}; if (use_out) vo = ldg16(out + off);
+    if constexpr (kDual) v2 = ldg16(dout2 + off);
+    body(rr, ldg16(dout + off), v2, ldg16(x + off), (relu && mask) ? mask[(size_t)rr * G + cg] : 0xffu, vo);
   }
 }
 
@@ -382,21 +404,41 @@ extern "C" int sy_ops_bn_apply_only(const void* x, const void* res, void* out, c
   RET_LAST();
 }
 
-extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
-                             const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
-                             int relu, int accum, const void* mask, void* stream) {
+static int bn_bwd_launch(const void* dout, const void* dout2, const void* out, const void* x, const float* mean, const float* invstd,
+                         const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
+                         int relu, int accum, const void* mask, void* stream) {
   if (!bn_shape_ok(C)) return -1;
+  if (dout2 && relu && !mask) return -2;          // the two-gradient variant gates with the saved bit mask only
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
   const int g = bn_grid(M, C, 2);
-  k_bn_bwd_reduce<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
-                                    ws, M, C, relu, (const uint8_t*)mask);
-  COUNT_LAUNCH();
-  k_bn_bwd_apply<<<g, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, mean, invstd,
-                                   (const __nv_bfloat16*)gamma, ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
-                                   (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum, (const uint8_t*)mask);
+  auto D = [](const void* p) { return (const __nv_bfloat16*)p; };
+  if (dout2) {
+    k_bn_bwd_reduce<true><<<g, 256, 0, s>>>(D(dout), D(dout2), D(out), D(x), mean, invstd, ws, M, C, relu, (const uint8_t*)mask);
+    COUNT_LAUNCH();
+    k_bn_bwd_apply<true><<<g, 256, 0, s>>>(D(dout), D(dout2), D(out), D(x), mean, invstd, D(gamma), ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                           (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum, (const uint8_t*)mask);
+  } else {
+    k_bn_bwd_reduce<false><<<g, 256, 0, s>>>(D(dout), nullptr, D(out), D(x), mean, invstd, ws, M, C, relu, (const uint8_t*)mask);
+    COUNT_LAUNCH();
+    k_bn_bwd_apply<false><<<g, 256, 0, s>>>(D(dout), nullptr, D(out), D(x), mean, invstd, D(gamma), ws, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                            (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, M, C, relu, accum, (const uint8_t*)mask);
+  }
   COUNT_LAUNCH();
   RET_LAST();
+}
+
+extern "C" int sy_ops_bn_bwd(const void* dout, const void* out, const void* x, const float* mean, const float* invstd,
+                             const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
+                             int relu, int accum, const void* mask, void* stream) {
+  return bn_bwd_launch(dout, nullptr, out, x, mean, invstd, gamma, dx, dres, dgamma, dbeta, ws, M, C, relu, accum, mask, stream);
+}
+
+// backward with the incoming gradient given as two tensors (dout + dout2 is formed in registers); needs `mask` when relu != 0
+extern "C" int sy_ops_bn_bwd_dual(const void* dout, const void* dout2, const void* x, const float* mean, const float* invstd,
+                                  const void* gamma, void* dx, void* dres, void* dgamma, void* dbeta, float* ws, long M, int C,
+                                  int relu, int accum, const void* mask, void* stream) {
+  return bn_bwd_launch(dout, dout2, nullptr, x, mean, invstd, gamma, dx, dres, dgamma, dbeta, ws, M, C, relu, accum, mask, stream);
 }
 
 // ===========================================================================
