@@ -154,9 +154,11 @@ def _halo_caps(x, w, stride) -> dict:
     n, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
     a = (n, h, wd)
-    return {"fprop": _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2), "fprop2": _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2, pair=True),
+    pair = os.environ.get("SHIPYARD_HALO_PAIR", "1") != "0"
+    return {"fprop": _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2),
+            "fprop2": pair and _gemm.halo_ok(*a, cin, cout, k, k, stride, k // 2, pair=True),
             "dgrad": _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, dgrad=True),
-            "dgrad2": _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, pair=True, dgrad=True)}
+            "dgrad2": pair and _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, pair=True, dgrad=True)}
 
 
 def _close(a: torch.Tensor, ref: torch.Tensor) -> bool:

@@ -26,6 +26,9 @@ def _mk(n, cin, h, w, cout):
 @pytest.mark.parametrize("pair", [False, True])
 def test_halo_fprop_stats_and_dgrad(n, cin, h, w, cout, pair):
     from batch_shipyard_b200.ops import gemm
+    import os
+    if pair and os.environ.get("SHIPYARD_HALO_PAIR", "1") == "0":
+        pytest.skip("CTA-pair halo kernels disabled (SHIPYARD_HALO_PAIR=0)")
     if pair and not gemm.halo_ok(n, h, w, cin, cout, 3, 3, 1, 1, pair=True):
         pytest.skip("CTA pairs need out channels % 128 and an even number of M tiles")
     x, wt = _mk(n, cin, h, w, cout)
@@ -65,7 +68,9 @@ def test_halo_in_dispatcher_matches_library():
         conv.set_halo(True)
         x2, w2 = _mk(32, 128, 28, 28, 128)
         plan = conv.plan_for(x2, w2, 1)
-        assert plan.fprop == "th2" and plan.dgrad == "th2"
+        import os
+        want = "th" if os.environ.get("SHIPYARD_HALO_PAIR", "1") == "0" else "th2"
+        assert plan.fprop == want and plan.dgrad == want
         y2, s2 = conv.conv_bn_input(x2, w2, 1)
         torch.testing.assert_close(y2.float(), F.conv2d(x2.float(), w2.float(), padding=1), atol=0.03, rtol=2e-2)
         assert s2 is not None
