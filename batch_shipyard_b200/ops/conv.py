@@ -7,7 +7,7 @@ The reference has no compute path at all (its recipes run third-party framework 
 ``SHIPYARD_CONV_IMPL`` = ``auto`` (default: measure, keep the faster), ``tc`` (always our kernels where the shape is
 supported) or ``cudnn`` (library only).  The chosen table is available from ``plan_table()`` and is printed by bench.py.
 
-``SHIPYARD_CONV_HALO=1`` adds the halo-load 3x3 kernels (``th`` / ``th2``, native/gemm/conv_halo.inc: one TMA box per tile and
+``SHIPYARD_CONV_HALO`` (default on; ``0`` removes them) adds the halo-load 3x3 kernels (``th`` / ``th2``, native/gemm/conv_halo.inc: one TMA box per tile and
 channel block instead of nine im2col boxes) to the candidates.  Every halo candidate is first compared against the cuDNN
 result of the same call; a mismatch disables the halo kernels for the process (``halo_state()``) instead of training on them.
 """
@@ -24,7 +24,7 @@ from . import gemm as _gemm
 
 _MODE = os.environ.get("SHIPYARD_CONV_IMPL", "auto").lower()
 _PLANS: dict = {}
-_HALO = os.environ.get("SHIPYARD_CONV_HALO", "0") not in ("0", "", "off", "false")
+_HALO = os.environ.get("SHIPYARD_CONV_HALO", "1") not in ("0", "", "off", "false")
 _HALO_STATE = {"enabled": _HALO, "checked": 0, "failed": []}
 _HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics pass (profiles/ncu_bn_kernels.md)
 
@@ -220,9 +220,10 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
         c2 = _two_cta_caps(x, w, stride)
         fp = ("tc2" if c2["fprop"] else "tc") if caps["fprop"] else "cudnn"
         dg = ("tc2" if c2["dgrad"] else "tc") if caps["dgrad"] else "cudnn"
-        if hc["fprop"]:
+        # forced mode: the halo kernels where they measured faster than the im2col ones (profiles/conv_halo.md): rows of >= 28 pixels
+        if hc["fprop"] and x.shape[3] >= 28:
             fp = "th2" if hc["fprop2"] else "th"
-        if hc["dgrad"]:
+        if hc["dgrad"] and x.shape[3] >= 28:
             dg = "th2" if hc["dgrad2"] else "th"
         return ConvPlan(fp, dg, "tc" if caps["wgrad"] else "cudnn",
                         stats=caps["fprop"] and (k > 1 or stride > 1 or cin >= 256), timings_us={})

@@ -407,7 +407,10 @@ def halo_ok(n: int, h: int, w: int, c_act: int, c_out: int, r: int, s: int, stri
     return True
 
 
-_HALO_BASE_MODE = int(os.environ.get("SHIPYARD_HALO_BASE_MODE", "1"))
+# A-descriptor base_offset for the row-shifted taps: 0.  Measured on B200 (profiles/conv_halo.md): tcgen05 applies the 128-byte
+# swizzle to the absolute shared-memory address, so a start address that is not 1024-byte aligned needs NO base offset when the
+# data was written by TMA into a 1024-byte aligned buffer; setting base_offset = (addr >> 7) & 7 gives wrong results.
+_HALO_BASE_MODE = int(os.environ.get("SHIPYARD_HALO_BASE_MODE", "0"))
 
 
 def conv3x3_halo(act: torch.Tensor, w: torch.Tensor, dgrad: bool = False, stats: Optional[torch.Tensor] = None, block_n: int = 0,

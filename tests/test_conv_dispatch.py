@@ -31,7 +31,7 @@ def test_capabilities_table():
 
 
 def test_halo_candidates_are_gated_and_self_checked():
-    """The halo-load kernels are opt-in, never offered for CPU tensors, and one wrong answer disables them for the process."""
+    """The halo-load kernels are never offered for CPU tensors, and one wrong answer disables them for the process."""
     x = torch.empty(256, 64, 56, 56, dtype=torch.bfloat16)
     w3 = torch.empty(64, 64, 3, 3, dtype=torch.bfloat16)
     conv.set_halo(True)
@@ -47,5 +47,5 @@ def test_halo_candidates_are_gated_and_self_checked():
         nan = ref.clone(); nan[1, 1, 1, 1] = float("nan")
         assert not conv._close(nan, ref)
     finally:
-        conv.set_halo(False)
-    assert conv.halo_state() == {"enabled": False, "checked": 0, "failed": []}
+        conv.set_halo(conv._HALO)            # back to the process default (SHIPYARD_CONV_HALO, on unless set to 0)
+    assert conv.halo_state() == {"enabled": conv._HALO, "checked": 0, "failed": []}

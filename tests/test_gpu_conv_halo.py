@@ -75,5 +75,5 @@ def test_halo_in_dispatcher_matches_library():
         torch.testing.assert_close(y2.float(), F.conv2d(x2.float(), w2.float(), padding=1), atol=0.03, rtol=2e-2)
         assert s2 is not None
     finally:
-        conv.set_halo(False)
+        conv.set_halo(conv._HALO)            # back to the process default
         conv.set_mode("auto")
