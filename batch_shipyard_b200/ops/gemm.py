@@ -414,11 +414,16 @@ _HALO_BASE_MODE = int(os.environ.get("SHIPYARD_HALO_BASE_MODE", "0"))
 
 
 def conv3x3_halo(act: torch.Tensor, w: torch.Tensor, dgrad: bool = False, stats: Optional[torch.Tensor] = None, block_n: int = 0,
-                 pair: bool = False, base_mode: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+                 pair: bool = False, base_mode: Optional[int] = None, max_ctas: int = 0, epi_alt: bool = False,
+                 weights_stationary: bool = False) -> torch.Tensor:
     """3x3 / stride 1 / pad 1 convolution through the halo-load kernel (native/gemm/conv_halo.inc).
 
     fprop: ``act`` = x[N,Cin,H,W], ``w`` = W[Cout,Cin,3,3] -> y[N,Cout,H,W] (optionally the BN statistics of y in ``stats``);
-    dgrad: ``act`` = dY[N,Cout,H,W], same ``w`` -> dX[N,Cin,H,W].  channels_last bf16 in and out."""
+    dgrad: ``act`` = dY[N,Cout,H,W], same ``w`` -> dX[N,Cin,H,W].  channels_last bf16 in and out.
+
+    ``epi_alt`` (64 output channels, no pair: the two epilogue warpgroups take alternate tiles) and ``weights_stationary``
+    (pair, 128 output channels, 128 input channels, 28x28-class images: all 18 weight tiles stay in shared memory) select
+    variants written after the last GPU run of round 1 — compiled, reviewed, not yet validated on hardware; off by default."""
     n, ca, h, wd = act.shape
     cn = w.shape[1] if dgrad else w.shape[0]
     a_s, w_s = _nhwc_storage(act), _nhwc_storage(w)
@@ -426,7 +431,8 @@ def conv3x3_halo(act: torch.Tensor, w: torch.Tensor, dgrad: bool = False, stats:
     lib = load()
     rc = lib.sy_conv3x3_halo(C.c_void_p(a_s.data_ptr()), C.c_void_p(w_s.data_ptr()), C.c_void_p(y.data_ptr()), n, h, wd, ca, cn,
                              1 if dgrad else 0, C.c_void_p(stats.data_ptr() if stats is not None else 0), block_n, 1 if pair else 0,
-                             _HALO_BASE_MODE if base_mode is None else base_mode, max_ctas,
+                             (_HALO_BASE_MODE if base_mode is None else base_mode) | (2 if epi_alt else 0) | (4 if weights_stationary else 0),
+                             max_ctas,
                              C.c_void_p(torch.cuda.current_stream(act.device).cuda_stream))
     if rc != 0:
         raise RuntimeError(f"sy_conv3x3_halo failed ({rc}): {lib.sy_gemm_last_error().decode()}")

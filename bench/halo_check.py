@@ -91,6 +91,13 @@ def timing(mode: int) -> None:
         if gemm.halo_ok(n, hw, hw, cin, cout, 3, 3, 1, 1, pair=True):
             cands["fprop_th2"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, base_mode=mode)
             cands["dgrad_th2"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode)
+        if os.environ.get("SHIPYARD_TEST_UNVERIFIED"):          # round-2 candidates (not yet validated on hardware)
+            if cout == 64:
+                cands["fprop_th_alt"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, base_mode=mode, epi_alt=True)
+                cands["dgrad_th_alt"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, base_mode=mode, epi_alt=True)
+            if cout == 128 and hw == 28:
+                cands["fprop_th2_ws"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, base_mode=mode, weights_stationary=True)
+                cands["dgrad_th2_ws"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode, weights_stationary=True)
         for k, fn in cands.items():
             try:
                 us = t_us(fn)
