@@ -106,6 +106,10 @@ DEVI void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "m
 template <int N> DEVI void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 DEVI void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+DEVI void st_global_v4(void* p, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------
 template <int NCOLS> DEVI void tmem_alloc(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
@@ -225,11 +229,18 @@ template <int BN> struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false>
+// kDirect: the output tile leaves through coalesced 16-byte st.global from the staging buffer instead of a TMA store.  Reason
+// (profiles/conv_halo.md, "epilogue"): on the short-K GEMMs of ResNet (K = 64..512, one to eight k-blocks per tile) every 128x64
+// epilogue chunk costs 1.7-2 us although TMEM -> registers -> smem is ~0.3 us of work: the group's single staging buffer may
+// only be rewritten once the previous TMA store has READ it (`cp.async.bulk.wait_group.read 0`), and that store queues in the
+// SM's TMA unit behind the producer's loads for the next 4-6 stages.  Plain stores have no such dependency.
+// [written after the last GPU run of round 1: compiled and reviewed, selected only with SHIPYARD_GEMM_DIRECT_STORE=1]
+template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false, bool kDirect = false>
 __global__ void __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
-                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats, const ConvGeom geom) {
+                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ stats, const ConvGeom geom,
+                    __nv_bfloat16* __restrict__ c_ptr = nullptr, int ldc = 0) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -404,14 +415,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk, v[0]);
             tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk + 32, v[1]);
           }
-          if (issuer) tma_store_wait_read<0>();   // the previous TMA store of this group has finished reading cbuf
+          if constexpr (!kDirect) { if (issuer) tma_store_wait_read<0>(); }   // the previous TMA store of this group has finished reading cbuf
           named_bar_sync(bar_a, kEpiThreads);
 #pragma unroll
           for (int q = 0; q < 8; ++q)       // 128B swizzle: 16-byte chunk index XOR (row % 8) — matches the TMA store, bank-conflict free
             *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w[q];
-          fence_proxy_async_smem();
+          if constexpr (!kDirect) fence_proxy_async_smem();
           named_bar_sync(bar_b, kEpiThreads);
-          if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m_blk * BM); tma_store_commit(); }
+          if constexpr (kDirect) {          // thread (rr = et / 8, sub = et % 8): 16-byte piece `sub` of rows rr, rr + 16, ...: full 128 B lines per 8 lanes
+            const int sub = et & 7, rr = et >> 3;
+            if (n0 + sub * 8 < N) {
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {
+                const int r = p * 16 + rr;
+                if (m_blk * BM + r < M)
+                  st_global_v4(c_ptr + (size_t)(m_blk * BM + r) * (size_t)ldc + n0 + sub * 8,
+                               *reinterpret_cast<const uint4*>(cbuf + r * 128 + ((sub ^ (r & 7)) << 4)));
+              }
+            }
+          } else {
+            if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m_blk * BM); tma_store_commit(); }
+          }
           if (kStats) {
             const int wcol = et & 31, rgrp = et >> 5;
             const int q = wcol >> 2, wi = wcol & 3;
@@ -429,7 +453,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       flush_stats(cur_n);
-      if (issuer) tma_store_wait_all();
+      if constexpr (!kDirect) { if (issuer) tma_store_wait_all(); }
     }
   }
   tc_fence_before();
@@ -802,9 +826,6 @@ DEVI void grid_barrier(const CommDev& c) {          // all CTAs are co-resident 
   }
   __syncthreads();
 }
-DEVI void st_global_v4(void* p, const uint4& v) {
-  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 DEVI void mc_st_v4(void* mc, const uint4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -1063,10 +1084,11 @@ template <int BN> struct Cfg2 {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kCBytes + 1024 + 256;
 };
 
-template <int BN, bool kStats, bool kConv, bool kBMN = false>
+template <int BN, bool kStats, bool kConv, bool kBMN = false, bool kDirect = false>     // kDirect: see gemm_bf16_tn_kernel
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, float* __restrict__ stats, const ConvGeom geom) {
+                         const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, float* __restrict__ stats, const ConvGeom geom,
+                         __nv_bfloat16* __restrict__ c_ptr = nullptr, int ldc = 0) {
   using C = Cfg2<BN>;
   constexpr int BM2 = 2 * BM;
   extern __shared__ uint8_t smem_raw[];
@@ -1232,14 +1254,27 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk, v[0]);
             tmem_ld32(tbase + (c + kEpiGroups) * kEpiChunk + 32, v[1]);
           }
-          if (issuer) tma_store_wait_read<0>();
+          if constexpr (!kDirect) { if (issuer) tma_store_wait_read<0>(); }
           named_bar_sync(bar_a, kEpiThreads);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<uint4*>(cbuf + row * 128 + ((q ^ (row & 7)) << 4)) = w[q];
-          fence_proxy_async_smem();
+          if constexpr (!kDirect) fence_proxy_async_smem();
           named_bar_sync(bar_b, kEpiThreads);
-          if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m0); tma_store_commit(); }
+          if constexpr (kDirect) {
+            const int sub = et & 7, rr = et >> 3;
+            if (n0 + sub * 8 < N) {
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {
+                const int r = p * 16 + rr;
+                if (m0 + r < M)
+                  st_global_v4(c_ptr + (size_t)(m0 + r) * (size_t)ldc + n0 + sub * 8,
+                               *reinterpret_cast<const uint4*>(cbuf + r * 128 + ((sub ^ (r & 7)) << 4)));
+              }
+            }
+          } else {
+            if (issuer) { tma_store_2d(&tmap_c, cbuf, n0, m0); tma_store_commit(); }
+          }
           if (kStats) {
             const int wcol = et & 31, rgrp = et >> 5;
             const int q = wcol >> 2, wi = wcol & 3;
@@ -1257,7 +1292,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       flush_stats(cur_n);
-      if (issuer) tma_store_wait_all();
+      if constexpr (!kDirect) { if (issuer) tma_store_wait_all(); }
     }
   }
   tc_fence_before();
@@ -1279,6 +1314,14 @@ bool load_encode() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
   g_encode = (EncodeTiledFn)fn;
   return true;
+}
+
+// SHIPYARD_GEMM_DIRECT_STORE=1 selects the kDirect epilogue (st.global instead of TMA stores) in the TN / CTA-pair GEMM and
+// im2col convolution launches; off by default until it has been measured (round 2).
+bool direct_store() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SHIPYARD_GEMM_DIRECT_STORE"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return v == 1;
 }
 
 // 2D bf16 tensor map: dims {inner, outer}, row pitch `ld` elements, box {box_inner, box_outer}, 128B swizzle
@@ -1353,12 +1396,17 @@ int launch_conv(const void* act, const void* wgt, void* out, int Nb, int H, int 
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, stats, g);
+    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, stats, g, (__nv_bfloat16*)out, N);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
     return 0;
   };
+  if (direct_store() && N % 8 == 0) {
+    if (dgrad) return go(gemm_bf16_tn_kernel<BN, false, false, true, true, true>);
+    if (stats) return go(gemm_bf16_tn_kernel<BN, true, false, false, true, true>);
+    return go(gemm_bf16_tn_kernel<BN, false, false, false, true, true>);
+  }
   if (dgrad) return go(gemm_bf16_tn_kernel<BN, false, false, true, true>);
   if (stats) return go(gemm_bf16_tn_kernel<BN, true, false, false, true>);
   return go(gemm_bf16_tn_kernel<BN, false, false, false, true>);
@@ -1379,20 +1427,21 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats, ConvGeom{});
+    kern<<<grid, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)bias, stats, ConvGeom{}, (__nv_bfloat16*)Cc, ldc);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
     return 0;
   };
   if (stats && bias) { snprintf(g_err, sizeof g_err, "stats and bias cannot be combined"); return 2; }
+  const bool direct = direct_store() && N % 8 == 0;
   if (b_mn) {
     if (stats || bias) { snprintf(g_err, sizeof g_err, "MN-major B: no fused epilogue"); return 2; }
-    return go(gemm_bf16_tn_kernel<BN, false, false, true>);
+    return direct ? go(gemm_bf16_tn_kernel<BN, false, false, true, false, true>) : go(gemm_bf16_tn_kernel<BN, false, false, true>);
   }
-  if (stats) return go(gemm_bf16_tn_kernel<BN, true, false>);
+  if (stats) return direct ? go(gemm_bf16_tn_kernel<BN, true, false, false, false, true>) : go(gemm_bf16_tn_kernel<BN, true, false>);
   if (bias) return go(gemm_bf16_tn_kernel<BN, false, true>);
-  return go(gemm_bf16_tn_kernel<BN, false, false>);
+  return direct ? go(gemm_bf16_tn_kernel<BN, false, false, false, false, true>) : go(gemm_bf16_tn_kernel<BN, false, false>);
 }
 
 }  // namespace
@@ -1446,12 +1495,20 @@ int launch_2cta(bool conv, int bmode, const void* A, const void* B, void* Cc, in
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
-    kern<<<2 * pairs, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, stats, g);
+    kern<<<2 * pairs, kThreadsTN, C::kSmemBytes, s>>>(ta, tb, tc, M, N, K, stats, g, (__nv_bfloat16*)Cc, ldc);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
     g_launches.fetch_add(1);
     return 0;
   };
+  if (direct_store()) {            // N % block_n == 0 here, so every 16-byte piece is whole
+    if (bmode != 0) {
+      if (stats) { snprintf(g_err, sizeof g_err, "2-CTA dgrad: no fused statistics"); return 2; }
+      return conv ? go(gemm_bf16_tn_2cta_kernel<BN, false, true, true, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false, true, true>);
+    }
+    if (conv) return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, true, false, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, true, false, true>);
+    return stats ? go(gemm_bf16_tn_2cta_kernel<BN, true, false, false, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false, false, true>);
+  }
   if (bmode != 0) {
     if (stats) { snprintf(g_err, sizeof g_err, "2-CTA dgrad: no fused statistics"); return 2; }
     return conv ? go(gemm_bf16_tn_2cta_kernel<BN, false, true, true>) : go(gemm_bf16_tn_2cta_kernel<BN, false, false, true>);

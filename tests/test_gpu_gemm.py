@@ -267,3 +267,20 @@ def test_conv_dgrad_two_cta(n, c, h, w, k):
     dx = gemm.conv_dgrad_nhwc(dy, wt, k // 2, two_cta=True)
     ref = torch.nn.grad.conv2d_input((n, c, h, w), wt.float(), dy.float(), stride=1, padding=k // 2)
     torch.testing.assert_close(dx.float(), ref, atol=0.05, rtol=2e-2)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
+                    reason="st.global epilogue variants were written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1)")
+def test_direct_store_epilogue_variants_in_subprocess():
+    """SHIPYARD_GEMM_DIRECT_STORE=1 switches the TN / CTA-pair / im2col kernels to the st.global epilogue; the switch is read
+    once per process, so the numerics tests of this file are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SHIPYARD_GEMM_DIRECT_STORE="1")
+    env.pop("SHIPYARD_TEST_UNVERIFIED", None)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "matches_fp32 or bias_stats or two_cta or conv_implicit or nn_mn_major or conv1x1_and_linear"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
