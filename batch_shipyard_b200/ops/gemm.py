@@ -52,6 +52,7 @@ def load() -> C.CDLL:
         lib.sy_conv_bf16_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sy_conv3x3_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         lib.sy_conv3x3_halo_rows.argtypes = [C.c_int, C.c_int]
+        lib.sy_conv3x3_wgrad_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -437,6 +438,30 @@ def conv3x3_halo(act: torch.Tensor, w: torch.Tensor, dgrad: bool = False, stats:
     if rc != 0:
         raise RuntimeError(f"sy_conv3x3_halo failed ({rc}): {lib.sy_gemm_last_error().decode()}")
     return y.permute(0, 3, 1, 2)
+
+
+def conv3x3_wgrad_halo(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+                       splits: int = 0) -> torch.Tensor:
+    """dW[Cout,Cin,3,3] (stored KRSC) of a 3x3 / stride-1 / pad-1 convolution through the halo-load wgrad kernel
+    (native/gemm/wgrad_halo.inc): X and dY are read once per (64 ci, 64 co) block, the nine taps are row-shifted descriptors of one
+    X halo box.  NOT yet validated on hardware (written after the last GPU run of round 1); nothing selects it by default."""
+    n, cin, h, wd = x.shape
+    cout = dy.shape[1]
+    xs, dys = _nhwc_storage(x), _nhwc_storage(dy)
+    if out is None:
+        out = torch.empty((cout, 3, 3, cin), dtype=torch.bfloat16, device=x.device)
+        accumulate = False
+    assert out.is_contiguous() and tuple(out.shape) == (cout, 3, 3, cin) and out.dtype == torch.bfloat16
+    ws, tickets = _workspace(x.device)
+    if 9 * cin * cout > ws.numel() or (cin // 64) * (cout // 64) > tickets.numel():
+        raise RuntimeError("conv wgrad output exceeds the split-K workspace")
+    lib = load()
+    rc = lib.sy_conv3x3_wgrad_halo(C.c_void_p(xs.data_ptr()), C.c_void_p(dys.data_ptr()), C.c_void_p(out.data_ptr()), n, h, wd, cin, cout,
+                                   C.c_void_p(ws.data_ptr()), C.c_void_p(tickets.data_ptr()), 1 if accumulate else 0, splits,
+                                   C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_conv3x3_wgrad_halo failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out.permute(0, 3, 1, 2)
 
 
 def conv_two_cta_ok(n: int, p: int, q: int, c_out: int) -> bool:

@@ -91,7 +91,10 @@ def timing(mode: int) -> None:
         if gemm.halo_ok(n, hw, hw, cin, cout, 3, 3, 1, 1, pair=True):
             cands["fprop_th2"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, base_mode=mode)
             cands["dgrad_th2"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode)
+        cands["wgrad_cudnn"] = lambda: torch.ops.aten.convolution_backward(dy, x, wt, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
+        cands["wgrad_tc"] = lambda: gemm.conv_wgrad_nhwc(x, dy, wt.shape, 1, 1)
         if os.environ.get("SHIPYARD_TEST_UNVERIFIED"):          # round-2 candidates (not yet validated on hardware)
+            cands["wgrad_th"] = lambda: gemm.conv3x3_wgrad_halo(x, dy)
             if cout == 64:
                 cands["fprop_th_alt"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, base_mode=mode, epi_alt=True)
                 cands["dgrad_th_alt"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, base_mode=mode, epi_alt=True)

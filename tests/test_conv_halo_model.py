@@ -87,3 +87,55 @@ def test_halo_rows_and_shape_filter():
     assert gemm.halo_ok(256, 28, 28, 128, 128, 3, 3, 1, 1, pair=True)
     assert not gemm.halo_ok(256, 56, 56, 64, 64, 3, 3, 1, 1, pair=True)   # CTA pairs need out channels % 128
     assert not gemm.halo_ok(1, 7, 7, 512, 512, 3, 3, 1, 1, pair=True)     # odd number of M tiles
+
+
+def _wgrad_halo_model(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """x [N,H,W,Ci], dy [N,H,W,Co] -> dW [Co,3,3,Ci]; mirrors native/gemm/wgrad_halo.inc (one X halo box + one dY box in padded
+    row coordinates per tile, five tap-pair accumulators of 128 rows = (tap parity, ci), k-steps of 16 pixel rows)."""
+    n, h, wd, ci = x.shape
+    co = dy.shape[3]
+    rows = gemm.halo_rows(h, wd)
+    wp = wd + 2
+    a_rows, b_rows = (rows + 2) * wp, rows * wp
+    ksteps = (b_rows + 15) // 16
+    acc = torch.zeros((5, 2 * ci, co))                              # [tap pair][slab * ci + c][co]
+    for img in range(n):
+        for h0 in range(0, h, rows):
+            a = torch.zeros((256, ci))                               # rows past the box are zeroed once at kernel start
+            box = torch.zeros((rows + 2, wp, ci))
+            for bh in range(rows + 2):
+                for bw in range(wp):
+                    hh, ww = h0 - 1 + bh, bw - 1
+                    if 0 <= hh < h and 0 <= ww < wd:
+                        box[bh, bw] = x[img, hh, ww]
+            a[:a_rows] = box.reshape(-1, ci)
+            b = torch.zeros((128, co))
+            bbox = torch.zeros((rows, wp, co))                       # TMA box {co, Wp, R} at w = 0: columns W, W+1 are out of bounds -> 0
+            bbox[:, :wd] = dy[img, h0:h0 + rows]
+            b[:b_rows] = bbox.reshape(-1, co)
+            k = ksteps * 16
+            for p in range(5):
+                ta, tb = 2 * p, 2 * p + 1
+                sh_a = (ta // 3) * wp + ta % 3
+                sh_b = (tb // 3) * wp + tb % 3 if tb < 9 else sh_a + 1
+                assert sh_b + k <= 256 and sh_b > sh_a
+                slab = torch.cat([a[sh_a:sh_a + k], a[sh_b:sh_b + k]], dim=1)      # [k, 2*ci]: M index = slab * ci + c
+                acc[p] += slab.t() @ b[:k]
+    dw = torch.zeros((co, 9, ci))
+    for p in range(5):
+        for half in range(2):
+            tap = 2 * p + half
+            if tap < 9:                                              # the dummy partner of tap 8 is discarded
+                dw[:, tap, :] = acc[p, half * ci:(half + 1) * ci, :].t()
+    return dw.reshape(co, 3, 3, ci)
+
+
+@pytest.mark.parametrize("h,wd", [(7, 7), (14, 14), (28, 28), (56, 56), (12, 20)])
+def test_halo_wgrad_geometry_matches_conv(h, wd):
+    torch.manual_seed(h + wd)
+    n, ci, co = 2, 8, 6
+    x = torch.randn(n, ci, h, wd)
+    dy = torch.randn(n, co, h, wd)
+    ref = torch.nn.grad.conv2d_weight(x, (co, ci, 3, 3), dy, padding=1)          # [co, ci, 3, 3]
+    got = _wgrad_halo_model(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous())
+    assert torch.allclose(got.permute(0, 3, 1, 2), ref, atol=1e-3, rtol=1e-4)

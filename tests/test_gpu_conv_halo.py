@@ -101,3 +101,23 @@ def test_halo_unverified_variants(variant):
     dx = gemm.conv3x3_halo(dy, wt, dgrad=True, **kw)
     dref = torch.nn.grad.conv2d_input(x.shape, wt.float(), dy.float(), stride=1, padding=1)
     torch.testing.assert_close(dx.float(), dref, atol=0.05, rtol=2e-2)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
+                    reason="halo-load wgrad was written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1 to run it)")
+@pytest.mark.parametrize("n,cin,h,w,cout", [(4, 64, 56, 56, 64), (8, 128, 28, 28, 128), (8, 256, 14, 14, 128), (16, 128, 7, 7, 256), (6, 64, 12, 20, 64)])
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_halo_wgrad_unverified(n, cin, h, w, cout, splits):
+    from batch_shipyard_b200.ops import gemm
+    x, wt = _mk(n, cin, h, w, cout)
+    dy = (torch.randn(n, cout, h, w, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, dy.float(), padding=1)
+    tol = 0.02 * (n * h * w) ** 0.5 * 0.25 + 0.05
+    dw = gemm.conv3x3_wgrad_halo(x, dy, splits=splits)
+    torch.testing.assert_close(dw.float(), ref, atol=tol, rtol=3e-2)
+    base = torch.randn(cout, 3, 3, cin, device="cuda").to(torch.bfloat16)
+    buf = base.clone()
+    gemm.conv3x3_wgrad_halo(x, dy, out=buf, accumulate=True, splits=splits)
+    torch.testing.assert_close(buf.permute(0, 3, 1, 2).float(), ref + base.permute(0, 3, 1, 2).float(), atol=tol + 0.05, rtol=3e-2)
+    ws, tickets = gemm._workspace(x.device)
+    assert float(ws.abs().max()) == 0.0 and int(tickets.abs().max()) == 0
