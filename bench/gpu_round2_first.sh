@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU call of round 2 (1 GPU, ~6 minutes): everything that was written after the last GPU run of round 1.
+#   1. the gated tests (halo variants, halo wgrad, two-gradient BN model test, st.global epilogue variants)
+#   2. epilogue probe with and without SHIPYARD_GEMM_DIRECT_STORE
+#   3. halo timing table incl. the unverified variants (epi_alt, weights_stationary, wgrad_th)
+#   4. bench with the st.global epilogue
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+( time SHIPYARD_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_conv_halo.py tests/test_zz_gpu_bn_dual.py tests/test_gpu_gemm.py -q -m gpu \
+    -k "unverified or wgrad_unverified or residual_gradient_fusion or direct_store" ) > gpurun_out/r2_unverified_tests.log 2>&1
+tail -15 gpurun_out/r2_unverified_tests.log
+timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_tma.jsonl 2> gpurun_out/r2_epilogue_tma.err
+SHIPYARD_GEMM_DIRECT_STORE=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct.jsonl 2> gpurun_out/r2_epilogue_direct.err
+tail -3 gpurun_out/r2_epilogue_tma.jsonl gpurun_out/r2_epilogue_direct.jsonl
+SHIPYARD_TEST_UNVERIFIED=1 timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing.jsonl 2> gpurun_out/r2_halo_timing.err
+cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
+timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
+SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct.json 2> gpurun_out/r2_bench_direct.err
+cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json

@@ -51,7 +51,7 @@ def _halo_model(act: torch.Tensor, w: torch.Tensor, dgrad: bool) -> torch.Tensor
     return out
 
 
-@pytest.mark.parametrize("h,wd", [(7, 7), (14, 14), (28, 28), (56, 56), (6, 10)])
+@pytest.mark.parametrize("h,wd", [(7, 7), (14, 14), (28, 28), (56, 56), (6, 10), (16, 16), (4, 4), (8, 8), (32, 32), (2, 2)])
 @pytest.mark.parametrize("dgrad", [False, True])
 def test_halo_geometry_matches_conv(h, wd, dgrad):
     torch.manual_seed(h * 10 + dgrad)
