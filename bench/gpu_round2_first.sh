@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 ( time SHIPYARD_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_conv_halo.py tests/test_zz_gpu_bn_dual.py tests/test_gpu_gemm.py -q -m gpu \
-    -k "unverified or wgrad_unverified or residual_gradient_fusion or direct_store" ) > gpurun_out/r2_unverified_tests.log 2>&1
+    -k "unverified or wgrad_unverified or residual_gradient_fusion or direct_store or maxpool_bwd2" ) > gpurun_out/r2_unverified_tests.log 2>&1
 tail -15 gpurun_out/r2_unverified_tests.log
 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_tma.jsonl 2> gpurun_out/r2_epilogue_tma.err
 SHIPYARD_GEMM_DIRECT_STORE=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct.jsonl 2> gpurun_out/r2_epilogue_direct.err
@@ -16,4 +16,5 @@ SHIPYARD_TEST_UNVERIFIED=1 timeout 120 python bench/halo_check.py timing 0 > gpu
 cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct.json 2> gpurun_out/r2_bench_direct.err
-cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json
+SHIPYARD_MAXPOOL_BWD2=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_pool2.json 2> gpurun_out/r2_bench_pool2.err
+cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json gpurun_out/r2_bench_pool2.json

@@ -514,6 +514,65 @@ k_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ 
   }
 }
 
+// Variant: one thread per 2x2 block of input pixels (and 8 channels).  The four pixels (2a..2a+1, 2b..2b+1) are covered by the same
+// four pooling windows (oy in {a, a+1}, ox in {b, b+1}), so each window's gradient vector and arg-max codes are loaded once per
+// thread instead of once per pixel (96 B of loads per 64 B stored instead of 216 B) and every thread has four independent 16-byte
+// stores in flight.  ncu (profiles/step_breakdown.md) has the per-pixel kernel at 494 us for the 411 MB stem gradient, 5x the HBM time.
+// [written after the last GPU run of round 1: selected with SHIPYARD_MAXPOOL_BWD2=1, even H and W only]
+__global__ void __launch_bounds__(256)
+k_maxpool_bwd2(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
+               int N, int H, int W, int C, int OH, int OW) {
+  const int G = C / 8, H2 = H / 2, W2 = W / 2;
+  const long total = (long)N * H2 * W2 * G;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G); long p = t / G;
+    const int b = (int)(p % W2); p /= W2;
+    const int a = (int)(p % H2); const int n = (int)(p / H2);
+    float acc[2][2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][j][c] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy) {
+      const int oy = a + wy;
+      if (oy >= OH) continue;
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int ox = b + wx;
+        if (ox >= OW) continue;
+        const long o = (((long)n * OH + oy) * OW + ox) * C + g * 8;
+        const uint2 c2 = *reinterpret_cast<const uint2*>(idx + o);
+        float d[8]; unpack8(ldg16(dy + o), d);
+        // window (oy, ox) covers input rows 2*oy-1 .. 2*oy+1: of this block's rows 2a, 2a+1 that is ky = 1, 2 (wy = 0) or ky = -, 0 (wy = 1)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int ky = 2 * a + i - (2 * oy - 1);
+          if (ky < 0 || ky > 2) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int kx = 2 * b + j - (2 * ox - 1);
+            if (kx < 0 || kx > 2) continue;
+            const uint32_t want = (uint32_t)(ky * 3 + kx);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t code = ((c < 4 ? c2.x : c2.y) >> (8 * (c & 3))) & 0xff;
+              if (code == want) acc[i][j][c] += d[c];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        stg16(dx + (((long)n * H + 2 * a + i) * W + 2 * b + j) * C + g * 8, pack8(acc[i][j]));
+  }
+}
+
 extern "C" int sy_ops_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
   if (C % 8) return -1;
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
@@ -526,6 +585,15 @@ extern "C" int sy_ops_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N,
 extern "C" int sy_ops_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
   if (C % 8) return -1;
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  static int bwd2 = -1;
+  if (bwd2 < 0) { const char* e = getenv("SHIPYARD_MAXPOOL_BWD2"); bwd2 = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  if (bwd2 && H % 2 == 0 && W % 2 == 0) {
+    const long total2 = (long)N * (H / 2) * (W / 2) * (C / 8);
+    const int blocks2 = (int)((total2 + 255) / 256 < 148 * 16 ? (total2 + 255) / 256 : 148 * 16);
+    k_maxpool_bwd2<<<blocks2, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, OH, OW);
+    COUNT_LAUNCH();
+    RET_LAST();
+  }
   long total = (long)N * H * W * (C / 8);
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   k_maxpool_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, OH, OW);

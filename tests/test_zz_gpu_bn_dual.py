@@ -72,3 +72,28 @@ def test_resnet_residual_gradient_fusion_matches_unfused():
     assert abs(grads[True][0] - grads[False][0]) < 1e-3 * max(1.0, abs(grads[False][0]))
     a, b = grads[True][1], grads[False][1]
     assert float((a - b).norm()) <= 0.03 * float(b.norm()) + 1e-6, (float((a - b).norm()), float(b.norm()))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
+                    reason="2x2-block max-pool backward was written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1)")
+def test_maxpool_bwd2_variant_in_subprocess():
+    """SHIPYARD_MAXPOOL_BWD2=1 (read once per process by the library) must reproduce the per-pixel kernel's gradient exactly."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from batch_shipyard_b200.ops import fused\n"
+        "import torch.nn.functional as F\n"
+        "torch.manual_seed(0)\n"
+        "for shape in [(3, 64, 24, 30), (8, 64, 112, 112), (2, 16, 6, 4)]:\n"
+        "    x = torch.randn(*shape, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)\n"
+        "    y = fused.maxpool3x3s2(x); g = torch.randn_like(y); y.backward(g)\n"
+        "    xr = x.detach().float().requires_grad_(True); yr = F.max_pool2d(xr, 3, 2, 1); yr.backward(g.float())\n"
+        "    assert torch.equal(y.float(), yr)\n"
+        "    torch.testing.assert_close(x.grad.float(), xr.grad, atol=2e-2, rtol=2e-2)\n"
+        "print('bwd2 ok')\n") % root
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SHIPYARD_MAXPOOL_BWD2="1"), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and "bwd2 ok" in p.stdout, p.stdout[-3000:]
