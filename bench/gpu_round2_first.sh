@@ -14,6 +14,7 @@ SHIPYARD_GEMM_DIRECT_STORE=1 timeout 120 python bench/gemm_epilogue_probe.py > g
 tail -3 gpurun_out/r2_epilogue_tma.jsonl gpurun_out/r2_epilogue_direct.jsonl
 SHIPYARD_TEST_UNVERIFIED=1 timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing.jsonl 2> gpurun_out/r2_halo_timing.err
 cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
+timeout 240 python bench/torch_kernel_census.py > gpurun_out/r2_kernel_census.txt 2> gpurun_out/r2_kernel_census.err; head -60 gpurun_out/r2_kernel_census.txt
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct.json 2> gpurun_out/r2_bench_direct.err
 SHIPYARD_MAXPOOL_BWD2=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_pool2.json 2> gpurun_out/r2_bench_pool2.err
