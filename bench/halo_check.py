@@ -98,6 +98,8 @@ def timing(mode: int) -> None:
             if cout == 64:
                 cands["fprop_th_alt"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, base_mode=mode, epi_alt=True)
                 cands["dgrad_th_alt"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, base_mode=mode, epi_alt=True)
+                cands["fprop_th2_64"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, block_n=64, base_mode=mode)
+                cands["fprop_th2_64_alt"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, block_n=64, base_mode=mode, epi_alt=True)
             if cout == 128 and hw == 28:
                 cands["fprop_th2_ws"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, base_mode=mode, weights_stationary=True)
                 cands["dgrad_th2_ws"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode, weights_stationary=True)

@@ -81,12 +81,14 @@ def test_halo_in_dispatcher_matches_library():
 
 @pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
                     reason="variants written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1 to run them)")
-@pytest.mark.parametrize("variant", ["epi_alt", "weights_stationary"])
+@pytest.mark.parametrize("variant", ["epi_alt", "weights_stationary", "pair64", "pair64_alt"])
 def test_halo_unverified_variants(variant):
     """Alternate-tile epilogue (BN = 64) and all-weights-stationary CTA pairs (128 channels, 28x28): same numerics as the base kernels."""
     from batch_shipyard_b200.ops import gemm
     if variant == "epi_alt":
         n, cin, h, w, cout, kw = 8, 64, 56, 56, 64, dict(epi_alt=True)
+    elif variant.startswith("pair64"):                   # 64-column CTA pairs (fprop only)
+        n, cin, h, w, cout, kw = 8, 64, 56, 56, 64, dict(pair=True, block_n=64, epi_alt=variant.endswith("alt"))
     else:
         n, cin, h, w, cout, kw = 8, 128, 28, 28, 128, dict(pair=True, weights_stationary=True)
     x, wt = _mk(n, cin, h, w, cout)
@@ -97,6 +99,8 @@ def test_halo_unverified_variants(variant):
     torch.testing.assert_close(stats[:cout], y.float().sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
     torch.testing.assert_close(stats[cout:], (y.float() ** 2).sum(dim=(0, 2, 3)), atol=0.5, rtol=5e-3)
     assert torch.equal(gemm.conv3x3_halo(x, wt, **kw), y)
+    if variant.startswith("pair64"):
+        return
     dy = (torch.randn_like(ref) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     dx = gemm.conv3x3_halo(dy, wt, dgrad=True, **kw)
     dref = torch.nn.grad.conv2d_input(x.shape, wt.float(), dy.float(), stride=1, padding=1)
