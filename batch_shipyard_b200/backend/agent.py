@@ -21,7 +21,6 @@ import time
 import uuid
 from typing import Optional
 
-from ..config import settings as S
 from ..state.store import NotFound
 from .local import BackendError, LocalBackend, _now
 from . import runspec

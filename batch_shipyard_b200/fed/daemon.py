@@ -21,7 +21,6 @@ import uuid
 
 from ..backend.agent import spawn_detached_agent
 from ..backend.local import BackendError, LocalBackend
-from . import client as FCl
 from . import constraints as FC
 from .scheduler import select_pool
 

@@ -11,7 +11,6 @@ JSON-able value; the CLI prints it (``--raw`` = JSON, otherwise a readable form)
 """
 from __future__ import annotations
 
-import json
 import os
 import shutil
 import subprocess
@@ -24,7 +23,7 @@ from . import __version__
 from .backend.agent import NodeAgent, spawn_detached_agent
 from .backend.local import BackendError, LocalBackend
 from .config import settings as S
-from .state.store import Store, default_state_dir, entity_names
+from .state.store import default_state_dir, entity_names
 from .utils import util
 
 logger = util.get_logger()

@@ -16,7 +16,7 @@ import datetime
 import time
 from typing import Optional
 
-from ..backend.local import BackendError, LocalBackend
+from ..backend.local import LocalBackend
 from ..config import settings as S
 from ..utils import util
 from . import builder as B

@@ -16,7 +16,6 @@ import sys
 import time
 
 from ..config import settings as S
-from . import exporter
 
 
 def _dir(b) -> str:

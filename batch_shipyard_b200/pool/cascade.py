@@ -26,7 +26,6 @@ import threading
 import time
 from typing import Callable, Optional
 
-from ..config import settings as S
 from ..state.store import Store
 
 TRANSIENT_ERRORS = ("toomanyrequests", "connection reset by peer", "error pulling image configuration",

@@ -21,7 +21,7 @@ import subprocess
 import time
 from typing import Optional
 
-from ..backend.local import MAX_REBOOT_RETRIES, BackendError, LocalBackend
+from ..backend.local import MAX_REBOOT_RETRIES, LocalBackend
 from ..config import settings as S
 from ..utils import util
 from . import cascade as C

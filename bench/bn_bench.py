@@ -5,7 +5,6 @@ Cold timing: a ring of buffer sets larger than 2x L2 is rotated so no call sees 
 Bytes counted: fwd = x read twice (stats + apply) [+res] + out write + mask; bwd = (dout + x) read twice + dx [+dres] + mask x2.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import sys

@@ -56,10 +56,8 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   if (!c->hub) { delete c; return SY_ERR_SYS; }
   int rc;
   if (transport == SY_TRANSPORT_STUB) {
-    static uint32_t dummy_status;  // stub has no mapped status word
     rc = stub_init(c);
-    c->status_host = (uint32_t*)calloc(1, sizeof(uint32_t));
-    (void)dummy_status;
+    c->status_host = (uint32_t*)calloc(1, sizeof(uint32_t));   // the stub has no mapped status word: a private one
   } else {
     rc = gpu_init(c, transport);
   }

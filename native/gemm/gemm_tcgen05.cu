@@ -849,7 +849,6 @@ gemm_bf16_tn_rsag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN, num_k = (K + BK - 1) / BK;
-  const int num_tiles = num_m * num_n;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b);
     for (int p = 0; p < comm.world; ++p) tma_prefetch_desc(&inbox_maps.m[p]);

@@ -1,5 +1,4 @@
 import copy
-import os
 
 from batch_shipyard_b200.backend.agent import NodeAgent
 from batch_shipyard_b200.backend.local import LocalBackend

@@ -5,7 +5,7 @@ Q10 (vestigial torrent containers) have no counterpart to test against (there is
 import copy
 import subprocess
 
-from _helpers import make, up, run, read
+from _helpers import make, up
 
 from batch_shipyard_b200.config import settings as S
 from batch_shipyard_b200.jobs import builder, mpi as M

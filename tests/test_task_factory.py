@@ -2,7 +2,6 @@
 import sys
 import types
 
-import pytest
 
 from batch_shipyard_b200.jobs import task_factory as tf
 
