@@ -35,14 +35,27 @@ class CliContext:
         self.configdir: Optional[str] = None
         self.paths: dict = {}
         self.ctx: Optional[fleet.Context] = None
-        # accepted for compatibility with the reference's cloud flags; unused locally
+        # the reference's cloud flags: recorded; only keyvault-credentials-secret-id has a local meaning (see init)
         self.compat: dict = {}
 
     def init(self, required: tuple = (), skip: tuple = ()) -> fleet.Context:
         util.setup_logger("shipyard", self.verbose)
+        # --keyvault-credentials-secret-id: the credentials section comes from the (local) key vault instead of credentials.yaml
+        # (/root/reference/shipyard.py:441-575 fetches it from Azure KeyVault at the same point)
+        vault_id = self.compat.get("keyvault-credentials-secret-id")
+        if vault_id:
+            required = tuple(k for k in required if k != ConfigType.Credentials)
+            skip = tuple(skip) + (ConfigType.Credentials,)
         try:
             config = loader.load_configs(self.paths, self.configdir, required=required, skip=skip, verbose=self.verbose,
                                          auto_confirm=self.yes, raw=self.raw)
+            if vault_id:
+                from . import keyvault
+                try:
+                    creds = keyvault.fetch_credentials(fleet.resolve_state_dir(config), vault_id)
+                except KeyError as e:
+                    raise loader.ConfigError(str(e).strip("'\"")) from e
+                config = util.merge_dict(creds if "credentials" in (creds or {}) else {"credentials": creds or {}}, config)
         except loader.ConfigError as e:
             click.echo(f"ERROR: {e}", err=True)
             sys.exit(1)

@@ -220,3 +220,27 @@ def test_generated_docs_are_current():
     cfg = open(os.path.join(root, "docs", "configuration.md")).read()
     for section in ("config.yaml", "credentials.yaml", "pool.yaml", "jobs.yaml", "fs.yaml", "federation.yaml", "monitor.yaml", "slurm.yaml"):
         assert f"## {section}" in cfg
+
+
+def test_credentials_from_local_keyvault(tmp_path, monkeypatch):
+    """`keyvault add` stores the credentials section; `--keyvault-credentials-secret-id` then replaces credentials.yaml."""
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "credentials.yaml").write_text("credentials:\n  storage:\n    acct: {account: local}\n")
+    (cfg / "config.yaml").write_text("batch_shipyard: {storage_account_settings: acct}\nglobal_resources: {docker_images: [busybox]}\n")
+    (cfg / "pool.yaml").write_text("pool_specification: {id: kv, vm_size: STANDARD_D2_V2, vm_count: {dedicated: 1, low_priority: 0}}\n")
+    r = CliRunner()
+    res = r.invoke(cli.cli, ["keyvault", "add", "mycreds", "--configdir", str(cfg), "--raw"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    assert "mycreds" in r.invoke(cli.cli, ["keyvault", "list", "--raw"], obj=cli.CliContext()).output
+    (cfg / "credentials.yaml").unlink()                               # from here on the vault is the only source of credentials
+    res = r.invoke(cli.cli, ["pool", "list", "--configdir", str(cfg), "--raw", "--show-config"], obj=cli.CliContext())
+    assert res.exit_code == 0 and "acct: {" not in res.output and "account: local" not in res.output   # no credentials anywhere now
+    res = r.invoke(cli.cli, ["pool", "list", "--configdir", str(cfg), "--raw", "--keyvault-credentials-secret-id", "mycreds"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    res = r.invoke(cli.cli, ["pool", "list", "--configdir", str(cfg), "--raw", "--keyvault-credentials-secret-id", "https://local.vault/secrets/mycreds",
+                             "--show-config"], obj=cli.CliContext())
+    assert res.exit_code == 0 and "account: local" in res.output       # the merged config really contains the vault's credentials
+    res = r.invoke(cli.cli, ["pool", "list", "--configdir", str(cfg), "--keyvault-credentials-secret-id", "nope"], obj=cli.CliContext())
+    assert res.exit_code == 1 and "not found" in res.output
