@@ -25,6 +25,12 @@ from . import gemm as _gemm
 _MODE = os.environ.get("SHIPYARD_CONV_IMPL", "auto").lower()
 _PLANS: dict = {}
 _HALO = os.environ.get("SHIPYARD_CONV_HALO", "1") not in ("0", "", "off", "false")
+# SHIPYARD_CONV_EXPERIMENTAL=1 adds the kernel variants that were written after the last GPU run of round 1 (NEXT.md) to the race:
+# every one of them must first reproduce the cuDNN result of the same call (_halo_check), exactly like the validated halo kernels.
+_EXP = os.environ.get("SHIPYARD_CONV_EXPERIMENTAL", "0") not in ("0", "", "off", "false")
+# impl name -> keyword arguments of ops.gemm.conv3x3_halo
+_HALO_KW = {"th": {}, "th2": {"pair": True}, "tha": {"epi_alt": True}, "th264": {"pair": True, "block_n": 64},
+            "th264a": {"pair": True, "block_n": 64, "epi_alt": True}, "th2w": {"pair": True, "weights_stationary": True}}
 _HALO_STATE = {"enabled": _HALO, "checked": 0, "failed": []}
 _HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics pass (profiles/ncu_bn_kernels.md)
 
@@ -32,6 +38,7 @@ _HBM_BPS = 5.4e12          # measured bandwidth of the stand-alone BN statistics
 @dataclass
 class ConvPlan:
     fprop: str = "cudnn"      # "tc" (1-CTA tcgen05 im2col) | "tc2" (CTA pair) | "th" (halo load) | "th2" (halo, CTA pair) | "cudnn"
+    #                           experimental (SHIPYARD_CONV_EXPERIMENTAL): "tha" | "th264" | "th264a" | "th2w" (see _HALO_KW); wgrad "th"
     dgrad: str = "cudnn"
     wgrad: str = "cudnn"
     stats: bool = False       # fprop produces the BatchNorm statistics in its epilogue
@@ -115,8 +122,8 @@ def _time(fn, iters: int = 5, reps: int = 4) -> float:
 
 # ---- the individual passes ---------------------------------------------------------------------------------------------
 def _fprop_tc(x, w, stride, pad, stats, two_cta=False, impl=None):
-    if impl in ("th", "th2"):
-        return _gemm.conv3x3_halo(x, w, False, stats=stats, pair=impl == "th2")
+    if impl in _HALO_KW:
+        return _gemm.conv3x3_halo(x, w, False, stats=stats, **_HALO_KW[impl])
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -126,8 +133,8 @@ def _fprop_tc(x, w, stride, pad, stats, two_cta=False, impl=None):
 
 
 def _dgrad_tc(dy, x, w, stride, pad, two_cta=False, impl=None):
-    if impl in ("th", "th2"):
-        return _gemm.conv3x3_halo(dy, w, True, pair=impl == "th2")
+    if impl in _HALO_KW:
+        return _gemm.conv3x3_halo(dy, w, True, **_HALO_KW[impl])
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -161,6 +168,30 @@ def _halo_caps(x, w, stride) -> dict:
             "dgrad2": pair and _gemm.halo_ok(*a, cout, cin, k, k, stride, k // 2, pair=True, dgrad=True)}
 
 
+def experimental_impls(n: int, cin: int, h: int, wd: int, cout: int, k: int, stride: int) -> dict:
+    """Not-yet-validated kernel variants that apply to a layer shape, per pass (pure function of the shape: testable on CPU).
+    fprop / dgrad values are keys of ``_HALO_KW``; wgrad "th" is the halo-load wgrad kernel."""
+    out = {"fprop": [], "dgrad": [], "wgrad": []}
+    if (k, stride) != (3, 1) or cin % 64 or cout % 64:
+        return out
+    rows = _gemm.halo_rows(h, wd)
+    if rows == 0:
+        return out
+    even_tiles = (n * (h // rows)) % 2 == 0
+    small_box = (rows + 2) * (wd + 2) <= 184                 # fits the 23 KB halo slots of the weights-stationary pair kernel
+    if cout == 64:                                           # BN = 64 tiles: one epilogue chunk per tile
+        out["fprop"].append("tha")
+        if even_tiles:
+            out["fprop"] += ["th264", "th264a"]
+    if cin == 64:                                            # dgrad writes cin channels
+        out["dgrad"].append("tha")
+    if cin == 128 and cout == 128 and even_tiles and small_box:
+        out["fprop"].append("th2w")
+        out["dgrad"].append("th2w")
+    out["wgrad"].append("th")
+    return out
+
+
 def _close(a: torch.Tensor, ref: torch.Tensor) -> bool:
     a, ref = a.float(), ref.float()
     return bool(torch.isfinite(a).all()) and float((a - ref).abs().max()) <= 0.02 * float(ref.abs().max()) + 1e-3
@@ -176,9 +207,14 @@ def _halo_check(tag: str, key, got: torch.Tensor, ref: torch.Tensor) -> bool:
     return False
 
 
-def _wgrad_tc(dy, x, w, stride, pad, out_view, accumulate):
+def _wgrad_tc(dy, x, w, stride, pad, out_view, accumulate, impl=None):
     """out_view: KRSC-dense [Cout,R,S,Cin] destination (the parameter's flat .grad) or None."""
     cout, cin, k, _ = w.shape
+    if impl == "th":                                         # halo-load wgrad (experimental)
+        if out_view is not None:
+            _gemm.conv3x3_wgrad_halo(x, dy, out=out_view, accumulate=accumulate)
+            return None
+        return _gemm.conv3x3_wgrad_halo(x, dy)
     if k == 1 and stride == 1:
         n, _, h, wd = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(n * h * wd, cin)
@@ -248,6 +284,12 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
                     t[f"fprop_{impl}_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st, impl=impl))
                     t[f"fprop_{impl}"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None, impl=impl)) + t_stats_pass
                     cands += [f"fprop_{impl}_stats", f"fprop_{impl}"]
+            exp = experimental_impls(*_key(x, w, stride)[:4], cout, k, stride) if (_EXP and _HALO_STATE["enabled"]) else {"fprop": [], "dgrad": [], "wgrad": []}
+            for impl in exp["fprop"]:
+                if _HALO_STATE["enabled"] and _halo_check("fprop_" + impl, _key(x, w, stride), _fprop_tc(xd, wd_, stride, pad, None, impl=impl), y):
+                    t[f"fprop_{impl}_stats"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, st, impl=impl))
+                    t[f"fprop_{impl}"] = _time(lambda: _fprop_tc(xd, wd_, stride, pad, None, impl=impl)) + t_stats_pass
+                    cands += [f"fprop_{impl}_stats", f"fprop_{impl}"]
             best = min(cands, key=lambda k_: t[k_])
             plan.fprop = best.split("_")[1]
             plan.stats = best.endswith("_stats")
@@ -262,6 +304,13 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
                 for impl, cap in (("th", "dgrad"), ("th2", "dgrad2")):
                     if hc[cap] and _HALO_STATE["enabled"] and _halo_check("dgrad_" + impl, _key(x, w, stride), _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl), dx_ref):
                         t[f"dgrad_{impl}"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl))
+            if _EXP and _HALO_STATE["enabled"]:
+                exp_d = experimental_impls(*_key(x, w, stride)[:4], cout, k, stride)["dgrad"]
+                if exp_d:
+                    dx_ref = _cudnn_bwd(dy, xd, wd_, stride, pad, True, False)[0]
+                for impl in exp_d:
+                    if _HALO_STATE["enabled"] and _halo_check("dgrad_" + impl, _key(x, w, stride), _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl), dx_ref):
+                        t[f"dgrad_{impl}"] = _time(lambda: _dgrad_tc(dy, xd, wd_, stride, pad, impl=impl))
             best = min([k_ for k_ in t if k_.startswith("dgrad_")], key=lambda k_: t[k_])
             plan.dgrad = best.split("_")[1]
         t_accum = w.numel() * 6 / 4e12 * 1e6 + 3.0                     # AccumulateGrad add the library path pays
@@ -269,7 +318,12 @@ def _autotune(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
         if caps["wgrad"]:
             buf = torch.zeros((cout, k, k, cin), dtype=torch.bfloat16, device=x.device)
             t["wgrad_tc"] = _time(lambda: _wgrad_tc(dy, xd, wd_, stride, pad, buf, True))
-            plan.wgrad = "tc" if t["wgrad_tc"] < t["wgrad_cudnn"] else "cudnn"
+            if _EXP and _HALO_STATE["enabled"] and "th" in experimental_impls(*_key(x, w, stride)[:4], cout, k, stride)["wgrad"]:
+                dw_ref = _cudnn_bwd(dy, xd, wd_, stride, pad, False, True)[1]
+                if _halo_check("wgrad_th", _key(x, w, stride), _wgrad_tc(dy, xd, wd_, stride, pad, None, False, impl="th"), dw_ref):
+                    buf.zero_()
+                    t["wgrad_th"] = _time(lambda: _wgrad_tc(dy, xd, wd_, stride, pad, buf, True, impl="th"))
+            plan.wgrad = min([k_ for k_ in t if k_.startswith("wgrad_")], key=lambda k_: t[k_]).split("_")[1]
     plan.timings_us = {k_: round(v, 1) for k_, v in t.items()}
     return plan
 
@@ -311,13 +365,14 @@ class _Conv(torch.autograd.Function):
         dx = dw = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         lib_dx = need_dx and plan.dgrad == "cudnn"
-        lib_dw = need_dw and plan.wgrad != "tc"
+        lib_dw = need_dw and plan.wgrad == "cudnn"
         if lib_dx or lib_dw:
             dx, dw = _cudnn_bwd(dy, x, w, stride, pad, lib_dx, lib_dw)
         if need_dx and plan.dgrad != "cudnn":
             dx = _dgrad_tc(dy, x, w, stride, pad, plan.dgrad == "tc2", impl=plan.dgrad)
-        if need_dw and plan.wgrad == "tc":
-            dw = _wgrad_tc(dy, x, w, stride, pad, _grad_view(ctx.w_ref), True)     # None when written into .grad in place
+        if need_dw and plan.wgrad != "cudnn":
+            dw = _wgrad_tc(dy, x, w, stride, pad, _grad_view(ctx.w_ref), True,      # None when written into .grad in place
+                           impl=plan.wgrad if plan.wgrad != "tc" else None)
         return dx, dw, None, None
 
 

@@ -222,7 +222,7 @@ def _conv_summary():
         for pas in ("fprop", "dgrad", "wgrad"):
             out[pas + "_tc"] = sum(1 for v in tab.values() if v[pas] != "cudnn")
             out[pas + "_tc_2cta"] = sum(1 for v in tab.values() if v[pas] in ("tc2", "th2"))
-            out[pas + "_halo"] = sum(1 for v in tab.values() if v[pas] in ("th", "th2"))
+            out[pas + "_halo"] = sum(1 for v in tab.values() if v[pas].startswith("th"))
         out["fprop_fused_bn_stats"] = sum(1 for v in tab.values() if v["stats"])
         out["halo"] = _conv.halo_state()
         if os.environ.get("SHIPYARD_CONV_PLAN_DUMP"):

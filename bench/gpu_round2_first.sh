@@ -17,5 +17,7 @@ cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
 timeout 240 python bench/torch_kernel_census.py > gpurun_out/r2_kernel_census.txt 2> gpurun_out/r2_kernel_census.err; head -60 gpurun_out/r2_kernel_census.txt
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct.json 2> gpurun_out/r2_bench_direct.err
+SHIPYARD_CONV_EXPERIMENTAL=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_experimental.json 2> gpurun_out/r2_bench_experimental.err
+cp gpurun_out/conv_plan.json gpurun_out/r2_conv_plan_experimental.json 2>/dev/null; cat gpurun_out/r2_bench_experimental.json
 SHIPYARD_MAXPOOL_BWD2=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_pool2.json 2> gpurun_out/r2_bench_pool2.err
 cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json gpurun_out/r2_bench_pool2.json

@@ -49,3 +49,17 @@ def test_halo_candidates_are_gated_and_self_checked():
     finally:
         conv.set_halo(conv._HALO)            # back to the process default (SHIPYARD_CONV_HALO, on unless set to 0)
     assert conv.halo_state() == {"enabled": conv._HALO, "checked": 0, "failed": []}
+
+
+def test_experimental_variant_table():
+    """Which not-yet-validated kernel variants SHIPYARD_CONV_EXPERIMENTAL=1 would add per ResNet-50 layer shape (pure shape logic)."""
+    e = conv.experimental_impls
+    assert e(256, 64, 56, 56, 64, 3, 1) == {"fprop": ["tha", "th264", "th264a"], "dgrad": ["tha"], "wgrad": ["th"]}
+    assert e(256, 128, 28, 28, 128, 3, 1) == {"fprop": ["th2w"], "dgrad": ["th2w"], "wgrad": ["th"]}
+    assert e(256, 256, 14, 14, 256, 3, 1) == {"fprop": [], "dgrad": [], "wgrad": ["th"]}
+    assert e(256, 512, 7, 7, 512, 3, 1) == {"fprop": [], "dgrad": [], "wgrad": ["th"]}
+    assert e(256, 128, 56, 56, 128, 3, 2) == {"fprop": [], "dgrad": [], "wgrad": []}          # stride 2: not a halo shape
+    assert e(256, 64, 56, 56, 256, 1, 1) == {"fprop": [], "dgrad": [], "wgrad": []}           # 1x1
+    assert e(256, 128, 56, 56, 128, 3, 1)["fprop"] == []                                     # 56x56 box does not fit the 23 KB slots
+    assert set(conv._HALO_KW) >= {"th", "th2", "tha", "th264", "th264a", "th2w"}
+    assert not conv._EXP                                                                     # off unless the environment asks for it
