@@ -4,6 +4,7 @@ Times the ResNet-50 1x1 layers as plain GEMMs (M = 256*H*W pixels, N = Cout, K =
 reports device time, achieved HBM bandwidth and the implied cost per 128x64 epilogue chunk per warpgroup.  Run it twice:
     python bench/gemm_epilogue_probe.py                                  (TMA-store epilogue)
     SHIPYARD_GEMM_DIRECT_STORE=1 python bench/gemm_epilogue_probe.py     (st.global epilogue, kDirect)
+    SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1 python bench/gemm_epilogue_probe.py   (+ alternate-tile epilogue on 64-column tiles)
 The switch is read once per process by the library, hence two processes.  cuBLAS (torch.matmul) is the reference column.
 """
 import json
@@ -33,7 +34,7 @@ def t_us(fn, iters=30):
 
 
 def main():
-    direct = os.environ.get("SHIPYARD_GEMM_DIRECT_STORE", "0")
+    direct = os.environ.get("SHIPYARD_GEMM_DIRECT_STORE", "0") + ("+alt" if os.environ.get("SHIPYARD_GEMM_EPI_ALT") else "")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     for hw, k, n in SHAPES:
         m = 256 * hw * hw

@@ -11,7 +11,8 @@ cd "$(dirname "$0")/.."
 tail -15 gpurun_out/r2_unverified_tests.log
 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_tma.jsonl 2> gpurun_out/r2_epilogue_tma.err
 SHIPYARD_GEMM_DIRECT_STORE=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct.jsonl 2> gpurun_out/r2_epilogue_direct.err
-tail -3 gpurun_out/r2_epilogue_tma.jsonl gpurun_out/r2_epilogue_direct.jsonl
+SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct_alt.jsonl 2> gpurun_out/r2_epilogue_direct_alt.err
+tail -3 gpurun_out/r2_epilogue_tma.jsonl gpurun_out/r2_epilogue_direct.jsonl gpurun_out/r2_epilogue_direct_alt.jsonl
 SHIPYARD_TEST_UNVERIFIED=1 timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing.jsonl 2> gpurun_out/r2_halo_timing.err
 cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
 timeout 240 python bench/torch_kernel_census.py > gpurun_out/r2_kernel_census.txt 2> gpurun_out/r2_kernel_census.err; head -60 gpurun_out/r2_kernel_census.txt
@@ -20,4 +21,5 @@ SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.
 SHIPYARD_CONV_EXPERIMENTAL=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_experimental.json 2> gpurun_out/r2_bench_experimental.err
 cp gpurun_out/conv_plan.json gpurun_out/r2_conv_plan_experimental.json 2>/dev/null; cat gpurun_out/r2_bench_experimental.json
 SHIPYARD_MAXPOOL_BWD2=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_pool2.json 2> gpurun_out/r2_bench_pool2.err
-cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json gpurun_out/r2_bench_pool2.json
+SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct_alt.json 2> gpurun_out/r2_bench_direct_alt.err
+cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_direct.json gpurun_out/r2_bench_direct_alt.json gpurun_out/r2_bench_pool2.json

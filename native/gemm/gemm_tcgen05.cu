@@ -235,7 +235,10 @@ template <int BN> struct Cfg {
 // only be rewritten once the previous TMA store has READ it (`cp.async.bulk.wait_group.read 0`), and that store queues in the
 // SM's TMA unit behind the producer's loads for the next 4-6 stages.  Plain stores have no such dependency.
 // [written after the last GPU run of round 1: compiled and reviewed, selected only with SHIPYARD_GEMM_DIRECT_STORE=1]
-template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false, bool kDirect = false>
+// kEpiAlt (BN = 64, with kDirect): a 64-column tile has one epilogue chunk, so warpgroup g drains accumulator stage g (alternate
+// tiles) instead of group 1 idling — same schedule as conv3x3_halo_kernel's kEpiAlt.  [round 1: compiled, not yet run; selected with
+// SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1]
+template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false, bool kDirect = false, bool kEpiAlt = false>
 __global__ void __launch_bounds__(kThreadsTN, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
@@ -351,8 +354,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // the smem round trip and the TMA store of one chunk overlap with the other group's chunk; inside a group the
     // tcgen05.ld of the next chunk is issued as soon as the current one has been packed into registers.
     constexpr int kChunks = BN / kEpiChunk;
+    static_assert(!kEpiAlt || (BN == kEpiChunk && kDirect), "kEpiAlt: single-chunk tiles with the st.global epilogue");
     const int grp = (warp - 4) >> 2;
-    if (grp < kChunks) {
+    if (grp < kChunks || kEpiAlt) {
+      const int cg = kEpiAlt ? 0 : grp;                               // chunk group (kEpiAlt: both groups drain chunk 0 of alternate tiles)
       const int ew = warp & 3, et = threadIdx.x - 128 - grp * 128;   // 0..127 inside the group
       const int row = ew * 32 + lane;                               // row of the 128-row tile owned by this thread
       const bool issuer = et == 0;
@@ -370,7 +375,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int wcol = et & 31;
 #pragma unroll
         for (int ci = 0; ci < kMyChunks; ++ci) {
-          const int c = grp + ci * kEpiGroups;
+          const int c = cg + ci * kEpiGroups;
           if (c < kChunks) {
             const int col = n_blk * BN + c * kEpiChunk + 2 * wcol;
             if (col < N) { atomicAdd(&stats[col], st[ci][0]); atomicAdd(&stats[N + col], st[ci][2]); }
@@ -380,17 +385,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       };
       for (int t = t_first; t < num_tiles; t += t_stride) {
+        if constexpr (kEpiAlt) {                           // accumulator stage `acc` belongs to warpgroup `acc`
+          if (acc != grp) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } continue; }
+        }
         int m_blk, n_blk; map_tile<kStats>(t, num_m, num_n, m_blk, n_blk);
         if (kStats && n_blk != cur_n) { flush_stats(cur_n); cur_n = n_blk; }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
         uint32_t v[2][32];
-        tmem_ld32(tbase + grp * kEpiChunk, v[0]);
-        tmem_ld32(tbase + grp * kEpiChunk + 32, v[1]);
+        tmem_ld32(tbase + cg * kEpiChunk, v[0]);
+        tmem_ld32(tbase + cg * kEpiChunk + 32, v[1]);
 #pragma unroll
         for (int ci = 0; ci < kMyChunks; ++ci) {
-          const int c = grp + ci * kEpiGroups;
+          const int c = cg + ci * kEpiGroups;
           if (c >= kChunks) break;
           tmem_ld_wait();
           const bool last = c + kEpiGroups >= kChunks;
@@ -1323,6 +1331,12 @@ bool direct_store() {
   return v == 1;
 }
 
+bool epi_alt() {                      // SHIPYARD_GEMM_EPI_ALT=1 (with SHIPYARD_GEMM_DIRECT_STORE=1): alternate-tile epilogue for 64-column GEMM tiles
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SHIPYARD_GEMM_EPI_ALT"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return v == 1;
+}
+
 // 2D bf16 tensor map: dims {inner, outer}, row pitch `ld` elements, box {box_inner, box_outer}, 128B swizzle
 bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
   cuuint64_t dims[2] = {inner, outer};
@@ -1434,6 +1448,15 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
   };
   if (stats && bias) { snprintf(g_err, sizeof g_err, "stats and bias cannot be combined"); return 2; }
   const bool direct = direct_store() && N % 8 == 0;
+  if constexpr (BN == 64) {
+    if (direct && epi_alt() && !bias) {
+      if (b_mn) {
+        if (stats) { snprintf(g_err, sizeof g_err, "MN-major B: no fused epilogue"); return 2; }
+        return go(gemm_bf16_tn_kernel<64, false, false, true, false, true, true>);
+      }
+      return stats ? go(gemm_bf16_tn_kernel<64, true, false, false, false, true, true>) : go(gemm_bf16_tn_kernel<64, false, false, false, false, true, true>);
+    }
+  }
   if (b_mn) {
     if (stats || bias) { snprintf(g_err, sizeof g_err, "MN-major B: no fused epilogue"); return 2; }
     return direct ? go(gemm_bf16_tn_kernel<BN, false, false, true, false, true>) : go(gemm_bf16_tn_kernel<BN, false, false, true>);

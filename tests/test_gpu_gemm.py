@@ -277,10 +277,11 @@ def test_direct_store_epilogue_variants_in_subprocess():
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SHIPYARD_GEMM_DIRECT_STORE="1")
-    env.pop("SHIPYARD_TEST_UNVERIFIED", None)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu", "-k",
-                        "matches_fp32 or bias_stats or two_cta or conv_implicit or nn_mn_major or conv1x1_and_linear"],
-                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert p.returncode == 0, p.stdout[-4000:]
+    for extra in ({}, {"SHIPYARD_GEMM_EPI_ALT": "1"}):              # second pass: alternate-tile epilogue on the 64-column GEMM tiles
+        env = dict(os.environ, SHIPYARD_GEMM_DIRECT_STORE="1", **extra)
+        env.pop("SHIPYARD_TEST_UNVERIFIED", None)
+        p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu", "-k",
+                            "matches_fp32 or bias_stats or two_cta or conv_implicit or nn_mn_major or conv1x1_and_linear"],
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert p.returncode == 0, (extra, p.stdout[-4000:])
