@@ -33,7 +33,22 @@ def t_us(fn, iters=30):
     return e0.elapsed_time(e1) * 1e3 / iters
 
 
+def one(idx: int, two_cta: bool, stats: bool) -> None:
+    """A handful of launches of one shape for `ncu` (bench/gpu_round2_ncu.sh): no timing, no warm-up loops."""
+    hw, k, n = SHAPES[idx]
+    m = 256 * hw * hw
+    a = (torch.randn(m, k, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16)
+    st = torch.zeros(2 * n, dtype=torch.float32, device="cuda") if stats else None
+    for _ in range(3):
+        gemm.gemm_tn(a, b, stats=st, two_cta=two_cta and gemm.two_cta_ok(m, n))
+    torch.cuda.synchronize()
+    print("probe one:", m, n, k, "two_cta" if two_cta else "1cta", "stats" if stats else "")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        return one(int(sys.argv[2]), "2cta" in sys.argv, "stats" in sys.argv)
     direct = os.environ.get("SHIPYARD_GEMM_DIRECT_STORE", "0") + ("+alt" if os.environ.get("SHIPYARD_GEMM_EPI_ALT") else "")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     for hw, k, n in SHAPES:
