@@ -12,9 +12,10 @@ $NCU -o gpurun_out/r2_ncu_n64_tma -f python bench/gemm_epilogue_probe.py --one 0
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1 $NCU -o gpurun_out/r2_ncu_n64_direct_alt -f python bench/gemm_epilogue_probe.py --one 0 > gpurun_out/r2_ncu_n64_direct_alt.log 2>&1
 ls -la gpurun_out/r2_ncu_*.ncu-rep
 for f in gpurun_out/r2_ncu_*.ncu-rep; do
-  ncu -i "$f" --page raw --csv 2>/dev/null | python - "$f" <<'PY'
+  ncu -i "$f" --page raw --csv > "$f.csv" 2>/dev/null
+  python - "$f" <<'PY'
 import csv, sys
-rows = list(csv.reader(sys.stdin))
+rows = list(csv.reader(open(sys.argv[1] + ".csv")))
 if len(rows) >= 3:
     hdr, vals = rows[0], rows[2]
     want = ("gpu__time_duration.sum", "dram__bytes_write.sum", "dram__bytes_read.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
