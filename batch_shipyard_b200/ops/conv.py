@@ -27,7 +27,10 @@ _PLANS: dict = {}
 _HALO = os.environ.get("SHIPYARD_CONV_HALO", "1") not in ("0", "", "off", "false")
 # SHIPYARD_CONV_EXPERIMENTAL=1 adds the kernel variants that were written after the last GPU run of round 1 (NEXT.md) to the race:
 # every one of them must first reproduce the cuDNN result of the same call (_halo_check), exactly like the validated halo kernels.
-_EXP = os.environ.get("SHIPYARD_CONV_EXPERIMENTAL", "0") not in ("0", "", "off", "false")
+# A comma list instead of 1 restricts it to those variants, e.g. SHIPYARD_CONV_EXPERIMENTAL=tha,wgrad_th (names: tha th264 th264a th2w wgrad_th).
+_EXP_RAW = os.environ.get("SHIPYARD_CONV_EXPERIMENTAL", "0")
+_EXP = _EXP_RAW not in ("0", "", "off", "false")
+_EXP_ALLOW = None if _EXP_RAW in ("0", "", "off", "false", "1", "on", "true", "all") else {v.strip() for v in _EXP_RAW.split(",") if v.strip()}
 # impl name -> keyword arguments of ops.gemm.conv3x3_halo
 _HALO_KW = {"th": {}, "th2": {"pair": True}, "tha": {"epi_alt": True}, "th264": {"pair": True, "block_n": 64},
             "th264a": {"pair": True, "block_n": 64, "epi_alt": True}, "th2w": {"pair": True, "weights_stationary": True}}
@@ -189,6 +192,9 @@ def experimental_impls(n: int, cin: int, h: int, wd: int, cout: int, k: int, str
         out["fprop"].append("th2w")
         out["dgrad"].append("th2w")
     out["wgrad"].append("th")
+    if _EXP_ALLOW is not None:
+        out = {"fprop": [v for v in out["fprop"] if v in _EXP_ALLOW], "dgrad": [v for v in out["dgrad"] if v in _EXP_ALLOW],
+               "wgrad": [v for v in out["wgrad"] if "wgrad_" + v in _EXP_ALLOW]}
     return out
 
 

@@ -22,8 +22,11 @@ timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_tma.jso
 SHIPYARD_GEMM_DIRECT_STORE=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct.jsonl 2> gpurun_out/r2_epilogue_direct.err
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1 timeout 120 python bench/gemm_epilogue_probe.py > gpurun_out/r2_epilogue_direct_alt.jsonl 2> gpurun_out/r2_epilogue_direct_alt.err
 tail -3 gpurun_out/r2_epilogue_tma.jsonl gpurun_out/r2_epilogue_direct.jsonl gpurun_out/r2_epilogue_direct_alt.jsonl
-SHIPYARD_TEST_UNVERIFIED=1 timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing.jsonl 2> gpurun_out/r2_halo_timing.err
-cat gpurun_out/r2_halo_timing.jsonl; tail -3 gpurun_out/r2_halo_timing.err
+timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing.jsonl 2> gpurun_out/r2_halo_timing.err      # validated kernels + cuDNN
+for v in th_alt th2_64 th2_64_alt th2_ws wgrad_th; do                                                                    # one process per unverified variant
+  SHIPYARD_TEST_UNVERIFIED=1 HALO_ONLY=$v timeout 120 python bench/halo_check.py timing 0 > gpurun_out/r2_halo_timing_$v.jsonl 2> gpurun_out/r2_halo_timing_$v.err
+done
+cat gpurun_out/r2_halo_timing*.jsonl; tail -3 gpurun_out/r2_halo_timing*.err
 timeout 240 python bench/torch_kernel_census.py > gpurun_out/r2_kernel_census.txt 2> gpurun_out/r2_kernel_census.err; head -60 gpurun_out/r2_kernel_census.txt
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_CONV_PLAN_DUMP=1 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_direct.json 2> gpurun_out/r2_bench_direct.err

@@ -103,6 +103,9 @@ def timing(mode: int) -> None:
             if cout == 128 and hw == 28:
                 cands["fprop_th2_ws"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, pair=True, base_mode=mode, weights_stationary=True)
                 cands["dgrad_th2_ws"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode, weights_stationary=True)
+        only = [v for v in os.environ.get("HALO_ONLY", "").split(",") if v]
+        if only:                                   # one process per unverified variant (a device trap is sticky): keep the library rows + the named ones
+            cands = {k: fn for k, fn in cands.items() if k.endswith("_cudnn") or any(k.endswith("_" + v) or k == v for v in only)}
         for k, fn in cands.items():
             try:
                 us = t_us(fn)
