@@ -738,9 +738,10 @@ def fs_disks_add(c):
 
 
 @_fs_cmd(fs_disks, "del", "Delete managed disks", [click.option("--all", is_flag=True), click.option("--delete-resource-group", is_flag=True),
-                                                   click.option("--name"), click.option("--resource-group"), click.option("--wait", is_flag=True)], need=())
-def fs_disks_del(c, all, delete_resource_group, name, resource_group, wait):
-    run_action(c, fleet.action_fs_disks_del, all, delete_resource_group, name, resource_group, wait)
+                                                   click.option("--name"), click.option("--resource-group"), click.option("--no-wait", is_flag=True),
+                                                   click.option("--wait", is_flag=True, hidden=True)], need=())
+def fs_disks_del(c, all, delete_resource_group, name, resource_group, no_wait, wait):
+    run_action(c, fleet.action_fs_disks_del, all, delete_resource_group, name, resource_group, wait or not no_wait)
 
 
 @_fs_cmd(fs_disks, "list", "List managed disks", [click.option("--resource-group"), click.option("--restrict-scope", is_flag=True)], need=())
@@ -909,7 +910,7 @@ def fed_jobs_list(c, federation_id, blocked, job_id, jobschedule_id, queued):
 
 
 _fj = [_fid, click.option("--all-jobs", is_flag=True), click.option("--all-jobschedules", is_flag=True),
-       click.option("--job-id", multiple=True), click.option("--job-schedule-id", multiple=True)]
+       click.option("--job-id", multiple=True), click.option("--jobschedule-id", "--job-schedule-id", "job_schedule_id", multiple=True)]
 
 
 @_fed_cmd(fed_jobs, "term", "Terminate federation jobs", _fj + [click.option("--force", is_flag=True)])
