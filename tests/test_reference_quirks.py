@@ -83,3 +83,26 @@ def test_q12_federated_job_schedule_reports_tasks_per_recurrence(tmp_path):
     out = submit.add_jobs(b, cfg)
     summary = out["job1"] if "job1" in out else list(out.values())[0]
     assert summary.get("kind") == "job_schedule" and summary.get("tasks_per_recurrence") == 2
+
+
+def test_q13_slurm_shared_volume_mount_path_spellings():
+    """reference: schema and code read `host_mount_path`, its own template and docs write `mount_path` (the template fails the
+    reference's schema).  Both spellings validate here and resolve to the same setting; neither is an error that names the key."""
+    import pytest
+    from batch_shipyard_b200.config.schema import ConfigType, ValidationError, validate
+    base = {"slurm": {"cluster_id": "c", "storage_account_settings": "acct", "location": "x", "resource_group": "rg",
+                      "shared_data_volumes": {"nfs": {"store_slurmctld_state": True}},
+                      "slurm_options": {"elastic_partitions": {"p": {"batch_pools": {"pool": {"max_compute_nodes": 2}}}}}}}
+    for key in ("host_mount_path", "mount_path"):
+        cfg = copy.deepcopy(base)
+        cfg["slurm"]["shared_data_volumes"]["nfs"][key] = "/shared"
+        try:
+            validate(ConfigType.Slurm, cfg)
+        except ValidationError as e:                      # other required keys of the full schema are not the point here
+            assert not any("mount_path" in m for m in e.errors), e.errors
+        assert S.slurm_options(cfg)["shared_data_volumes"]["nfs"] == {"host_mount_path": "/shared", "store_slurmctld_state": True}
+    with pytest.raises(ValueError, match="host_mount_path"):
+        S.slurm_options(base)
+    bad = copy.deepcopy(base); bad["slurm"]["shared_data_volumes"]["nfs"]["mount_path"] = "/home/"
+    with pytest.raises(ValueError, match="/home"):
+        S.slurm_options(bad)

@@ -1,0 +1,54 @@
+"""Every key path of the reference's pykwalify schemas (`/root/reference/schemas/*.yaml`, read as data) is accepted by our schemas.
+
+Only key NAMES and nesting are compared (our notation for types / enums is different on purpose).  Skipped without the reference."""
+import os
+
+import pytest
+import yaml
+
+REF = "/root/reference/schemas"
+OURS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "batch_shipyard_b200", "config", "schemas")
+
+
+def _ref_paths(node, prefix=""):
+    out = set()
+    if not isinstance(node, dict):
+        return out
+    if "mapping" in node or node.get("type") == "map":
+        for k, v in (node.get("mapping") or {}).items():
+            key = "*" if str(k).startswith(("regex;", "re;")) else str(k)
+            p = f"{prefix}.{key}" if prefix else key
+            out.add(p)
+            out |= _ref_paths(v, p)
+    if "sequence" in node or node.get("type") == "seq":
+        for v in node.get("sequence") or []:
+            out |= _ref_paths(v, prefix + "[]")
+    return out
+
+
+def _our_paths(node, prefix=""):
+    out = set()
+    if isinstance(node, dict):
+        for k, v in node.items():
+            p = f"{prefix}.{str(k).rstrip('!')}" if prefix else str(k).rstrip("!")
+            out.add(p)
+            out |= _our_paths(v, p)
+    elif isinstance(node, list):
+        for v in node:
+            out |= _our_paths(v, prefix + "[]")
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not mounted")
+@pytest.mark.parametrize("name", ["credentials", "config", "pool", "jobs", "fs", "monitor", "federation", "slurm"])
+def test_reference_schema_keys_are_accepted(name):
+    ref = _ref_paths(yaml.safe_load(open(os.path.join(REF, name + ".yaml"))))
+    ours = _our_paths(yaml.safe_load(open(os.path.join(OURS, name + ".yaml"))))
+
+    def covered(p):                                   # a named key of the reference may be served by a "*" (any key) entry of ours
+        parts = p.split(".")
+        return p in ours or any(".".join(parts[:i] + ["*"] + parts[i + 1:]) in ours for i in range(len(parts)))
+
+    missing = sorted(p for p in ref if not covered(p))
+    assert missing == [], missing
+    assert len(ref) > 40
