@@ -33,13 +33,14 @@ class CliContext:
         self.raw = False
         self.show_config = False
         self.configdir: Optional[str] = None
+        self.log_file: Optional[str] = None
         self.paths: dict = {}
         self.ctx: Optional[fleet.Context] = None
         # the reference's cloud flags: recorded; only keyvault-credentials-secret-id has a local meaning (see init)
         self.compat: dict = {}
 
     def init(self, required: tuple = (), skip: tuple = ()) -> fleet.Context:
-        util.setup_logger("shipyard", self.verbose)
+        util.setup_logger("shipyard", self.verbose, logfile=self.log_file)
         # --keyvault-credentials-secret-id: the credentials section comes from the (local) key vault instead of credentials.yaml
         # (/root/reference/shipyard.py:441-575 fetches it from Azure KeyVault at the same point)
         vault_id = self.compat.get("keyvault-credentials-secret-id")
@@ -96,6 +97,8 @@ def common_options(f):
                      help="Verbose output"),
         click.option("--raw", is_flag=True, expose_value=False, envvar="SHIPYARD_RAW", callback=_setter("raw"),
                      help="Output data as returned by the backend, as JSON"),
+        click.option("--log-file", expose_value=False, envvar="SHIPYARD_LOG_FILE", callback=_setter("log_file"),
+                     help="Write log messages to this file instead of stderr"),
         click.option("--configdir", expose_value=False, envvar="SHIPYARD_CONFIGDIR", callback=_setter("configdir"),
                      help="Configuration directory holding all configuration files"),
         click.option("--credentials", expose_value=False, envvar="SHIPYARD_CREDENTIALS_CONF",

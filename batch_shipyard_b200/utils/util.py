@@ -24,15 +24,15 @@ from typing import Any, Iterable, Optional, Sequence
 _LOGGERS: dict[str, logging.Logger] = {}
 
 
-def setup_logger(name: str = "shipyard", verbose: bool = False, stream=None) -> logging.Logger:
-    """One stream handler per logger; verbose adds origin (module:func:line)."""
+def setup_logger(name: str = "shipyard", verbose: bool = False, stream=None, logfile: Optional[str] = None) -> logging.Logger:
+    """One handler per logger (stderr, or ``logfile`` when given); verbose adds origin (module:func:line)."""
     lg = logging.getLogger(name)
     lg.setLevel(logging.DEBUG if verbose else logging.INFO)
     fmt = "%(asctime)s %(levelname)s %(name)s:%(funcName)s:%(lineno)d - %(message)s" if verbose \
         else "%(asctime)s %(levelname)s - %(message)s"
     for h in list(lg.handlers):
         lg.removeHandler(h)
-    h = logging.StreamHandler(stream or sys.stderr)
+    h = logging.FileHandler(logfile, encoding="utf-8") if logfile else logging.StreamHandler(stream or sys.stderr)
     h.setFormatter(logging.Formatter(fmt))
     lg.addHandler(h)
     lg.propagate = False
