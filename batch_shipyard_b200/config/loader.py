@@ -78,6 +78,18 @@ def form_conf_path(explicit: Optional[str], configdir: Optional[str], kind: Conf
     return None
 
 
+def normalize(kind: ConfigType, data):
+    """Rewrite spellings that older releases of the reference accepted (and some of its own recipes still use) into the current
+    form before validation.  Today: ``auto_scratch: true`` on a job (recipes/OpenFOAM-*) -> ``{setup: dependency}``."""
+    if kind is ConfigType.Jobs and isinstance(data, dict):
+        for job in data.get("job_specifications") or []:
+            if isinstance(job, dict) and job.get("auto_scratch") is True:
+                job["auto_scratch"] = {"setup": "dependency"}
+            elif isinstance(job, dict) and job.get("auto_scratch") is False:
+                job.pop("auto_scratch")
+    return data
+
+
 def load_configs(paths: Optional[dict] = None, configdir: Optional[str] = None,
                  required: tuple = (), skip: tuple = (), verbose: bool = False, auto_confirm: bool = False,
                  raw: bool = False) -> dict:
@@ -96,7 +108,7 @@ def load_configs(paths: Optional[dict] = None, configdir: Optional[str] = None,
             continue
         if not os.path.isfile(p):
             raise ConfigError(f"{_KIND_FILES[kind]} config '{p}' does not exist")
-        data = load_file(p)
+        data = normalize(kind, load_file(p))
         try:
             validate(kind, data, source=p)
         except ValidationError as e:

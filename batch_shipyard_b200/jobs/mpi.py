@@ -31,7 +31,7 @@ class MpiSettings:
     runtime: str
     executable_path: str = "mpirun"
     options: list = field(default_factory=list)
-    processes_per_node: Union[int, str] = 1
+    processes_per_node: Union[int, str, None] = 1      # None: not given -> the launcher line carries no -np / per-node flags
 
 
 def mpi_settings(spec: Optional[dict]) -> Optional[MpiSettings]:
@@ -40,7 +40,7 @@ def mpi_settings(spec: Optional[dict]) -> Optional[MpiSettings]:
     rt = str(spec["runtime"]).lower()
     if rt not in RUNTIMES:
         raise ValueError(f"mpi.runtime '{rt}' is not one of {list(RUNTIMES)}")
-    ppn = spec["processes_per_node"]
+    ppn = spec.get("processes_per_node")
     if isinstance(ppn, str) and ppn.strip().isdigit():
         ppn = int(ppn)
     if isinstance(ppn, int) and ppn < 1:
@@ -63,7 +63,9 @@ def construct_mpi_command(mpi: MpiSettings, num_instances: int, command: str, in
     ppn = mpi.processes_per_node
     opts = list(mpi.options) + list(lead)
     opts.append(f"{host_flag} $AZ_BATCH_HOST_LIST")
-    if isinstance(ppn, int):
+    if ppn is None:
+        pass                                       # optional in the reference: the MPI runtime decides
+    elif isinstance(ppn, int):
         opts.append(f"-np {num_instances * ppn}")
         opts.append(per_node.format(ppn=ppn))
     else:
@@ -106,6 +108,8 @@ def construct_mpi_command(mpi: MpiSettings, num_instances: int, command: str, in
 def resolve_processes_per_node(ppn: Union[int, str], gpu_count: int, dry_run: bool = False) -> int:
     """Evaluate ``processes_per_node`` locally.  Known GPU/CPU counting idioms are answered
     from the topology (so they work in dry-run / on a CPU box); anything else is run by a shell."""
+    if ppn is None:
+        return 1                                   # the native runner starts one rank per instance
     if isinstance(ppn, int):
         return ppn
     s = ppn.strip()
