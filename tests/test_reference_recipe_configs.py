@@ -52,3 +52,33 @@ def test_optional_processes_per_node_and_legacy_auto_scratch():
     assert a is not None and a.setup == "dependency"
     off = loader.normalize(ConfigType.Jobs, {"job_specifications": [{"id": "j", "auto_scratch": False, "tasks": []}]})
     assert "auto_scratch" not in off["job_specifications"][0]
+
+
+@pytest.mark.skipif(not os.path.isdir(ROOT), reason="reference checkout not mounted")
+def test_every_reference_recipe_dry_runs_through_the_job_builder(tmp_path, monkeypatch):
+    """`shipyard jobs add --dry-run` on the reference's own recipe directories (their pool / jobs / config files, untouched): task-factory
+    expansion, image policy, container option synthesis, MPI launcher line, multi-instance settings and data-movement specs all resolve."""
+    from batch_shipyard_b200.backend.local import LocalBackend
+    from batch_shipyard_b200.jobs import submit
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
+    skip = (ConfigType.RemoteFS, ConfigType.Monitor, ConfigType.Federation, ConfigType.Slurm)
+    done, problems = 0, []
+    for recipe in sorted(os.listdir(ROOT)):
+        cfgd = os.path.join(ROOT, recipe, "config")
+        if not os.path.isdir(cfgd):
+            continue
+        variants = [cfgd] if os.path.exists(os.path.join(cfgd, "jobs.yaml")) else \
+            [os.path.join(cfgd, v) for v in sorted(os.listdir(cfgd)) if os.path.isdir(os.path.join(cfgd, v))]
+        for v in variants:
+            if not os.path.exists(os.path.join(v, "jobs.yaml")):
+                continue
+            try:
+                cfg = loader.load_configs({}, v, skip=skip)
+                cfg.setdefault("credentials", {"storage": {"mystorageaccount": {"account": "local"}}})
+                out = submit.add_jobs(LocalBackend(state_dir=str(tmp_path / f"s{done}")), cfg, dry_run=True)
+                assert out and all(j.get("dry_run") for j in out.values())
+                done += 1
+            except Exception as e:  # noqa: BLE001
+                problems.append((os.path.relpath(v, ROOT), f"{type(e).__name__}: {e}"[:300]))
+    assert problems == [], problems
+    assert done >= 50
