@@ -13,6 +13,7 @@ from __future__ import annotations
 import os
 import subprocess
 import time
+from typing import Optional
 
 from ..config import settings as S
 
@@ -204,17 +205,33 @@ def daemon(b, config: dict, poll_interval: float = 5.0, max_iterations: int = 0)
     return dict(total, iterations=it)
 
 
+def node_assignment(b, config: dict, node_or_host: str) -> Optional[dict]:
+    """The Slurm host bound to a GPU node id (or the record of a host name): what a compute node asks for when it comes up
+    (/root/reference/slurm/slurm.py `get-node-assignment`)."""
+    cid = S.slurm_options(config)["cluster_id"]
+    for h in b.store.query("slurmhost", cid):
+        if h.get("gpu_node") == node_or_host or h.get("name") == node_or_host or h.get("_rk") == node_or_host:
+            return {"host": h.get("name") or h.get("_rk"), "node": h.get("gpu_node"), "state": h.get("state"),
+                    "partition": h.get("partition"), "pool": h.get("pool"), "assignment_complete": bool(h.get("assignment_complete"))}
+    return None
+
+
 def main(argv=None) -> int:
-    """``python -m batch_shipyard_b200.slurm.cluster <resume|suspend|resume-fail|daemon> --conf slurm.yaml [--hosts LIST]``
-    — the programs a slurm.conf generated by ``slurm_conf`` points ResumeProgram / SuspendProgram / ResumeFailProgram at."""
+    """``python -m batch_shipyard_b200.slurm.cluster <verb> --conf slurm.yaml [--hosts LIST | --hostfile FILE | --host NAME]``
+    — the programs a slurm.conf generated by ``slurm_conf`` points ResumeProgram / SuspendProgram / ResumeFailProgram at, plus the
+    node-side verbs of the reference's helper (/root/reference/slurm/slurm.py:1448-1466: daemon, sakey, resume, resume-fail, suspend,
+    check-provisioning-status, get-node-assignment, complete-node-assignment; ``--hostfile`` lines are ``host [partition]``)."""
     import argparse
     import json
     from ..backend.local import LocalBackend
     from ..config.loader import load_file
     ap = argparse.ArgumentParser(prog="shipyard-slurm")
-    ap.add_argument("verb", choices=["resume", "suspend", "resume-fail", "daemon"])
+    ap.add_argument("verb", choices=["resume", "suspend", "resume-fail", "daemon", "sakey", "check-provisioning-status",
+                                     "get-node-assignment", "complete-node-assignment"])
     ap.add_argument("--conf", required=True)
     ap.add_argument("--hosts", default="")
+    ap.add_argument("--hostfile")
+    ap.add_argument("--host")
     ap.add_argument("--state-dir", default=os.environ.get("SHIPYARD_STATE_DIR"))
     ap.add_argument("--poll-interval", type=float, default=5.0)
     ap.add_argument("--iterations", type=int, default=0)
@@ -222,14 +239,37 @@ def main(argv=None) -> int:
     config = load_file(a.conf)
     b = LocalBackend(state_dir=a.state_dir) if a.state_dir else LocalBackend()
     hosts = expand_hostlist(a.hosts) if a.hosts else []
+    if a.hostfile:
+        with open(a.hostfile) as f:
+            for line in f:
+                if line.split():
+                    hosts += expand_hostlist(line.split()[0])
+    if a.host and a.verb in ("resume", "suspend", "resume-fail"):
+        hosts += expand_hostlist(a.host)
     if a.verb == "resume":
         out = resume(b, config, hosts)
     elif a.verb == "suspend":
         out = suspend(b, config, hosts)
     elif a.verb == "resume-fail":
         out = resume_failed(b, config, hosts)
-    else:
+    elif a.verb == "daemon":
         out = daemon(b, config, a.poll_interval, a.iterations)
+    elif a.verb == "sakey":
+        out = {"storage_account": "local", "key": None, "note": "the state store is local: no storage account key is needed"}
+    else:
+        if not a.host:
+            ap.error(f"{a.verb} needs --host")
+        rec = node_assignment(b, config, a.host)
+        if rec is None:
+            print(json.dumps({"host": a.host, "assigned": False}))
+            return 1
+        if a.verb == "complete-node-assignment":
+            b.store.merge("slurmhost", S.slurm_options(config)["cluster_id"], rec["host"], {"assignment_complete": True})
+            rec["assignment_complete"] = True
+        out = dict(rec, assigned=True)
+        if a.verb == "check-provisioning-status" and rec["state"] != "up":
+            print(json.dumps(out))
+            return 1
     print(json.dumps(out))
     return 0 if not out.get("failed") else 1
 

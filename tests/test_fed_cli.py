@@ -244,3 +244,34 @@ def test_credentials_from_local_keyvault(tmp_path, monkeypatch):
     assert res.exit_code == 0 and "account: local" in res.output       # the merged config really contains the vault's credentials
     res = r.invoke(cli.cli, ["pool", "list", "--configdir", str(cfg), "--keyvault-credentials-secret-id", "nope"], obj=cli.CliContext())
     assert res.exit_code == 1 and "not found" in res.output
+
+
+def test_slurm_helper_node_side_verbs(tmp_path, capsys):
+    """The reference helper's verbs and host options: --hostfile ("host partition" lines), --host, sakey, get-node-assignment,
+    complete-node-assignment, check-provisioning-status."""
+    import yaml
+    from batch_shipyard_b200.backend.local import LocalBackend
+    from batch_shipyard_b200.slurm import cluster as sl
+    sd = str(tmp_path / "st")
+    b = LocalBackend(state_dir=sd)
+    conf = tmp_path / "slurm.yaml"
+    conf.write_text(yaml.safe_dump({"slurm": {"cluster_id": "sc", "slurm_options": {"elastic_partitions": {}}}}))
+    b.store.insert("slurmhost", "sc", "sc-p-x-0", {"name": "sc-p-x-0", "state": "up", "gpu_node": "gpu-3", "partition": "p", "pool": "x"})
+    b.store.insert("slurmhost", "sc", "sc-p-x-1", {"name": "sc-p-x-1", "state": "suspended", "gpu_node": None, "partition": "p", "pool": "x"})
+    base = ["--conf", str(conf), "--state-dir", sd]
+    assert sl.main(["sakey"] + base) == 0 and "local" in capsys.readouterr().out
+    assert sl.main(["get-node-assignment", "--host", "gpu-3"] + base) == 0                 # a node asks which Slurm host it is
+    assert json.loads(capsys.readouterr().out)["host"] == "sc-p-x-0"
+    assert sl.main(["get-node-assignment", "--host", "gpu-9"] + base) == 1
+    capsys.readouterr()
+    assert sl.main(["complete-node-assignment", "--host", "sc-p-x-0"] + base) == 0
+    assert b.store.get("slurmhost", "sc", "sc-p-x-0")["assignment_complete"] is True
+    capsys.readouterr()
+    assert sl.main(["check-provisioning-status", "--host", "sc-p-x-0"] + base) == 0
+    assert sl.main(["check-provisioning-status", "--host", "sc-p-x-1"] + base) == 1         # still suspended
+    capsys.readouterr()
+    hf = tmp_path / "hosts"
+    hf.write_text("sc-p-x-1 p\n\nghost p\n")
+    rc = sl.main(["resume-fail", "--hostfile", str(hf)] + base)
+    out = json.loads(capsys.readouterr().out)
+    assert rc in (0, 1) and isinstance(out, dict)
