@@ -48,3 +48,17 @@ def test_every_reference_option_exists_on_the_same_command():
         if lost:
             missing.append((" ".join(cands[0]), lost))
     assert missing == [], missing
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/docs/20-batch-shipyard-usage.md"), reason="reference checkout not mounted")
+def test_raw_capable_commands_and_environment_variables_of_the_usage_guide_exist():
+    """docs/20-batch-shipyard-usage.md lists the ~30 commands that support --raw and the SHIPYARD_* variables of the CLI."""
+    txt = open("/root/reference/docs/20-batch-shipyard-usage.md").read()
+    block = txt[txt.index("The following commands support this option:"):txt.index("`--show-config` will output")]
+    listed = [tuple(m.split()) for m in re.findall(r"\* `([a-z \-]+)`", block)]
+    assert len(listed) >= 30
+    ours = _ours()
+    assert [c for c in listed if c not in ours] == []
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "batch_shipyard_b200", "cli.py")).read()
+    env = set(re.findall(r"envvar='(SHIPYARD_[A-Z_]+)'", open(REF).read()))
+    assert len(env) >= 20 and sorted(e for e in env if e not in src) == []
