@@ -116,13 +116,42 @@ static std::string json_escape(const std::string& s) {
   return o;
 }
 
+// Environment-variable contract of the reference's task runner script (/root/reference/scripts/shipyard_task_runner.sh:24-63), so
+// this binary can stand in for it: SHIPYARD_SYSTEM_PROLOGUE_CMD -> SHIPYARD_USER_PROLOGUE_CMD (a failing prologue aborts with its
+// code: the script runs under `set -e`) -> environment minus SHIPYARD_ENV_EXCLUDE (grep -E pattern) written to SHIPYARD_ENV_FILE ->
+// `$SHIPYARD_RUNTIME $SHIPYARD_RUNTIME_CMD $SHIPYARD_RUNTIME_CMD_OPTS $SHIPYARD_CONTAINER_IMAGE_NAME $SHIPYARD_USER_CMD` (or the bare
+// user command) -> SHIPYARD_SYSTEM_EPILOGUE_CMD with SHIPYARD_TASK_RESULT=success|fail -> exit with the task's code.
+static int run_env_contract() {
+  auto env = [](const char* k) { const char* v = getenv(k); return std::string(v ? v : ""); };
+  const std::string shell = "/bin/bash";
+  int rc = run_shell(shell, env("SHIPYARD_SYSTEM_PROLOGUE_CMD"), {}, -1, -1, "");
+  if (rc != 0) return rc;
+  rc = run_shell(shell, env("SHIPYARD_USER_PROLOGUE_CMD"), {}, -1, -1, "");
+  if (rc != 0) return rc;
+  if (!env("SHIPYARD_ENV_FILE").empty()) {
+    const std::string dump = env("SHIPYARD_ENV_EXCLUDE").empty() ? "env > \"$SHIPYARD_ENV_FILE\""
+                                                                 : "env | grep -vE \"$SHIPYARD_ENV_EXCLUDE\" > \"$SHIPYARD_ENV_FILE\"";
+    rc = run_shell(shell, dump, {}, -1, -1, "");
+    if (rc != 0 && env("SHIPYARD_ENV_EXCLUDE").empty()) return rc;      // (grep exits 1 when every line was excluded: not an error)
+  }
+  const std::string task = env("SHIPYARD_RUNTIME").empty()
+      ? "eval \"$SHIPYARD_USER_CMD\""
+      : "SHIPYARD_RUNTIME_CMD_OPTS=$(eval echo \"${SHIPYARD_RUNTIME_CMD_OPTS}\"); "
+        "eval \"$SHIPYARD_RUNTIME $SHIPYARD_RUNTIME_CMD $SHIPYARD_RUNTIME_CMD_OPTS $SHIPYARD_CONTAINER_IMAGE_NAME $SHIPYARD_USER_CMD\"";
+  const int task_rc = run_shell(shell, task, {}, -1, -1, "");
+  if (!env("SHIPYARD_SYSTEM_EPILOGUE_CMD").empty())
+    run_shell(shell, "eval \"$SHIPYARD_SYSTEM_EPILOGUE_CMD\"", {std::string("SHIPYARD_TASK_RESULT=") + (task_rc == 0 ? "success" : "fail")}, -1, -1, "");
+  return task_rc;
+}
+
 int main(int argc, char** argv) {
   const char* spec_path = nullptr;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--spec") && i + 1 < argc) spec_path = argv[++i];
     else if (!strcmp(argv[i], "--version")) { puts("shipyard-taskrun 0.1"); return 0; }
   }
-  if (!spec_path) { fprintf(stderr, "usage: shipyard-taskrun --spec <file>\n"); return 2; }
+  if (!spec_path && getenv("SHIPYARD_USER_CMD")) return run_env_contract();
+  if (!spec_path) { fprintf(stderr, "usage: shipyard-taskrun --spec <file>   (or the SHIPYARD_USER_CMD environment contract)\n"); return 2; }
   Spec sp;
   if (!load_spec(spec_path, sp)) return 2;
 

@@ -287,3 +287,30 @@ def test_max_tasks_per_node_and_fill(tmp_path):
                   tasks=[{"docker_image": "busybox", "task_factory": {"repeat": 2}, "command": "sleep 0.4; echo $AZ_BATCH_NODE_ID"}])
     up(cfg, b); run(cfg, b)
     assert {read(b, "job1", t["id"]).strip() for t in b.list_tasks("job1")} == {"cpu-0", "cpu-1"}
+
+
+def test_taskrun_accepts_the_reference_runner_environment_contract(tmp_path):
+    """`shipyard-taskrun` without --spec behaves like the reference's shipyard_task_runner.sh: prologues, env file minus exclusions,
+    `$RUNTIME $CMD $OPTS $IMAGE $USER_CMD`, epilogue with SHIPYARD_TASK_RESULT, exit code of the task."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "batch_shipyard_b200", "_native", "shipyard-taskrun")
+    if not os.path.exists(exe):
+        pytest.skip("native runner not built")
+    envfile = tmp_path / "envlist"
+    env = {"PATH": os.environ["PATH"], "KEEP": "y", "SECRET": "x", "SHIPYARD_ENV_EXCLUDE": "^SECRET=", "SHIPYARD_ENV_FILE": str(envfile),
+           "SHIPYARD_SYSTEM_PROLOGUE_CMD": "echo sys-pro", "SHIPYARD_USER_PROLOGUE_CMD": "echo user-pro",
+           "SHIPYARD_USER_CMD": "echo hello; exit 3", "SHIPYARD_SYSTEM_EPILOGUE_CMD": "echo result=$SHIPYARD_TASK_RESULT"}
+    p = subprocess.run([exe], env=env, stdout=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert p.returncode == 3 and p.stdout.split() == ["sys-pro", "user-pro", "hello", "result=fail"]
+    lines = envfile.read_text().splitlines()
+    assert "KEEP=y" in lines and not any(ln.startswith("SECRET=") for ln in lines)
+    # container form: runtime + command + expanded options + image + user command
+    env2 = {"PATH": os.environ["PATH"], "SHIPYARD_RUNTIME": "echo", "SHIPYARD_RUNTIME_CMD": "run", "SHIPYARD_RUNTIME_CMD_OPTS": "--rm -e HOME=$HOME",
+            "HOME": "/h", "SHIPYARD_CONTAINER_IMAGE_NAME": "busybox", "SHIPYARD_USER_CMD": "true", "SHIPYARD_SYSTEM_EPILOGUE_CMD": "echo $SHIPYARD_TASK_RESULT"}
+    p = subprocess.run([exe], env=env2, stdout=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert p.returncode == 0 and p.stdout.splitlines() == ["run --rm -e HOME=/h busybox true", "success"]
+    # a failing prologue aborts with its exit code (the reference script runs under `set -e`)
+    p = subprocess.run([exe], env={"PATH": os.environ["PATH"], "SHIPYARD_SYSTEM_PROLOGUE_CMD": "exit 7", "SHIPYARD_USER_CMD": "echo no"},
+                       stdout=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert p.returncode == 7 and "no" not in p.stdout
