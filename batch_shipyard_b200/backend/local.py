@@ -328,16 +328,20 @@ class LocalBackend:
         tasks = list(tasks)
         added = 0
         for i in range(0, len(tasks), MAX_TASKS_PER_REQUEST):
+            rows, seen = [], set()
             for t in tasks[i:i + MAX_TASKS_PER_REQUEST]:
                 rec = {"state": "active", "created": _now(), "state_transition_time": _now(), "retry_count": 0,
                        "exit_code": None, "result": None, "node_ids": [], "start_time": None, "end_time": None,
                        "pid": None, "failure_info": None, "requeue_count": 0}
                 rec.update(t)
-                try:
-                    self.store.insert("task", job_id, rec["id"], rec)
-                except EntityExists:
-                    raise BackendError(f"task {rec['id']} already exists in job {job_id}") from None
-                added += 1
+                if rec["id"] in seen:
+                    raise BackendError(f"task {rec['id']} already exists in job {job_id}")
+                seen.add(rec["id"])
+                rows.append((rec["id"], rec))
+            try:
+                added += self.store.insert_many("task", job_id, rows)      # one transaction per collection of <= 100 tasks
+            except EntityExists as e:
+                raise BackendError(f"task {str(e).rsplit('/', 1)[-1]} already exists in job {job_id}") from None
         return added
 
     def get_task(self, job_id: str, task_id: str) -> dict:

@@ -72,20 +72,46 @@ class TaskRecord:
 # ---------------------------------------------------------------------------
 # task ids
 # ---------------------------------------------------------------------------
+class TaskIdAllocator:
+    """Generic task ids ``<prefix>NNNNN`` continuing after the highest id already in the job.  The highest number per prefix is
+    found once (one pass over the existing ids) and then counted up, so a 10 000-task sweep does not rescan the job for every
+    task (the reference lists the job's tasks once per submission for the same reason, convoy/batch.py:4165-4240)."""
+
+    def __init__(self, existing: set, reserved: Optional[set] = None):
+        self._ids = set(existing) | set(reserved or ())
+        self._next: dict = {}
+
+    def _start(self, pfx: str) -> int:
+        pat = re.compile("^" + re.escape(pfx) + r"(\d+)$")
+        mx = -1
+        for tid in self._ids:
+            m = pat.match(tid)
+            if m:
+                mx = max(mx, int(m.group(1)))
+        return mx + 1
+
+    def reserve(self, tid: str) -> None:
+        self._ids.add(tid)
+        for pfx in self._next:                       # an explicit id of the same shape moves the counter past it
+            if tid.startswith(pfx) and tid[len(pfx):].isdigit():
+                self._next[pfx] = max(self._next[pfx], int(tid[len(pfx):]) + 1)
+
+    def next(self, prefix: str, zfill: int, is_merge: bool = False) -> str:
+        pfx = ("merge-" if is_merge else "") + prefix
+        if pfx not in self._next:
+            self._next[pfx] = self._start(pfx)
+        tid = f"{pfx}{str(self._next[pfx]).zfill(zfill)}"
+        if len(tid) > MAX_TASK_ID_LEN:
+            raise ValueError(f"generated task id '{tid}' exceeds {MAX_TASK_ID_LEN} characters")
+        self._next[pfx] += 1
+        self._ids.add(tid)
+        return tid
+
+
 def next_generic_task_id(existing: set, prefix: str, zfill: int, reserved: Optional[set] = None,
                          is_merge: bool = False) -> str:
-    """``<prefix>NNNNN`` continuing after the highest id already in the job (merge: ``merge-<prefix>NNNNN``)."""
-    pfx = ("merge-" if is_merge else "") + prefix
-    pat = re.compile("^" + re.escape(pfx) + r"(\d+)$")
-    mx = -1
-    for tid in existing | (reserved or set()):
-        m = pat.match(tid)
-        if m:
-            mx = max(mx, int(m.group(1)))
-    tid = f"{pfx}{str(mx + 1).zfill(zfill)}"
-    if len(tid) > MAX_TASK_ID_LEN:
-        raise ValueError(f"generated task id '{tid}' exceeds {MAX_TASK_ID_LEN} characters")
-    return tid
+    """One-shot form of :class:`TaskIdAllocator` (``merge-<prefix>NNNNN`` for merge tasks)."""
+    return TaskIdAllocator(existing, reserved).next(prefix, zfill, is_merge)
 
 
 def validate_task_id(tid: str) -> None:

@@ -168,13 +168,16 @@ def add_jobs(b: LocalBackend, config: dict, recreate: bool = False, tail: Option
         if scratch is not None:
             records.append(scratch)
             reserved.add(scratch["id"])
+        ids = B.TaskIdAllocator(existing_ids, reserved)       # one scan of the job's ids, then a counter per prefix
         for t in expanded:
             prefix, zfill = t.pop("##autoid")
             tid = t.get("id")
             if not tid:
-                tid = B.next_generic_task_id(existing_ids, prefix, zfill, reserved)
+                tid = ids.next(prefix, zfill)
             elif tid in existing_ids or tid in reserved:
                 raise JobSubmissionError(f"task id {tid} already exists in job {jid}")
+            else:
+                ids.reserve(tid)
             reserved.add(tid)
             try:
                 rec = B.build_task(config, pool, jobspec, t, tid, counts, gpu_count=gpu_count, dry_run=dry_run).to_dict()
@@ -188,7 +191,7 @@ def add_jobs(b: LocalBackend, config: dict, recreate: bool = False, tail: Option
         if merge is not None:
             gid = S.global_settings(config).autogenerated_task_id
             jauto = S.autogenerated_task_id(jobspec.get("autogenerated_task_id"), gid)
-            mid = merge.get("id") or B.next_generic_task_id(existing_ids, jauto.prefix, jauto.zfill_width, reserved, is_merge=True)
+            mid = merge.get("id") or ids.next(jauto.prefix, jauto.zfill_width, is_merge=True)
             mrec = B.build_task(config, pool, jobspec, merge, mid, counts, is_merge=True, gpu_count=gpu_count, dry_run=dry_run).to_dict()
             mrec["depends_on"] = [r["id"] for r in records if not r.get("is_auto_scratch")]
             if sum(len(x) + 1 for x in mrec["depends_on"]) > MAX_MERGE_DEP_CHARS:

@@ -131,6 +131,18 @@ class Store:
             c.execute("INSERT OR REPLACE INTO entities VALUES (?,?,?,?,?,?)", (kind, pk, rk, self._clean(data), etag, time.time()))
         return etag
 
+    def insert_many(self, kind: str, pk: str, rows: list, replace: bool = False) -> int:
+        """Insert ``[(rk, data), ...]`` in ONE transaction (a task collection): all rows or none; EntityExists names the first clash."""
+        now = time.time()
+        with self._tx() as c:
+            if not replace:
+                for rk, _ in rows:
+                    if c.execute("SELECT 1 FROM entities WHERE kind=? AND pk=? AND rk=?", (kind, pk, rk)).fetchone():
+                        raise EntityExists(f"{kind}/{pk}/{rk}")
+            c.executemany("INSERT OR REPLACE INTO entities VALUES (?,?,?,?,?,?)",
+                          [(kind, pk, rk, self._clean(data), uuid.uuid4().hex, now) for rk, data in rows])
+        return len(rows)
+
     def get(self, kind: str, pk: str, rk: str) -> dict:
         r = self._conn().execute("SELECT kind,pk,rk,data,etag,updated FROM entities WHERE kind=? AND pk=? AND rk=?",
                                  (kind, pk, rk)).fetchone()
