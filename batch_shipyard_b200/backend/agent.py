@@ -283,7 +283,9 @@ class NodeAgent:
                                                          "message": f"job preparation exited with {rc} on {n['id']}"})
                         return True
                     prepped.add(n["id"])
-            self.b.update_job(jid, prep_nodes=sorted(prepped))
+            if sorted(prepped) != sorted(job.get("prep_nodes") or []):
+                self.b.update_job(jid, prep_nodes=sorted(prepped))
+                job["prep_nodes"] = sorted(prepped)       # the caller's snapshot is reused for the other tasks of this scheduling pass
         spec, tdir = runspec.build_task_spec(self.b, pool, job, t, nodes)
         for n in nodes:
             def fn(x, _j=jid, _t=tid):

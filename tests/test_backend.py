@@ -339,3 +339,18 @@ def test_large_sweep_submission_is_linear(tmp_path):
     assert got == ["task-00004", "task-00005", "task-00011", "merge-task-00000"]
     with pytest.raises(Exception):
         b.add_tasks("job1", [{"id": "task-00001"}])                     # a clash rolls the whole collection back
+
+
+def test_job_preparation_runs_once_per_node_even_when_many_tasks_start_in_one_pass(tmp_path):
+    """Regression: the scheduler reused a stale job snapshot inside one scheduling pass, so every task launched in that pass re-ran
+    the job preparation on its node (80 preparations for 100 tasks on 4 nodes)."""
+    cfg, b = make(tmp_path, pool={"vm_count": {"dedicated": 3, "low_priority": 0}, "max_tasks_per_node": 4},
+                  job={"job_preparation": {"command": "echo prep-$AZ_BATCH_NODE_ID >> $AZ_BATCH_NODE_SHARED_DIR/prep.log"}},
+                  tasks=[{"docker_image": "busybox", "command": "true", "task_factory": {"repeat": 40}}])
+    up(cfg, b)
+    run(cfg, b, max_seconds=120)
+    tasks = b.list_tasks("job1")
+    assert len(tasks) == 40 and all(t["state"] == "completed" and t["result"] == "success" for t in tasks)
+    lines = open(os.path.join(b.node_shared_dir("testpool"), "prep.log")).read().split()
+    assert len(lines) == len(set(lines)) <= 3 and len(lines) >= 1          # at most once per node, never twice on the same node
+    assert sorted(b.get_job("job1")["prep_nodes"]) == sorted(ln[len("prep-"):] for ln in lines)
