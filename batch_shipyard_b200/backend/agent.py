@@ -227,8 +227,8 @@ class NodeAgent:
         return state
 
     # -- placement ------------------------------------------------------------------------
-    def _free_nodes(self, pool: dict) -> list[dict]:
-        nodes = [n for n in self.b.list_nodes(self.pool_id)
+    def _free_nodes(self, pool: dict, all_nodes: Optional[list] = None) -> list[dict]:
+        nodes = [n for n in (self.b.list_nodes(self.pool_id) if all_nodes is None else all_nodes)
                  if n["state"] in ("idle", "running") and n.get("scheduling", "enabled") == "enabled"
                  and len(n["running_tasks"]) < pool["max_tasks_per_node"]]
         if pool.get("node_fill_type", "pack") == "pack":
@@ -242,6 +242,16 @@ class NodeAgent:
         progressed = False
         jobs = [j for j in self.b.list_jobs(self.pool_id) if j["state"] == "active"]
         jobs.sort(key=lambda j: (-int(j.get("priority") or 0), j["created"]))
+        # the node table is read once per pass and again after every launch (the only thing that changes it here): a saturated pool
+        # with thousands of queued tasks costs one query per pass instead of two per queued task
+        snap: dict = {"nodes": None, "free": None}
+
+        def nodes_now():
+            if snap["nodes"] is None:
+                snap["nodes"] = self.b.list_nodes(self.pool_id)
+                snap["free"] = self._free_nodes(pool, snap["nodes"])
+            return snap["nodes"], snap["free"]
+
         for job in jobs:
             tasks = self.b.list_tasks(job["id"])
             if not tasks:
@@ -255,11 +265,11 @@ class NodeAgent:
                     continue
                 mi = t.get("multi_instance")
                 need = int(mi["num_instances"]) if mi else 1
-                free = self._free_nodes(pool)
+                all_nodes, free = nodes_now()
                 if mi:
                     free = [n for n in free if not n["running_tasks"]] if need > 1 else free
                 if len(free) < need:
-                    total = len([n for n in self.b.list_nodes(self.pool_id) if n["state"] in ("idle", "running")])
+                    total = len([n for n in all_nodes if n["state"] in ("idle", "running")])
                     if mi and need > total and total > 0 and not t.get("_warned"):
                         self.b.update_task(job["id"], t["id"], _warned=True, scheduling_note=(
                             f"needs {need} instances but pool has {total} usable node(s)"))
@@ -267,6 +277,7 @@ class NodeAgent:
                 chosen = free[:need]
                 if self._launch(pool, job, t, chosen):
                     progressed = True
+                snap["nodes"] = None                      # running_tasks / states changed
         return progressed
 
     def _launch(self, pool: dict, job: dict, t: dict, nodes: list[dict]) -> bool:
