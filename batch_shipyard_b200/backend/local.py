@@ -227,15 +227,30 @@ class LocalBackend:
         a2r = [n["last_boot_time"] - n["allocation_time"] for n in ready if n.get("allocation_time")]
         slots = len(nodes) * pool["max_tasks_per_node"]
         running = sum(len(n["running_tasks"]) for n in nodes)
+
+        def agg(vals, with_sum=False):
+            vals = [v for v in vals if v is not None]
+            out = {"min": min(vals, default=None), "mean": (sum(vals) / len(vals)) if vals else None, "max": max(vals, default=None)}
+            if with_sum:
+                out["sum"] = sum(vals)
+            return out
+
+        # the fields `pool stats` of the reference prints (/root/reference/convoy/batch.py:1460-1633): node-state histogram, uptime,
+        # allocation-to-ready and last start-task time, total / running tasks per node, scheduling slots busy / available / runnable
+        runnable_nodes = [n for n in nodes if n["state"] in ("idle", "running")]
+        runnable = len(runnable_nodes) * pool["max_tasks_per_node"]
+        busy = sum(len(n["running_tasks"]) for n in runnable_nodes)
         return {"pool_id": pool_id, "node_states": by_state, "total_nodes": len(nodes),
                 "dedicated_nodes": sum(1 for n in nodes if n["dedicated"]),
                 "low_priority_nodes": sum(1 for n in nodes if not n["dedicated"]),
                 "allocation_state": pool["allocation_state"], "created": _iso(pool["created"]),
-                "uptime_s": {"min": min((now - n["last_boot_time"] for n in ready), default=None),
-                             "max": max((now - n["last_boot_time"] for n in ready), default=None)},
-                "allocation_to_ready_s": {"min": min(a2r, default=None), "mean": sum(a2r) / len(a2r) if a2r else None,
-                                          "max": max(a2r, default=None)},
+                "uptime_s": agg(now - n["last_boot_time"] for n in ready),
+                "allocation_to_ready_s": agg(a2r),
+                "start_task_s": agg(n.get("start_task_seconds") for n in nodes),
+                "total_tasks_run": agg((n.get("total_tasks_run") or 0 for n in nodes), with_sum=True),
+                "running_tasks_per_node": agg((len(n["running_tasks"]) for n in nodes), with_sum=True),
                 "running_tasks": running, "task_slots": slots,
+                "scheduling_slots": {"busy": busy, "available": max(runnable - busy, 0), "runnable": runnable, "total": slots},
                 "slot_utilization_pct": round(100.0 * running / slots, 2) if slots else 0.0}
 
     # ------------------------------------------------------------------ jobs

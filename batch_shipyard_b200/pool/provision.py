@@ -187,10 +187,11 @@ def bring_up_nodes(b: LocalBackend, pool_id: str, ps: Optional[S.PoolSettings] =
         attempt = 0
         while True:
             b.set_node_state(pool_id, node["id"], "starting")
+            t_prep = time.time()
             injected = fault_hook(node, attempt) if fault_hook else None
             ok, msg = (False, injected) if injected else prep_node(b, pool_id, node, ps, gpus)
             if ok:
-                b.set_node_state(pool_id, node["id"], "idle", last_boot_time=time.time(),
+                b.set_node_state(pool_id, node["id"], "idle", last_boot_time=time.time(), start_task_seconds=time.time() - t_prep,
                                  start_task={"exit_code": 0, "message": msg, "attempts": attempt + 1})
                 summary["ready"] += 1
                 break
