@@ -415,8 +415,11 @@ class LocalBackend:
         jobs = [self.get_job(job_id)] if job_id else self.list_jobs()
         tot = {"jobs": len(jobs), "tasks": 0, "active": 0, "running": 0, "completed": 0, "succeeded": 0, "failed": 0,
                "retries": 0, "wall_time_s": 0.0, "wait_time_s": 0.0}
-        durations = []
+        durations, e2e, walltime, job_spans = [], [], [], []
+        now = _now()
         for j in jobs:
+            if j.get("state") == "completed" and j.get("end_time") or j.get("state") == "completed" and j.get("state_transition_time"):
+                job_spans.append((j.get("end_time") or j["state_transition_time"]) - j["created"])
             for t in self.list_tasks(j["id"]):
                 tot["tasks"] += 1
                 st = "running" if t["state"] in ("running", "preparing") else t["state"]
@@ -427,9 +430,23 @@ class LocalBackend:
                     if t.get("start_time") and t.get("end_time"):
                         d = t["end_time"] - t["start_time"]
                         durations.append(d); tot["wall_time_s"] += d
+                        walltime.append(d)
+                        e2e.append(t["end_time"] - t["created"])
                         tot["wait_time_s"] += max(0.0, t["start_time"] - t["created"])
-        tot["task_wall_time_s"] = {"min": min(durations, default=None), "max": max(durations, default=None),
-                                   "mean": sum(durations) / len(durations) if durations else None}
+                elif st == "running" and t.get("start_time"):
+                    walltime.append(now - t["start_time"])
+
+        def agg(v):
+            return {"min": min(v, default=None), "max": max(v, default=None), "mean": sum(v) / len(v) if v else None}
+
+        tot["task_wall_time_s"] = agg(durations)
+        # the three timing blocks `jobs stats` of the reference prints (/root/reference/convoy/batch.py:2040-2099)
+        tot["job_creation_to_completion_s"] = agg(job_spans)
+        tot["task_end_to_end_s"] = agg(e2e)                       # creation -> end, completed tasks
+        tot["task_command_walltime_s"] = agg(walltime)            # start -> end (or now), running and completed tasks
+        tot["completed_pct_of_total"] = round(100.0 * tot["completed"] / tot["tasks"], 2) if tot["tasks"] else None
+        tot["succeeded_pct_of_completed"] = round(100.0 * tot["succeeded"] / tot["completed"], 2) if tot["completed"] else None
+        tot["failed_pct_of_completed"] = round(100.0 * tot["failed"] / tot["completed"], 2) if tot["completed"] else None
         return tot
 
     # ------------------------------------------------------------------ files
