@@ -354,3 +354,20 @@ def test_job_preparation_runs_once_per_node_even_when_many_tasks_start_in_one_pa
     lines = open(os.path.join(b.node_shared_dir("testpool"), "prep.log")).read().split()
     assert len(lines) == len(set(lines)) <= 3 and len(lines) >= 1          # at most once per node, never twice on the same node
     assert sorted(b.get_job("job1")["prep_nodes"]) == sorted(ln[len("prep-"):] for ln in lines)
+
+
+@pytest.mark.parametrize("fill,expect", [("pack", [4, 0]), ("spread", [2, 2])])
+def test_node_fill_type_places_tasks_pack_or_spread(tmp_path, fill, expect):
+    """Four tasks that start in ONE scheduling pass on a 2-node x 4-slot pool: `pack` fills a node first, `spread` alternates
+    (the per-pass node snapshot must be refreshed after every launch for this to hold)."""
+    from batch_shipyard_b200.backend.agent import NodeAgent
+    cfg, b = make(tmp_path, pool={"vm_count": {"dedicated": 2, "low_priority": 0}, "max_tasks_per_node": 4, "node_fill_type": fill},
+                  tasks=[{"docker_image": "busybox", "command": "sleep 1.5", "task_factory": {"repeat": 4}}])
+    up(cfg, b)
+    submit.add_jobs(b, cfg)
+    agent = NodeAgent(b, "testpool", poll=0.02)
+    agent.tick()                                                       # one pass launches all four
+    per_node = sorted((len(n["running_tasks"]) for n in b.list_nodes("testpool")), reverse=True)
+    assert per_node == expect, per_node
+    agent.run(until_idle=True, max_seconds=60)
+    assert all(t["result"] == "success" for t in b.list_tasks("job1"))
