@@ -149,8 +149,11 @@ def emit(cctx: CliContext, value: Any) -> None:
 def run_action(cctx: CliContext, fn: Callable, *a, **kw) -> Any:
     try:
         out = fn(cctx.ctx, *a, **kw)
-    except (fleet.ActionError, fleet.BackendError, KeyError, ValueError) as e:
-        click.echo(f"ERROR: {e}", err=True)
+    except (KeyError, ValueError, RuntimeError, loader.ConfigError, OSError) as e:
+        # every domain error of the package derives from RuntimeError / ValueError (ActionError, BackendError, FederationError,
+        # RemoteFsError, JobSubmissionError, PoolCreationError, FormulaError, ...): report it like the reference does, no traceback
+        msg = e.args[0] if isinstance(e, KeyError) and e.args else e
+        click.echo(f"ERROR: {msg}", err=True)
         sys.exit(1)
     emit(cctx, out)
     return out

@@ -275,3 +275,35 @@ def test_slurm_helper_node_side_verbs(tmp_path, capsys):
     rc = sl.main(["resume-fail", "--hostfile", str(hf)] + base)
     out = json.loads(capsys.readouterr().out)
     assert rc in (0, 1) and isinstance(out, dict)
+
+
+def test_no_command_leaks_a_traceback(tmp_path, monkeypatch):
+    """Every leaf command, invoked with plausible arguments against a provisioned pool, either succeeds or ends with `ERROR: ...`
+    and exit code 1 — domain errors (unknown federation, missing storage cluster, ...) never surface as Python tracebacks."""
+    import click
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
+    monkeypatch.setenv("SHIPYARD_INLINE_AGENT", "1")
+    monkeypatch.setenv("SHIPYARD_FAKE_GPUS", "8")
+    recipe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "recipes", "mpiBench-OpenMPI", "config")
+    r = CliRunner()
+    assert r.invoke(cli.cli, ["pool", "add", "--configdir", recipe, "--raw", "-y"], obj=cli.CliContext()).exit_code == 0
+    leaves = []
+
+    def walk(g, path):
+        for n, c in g.commands.items():
+            (walk(c, path + [n]) if isinstance(c, click.Group) else leaves.append((path + [n], c)))
+    walk(cli.cli, [])
+    skip = {("pool", "del"), ("pool", "add"), ("jobs", "add"), ("storage", "del"), ("storage", "clear"), ("misc", "tensorboard")}
+    plausible = {"federation_id": "fed1", "storage_cluster_id": "sc1", "name": "sec1", "storage_account": "acct", "path": "cont/x"}
+    leaked = []
+    for path, c in leaves:
+        if tuple(path) in skip:
+            continue
+        args = list(path) + [plausible.get(p.name, "x") for p in c.params if isinstance(p, click.Argument) and p.nargs != -1]
+        res = r.invoke(cli.cli, args + ["--configdir", recipe, "--raw", "-y"], obj=cli.CliContext())
+        if res.exception is not None and not isinstance(res.exception, SystemExit):
+            leaked.append((" ".join(path), repr(res.exception)[:160]))
+        elif res.exit_code not in (0, 1, 2):
+            leaked.append((" ".join(path), f"exit code {res.exit_code}"))
+    assert leaked == [], leaked
+    assert len(leaves) == 105
