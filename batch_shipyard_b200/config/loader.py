@@ -82,7 +82,8 @@ def normalize(kind: ConfigType, data):
     """Rewrite spellings that older releases of the reference accepted (and some of its own recipes still use) into the current
     form before validation.  Today: ``auto_scratch: true`` on a job (recipes/OpenFOAM-*) -> ``{setup: dependency}``."""
     if kind is ConfigType.Jobs and isinstance(data, dict):
-        for job in data.get("job_specifications") or []:
+        jobs = data.get("job_specifications")
+        for job in jobs if isinstance(jobs, list) else []:            # anything else is left for the validator to report
             if isinstance(job, dict) and job.get("auto_scratch") is True:
                 job["auto_scratch"] = {"setup": "dependency"}
             elif isinstance(job, dict) and job.get("auto_scratch") is False:

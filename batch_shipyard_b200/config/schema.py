@@ -124,6 +124,9 @@ def _check(node: Node, val: Any, path: str, errs: list[str]) -> None:
             errs.append(f"{path}: expected a list, got {type(val).__name__}")
             return
         for i, v in enumerate(val):
+            if v is None and node.item.kind != "any":
+                errs.append(f"{path}[{i}]: empty list item")          # `- ` with nothing after it: never meaningful, crashes consumers
+                continue
             _check(node.item, v, f"{path}[{i}]", errs)
     elif node.kind == "map":
         if not isinstance(val, dict):
@@ -137,6 +140,9 @@ def _check(node: Node, val: Any, path: str, errs: list[str]) -> None:
             if ks in node.keys:
                 _check(node.keys[ks][0], v, f"{path}.{ks}", errs)
             elif node.wildcard is not None:
+                if v is None and node.wildcard.kind == "map":
+                    errs.append(f"{path}.{ks}: empty entry (a user-named entry needs its settings)")
+                    continue
                 _check(node.wildcard, v, f"{path}.{ks}", errs)
             else:
                 errs.append(f"{path}.{ks}: unknown key")

@@ -41,6 +41,8 @@ def mpi_settings(spec: Optional[dict]) -> Optional[MpiSettings]:
     if rt not in RUNTIMES:
         raise ValueError(f"mpi.runtime '{rt}' is not one of {list(RUNTIMES)}")
     ppn = spec.get("processes_per_node")
+    if ppn is not None and not isinstance(ppn, (int, str)) or isinstance(ppn, bool):
+        raise ValueError(f"mpi.processes_per_node must be an integer or a command string, not {ppn!r}")
     if isinstance(ppn, str) and ppn.strip().isdigit():
         ppn = int(ppn)
     if isinstance(ppn, int) and ppn < 1:
