@@ -14,3 +14,17 @@ echo "-- per-kernel registers / smem (cuobjdump -res-usage)" >> $out
 for so in gemm coll ops; do
   cuobjdump -res-usage batch_shipyard_b200/_native/libshipyard_$so.so 2>/dev/null | grep -A1 "Function" | grep -vE "^--" | paste - - | sed -E 's/ +/ /g' | cut -c1-260 >> $out
 done
+
+# per-instantiation mnemonic counts of the halo-load kernels (tcgen05 MMA, tiled 4-D TMA halo box, TMEM loads)
+python3 - >> $out <<'PY'
+import re, subprocess
+txt = subprocess.run(["cuobjdump", "-sass", "batch_shipyard_b200/_native/libshipyard_gemm.so"], stdout=subprocess.PIPE, text=True).stdout
+print("\n-- halo-load kernels: tcgen05 / TMA mnemonics per instantiation (validated on B200: conv3x3_halo_kernel<BN, stats, dgrad, pair, 0, 0>)")
+for f in re.split(r"\n\s*Function : ", txt)[1:]:
+    name = f.split("\n", 1)[0].strip()
+    if "halo" not in name:
+        continue
+    cnt = {m: len(re.findall(r"\b" + re.escape(m), f)) for m in ("UTCHMMA", "UTMALDG.4D", "UTMALDG.2D", "UTMALDG.3D", "UTCBAR", "LDTM", "REDG", "SYNCS.PHASECHK")}
+    short = re.sub(r"Ev14CUtensorMap.*", "", re.sub(r"^_Z\d+", "", name))
+    print(f"{short:60s} " + " ".join(f"{k}={v}" for k, v in cnt.items() if v))
+PY
