@@ -262,12 +262,22 @@ class FormulaInterpreter:
             if name == "$NodeDeallocationOption":
                 self.vars[name] = self.toks[2]
                 continue
-            val = self._ternary()
+            try:
+                val = self._ternary()
+            except (TypeError, IndexError, AttributeError, ZeroDivisionError, OverflowError, RecursionError) as e:
+                # a well-tokenised but ill-typed statement (an interval used as a number, a function without arguments, ...)
+                raise FormulaError(f"cannot evaluate {stmt!r}: {e}") from e
             if self.i != len(self.toks):
                 raise FormulaError(f"trailing tokens in: {stmt!r}")
             self.vars[name] = val
         d = self.vars.get("$TargetDedicatedNodes", self.m.current.get("$CurrentDedicatedNodes", 0))
         lp = self.vars.get("$TargetLowPriorityNodes", self.m.current.get("$CurrentLowPriorityNodes", 0))
+        try:
+            d, lp = float(d), float(lp)
+            if d != d or lp != lp or abs(d) == float("inf") or abs(lp) == float("inf"):
+                raise ValueError("not a finite number")
+        except (TypeError, ValueError) as e:
+            raise FormulaError(f"$TargetDedicatedNodes / $TargetLowPriorityNodes must evaluate to finite numbers: {e}") from e
         return AutoscaleResult(max(0, int(float(d))), max(0, int(float(lp))),
                                str(self.vars.get("$NodeDeallocationOption", "requeue")),
                                {k: v for k, v in self.vars.items() if not isinstance(v, (_Interval, list))})

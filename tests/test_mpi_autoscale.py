@@ -95,3 +95,31 @@ def test_calendar_scenarios_and_custom_formula():
         AS.FormulaInterpreter(m, now).run("x = undefined_thing + 1;")
     with pytest.raises(ValueError):
         AS.get_formula(_pool({"name": "active_tasks", "maximum_vm_count": {"dedicated": 0, "low_priority": 0}}))
+
+
+def test_formula_interpreter_fuzz_only_raises_formula_errors():
+    """20 000 random token soups: the interpreter answers or raises FormulaError (a ValueError) — no TypeError / IndexError / hang."""
+    import random
+    import time
+    from batch_shipyard_b200.pool.autoscale import FormulaError, FormulaInterpreter, MetricsWindow
+    rng = random.Random(3)
+    toks = ["$ActiveTasks", "$PendingTasks", "$CurrentDedicatedNodes", "$TargetDedicatedNodes", "$TargetLowPriorityNodes", "$NodeDeallocationOption",
+            "x", "y", "=", "+", "-", "*", "/", "(", ")", "?", ":", "<", ">", "<=", ">=", "==", "!=", "&&", "||", "!", ",", ".", "GetSample",
+            "GetSamplePercent", "(1)", "TimeInterval_Minute", "* 5", "min", "max", "avg", "val", "time", "()", "1", "0", "3.5", "taskcompletion",
+            "t", ".hour", ".weekday", ";", "1e309", "--"]
+    m = MetricsWindow()
+    now = time.time()
+    for i in range(20):
+        m.add("$ActiveTasks", now - 60 * i, i); m.add("$PendingTasks", now - 60 * i, 2 * i)
+    m.current.update({"$CurrentDedicatedNodes": 2, "$CurrentLowPriorityNodes": 0})
+    answered = 0
+    for _ in range(20000):
+        f = " ".join(rng.choice(toks) for _ in range(rng.randint(1, 14)))
+        if rng.random() < 0.5:
+            f = "$TargetDedicatedNodes = " + f
+        try:
+            FormulaInterpreter(m).run(f)
+            answered += 1
+        except (FormulaError, ValueError):
+            pass
+    assert answered > 0
