@@ -439,7 +439,26 @@ def _jobs_cmd(group, name, help_, opts=(), need=(ConfigType.Jobs,)):
             click.option("--dry-run", is_flag=True, help="Validate and show the synthesised tasks without submitting")],
            need=(ConfigType.Jobs, ConfigType.Pool))
 def jobs_add(c, recreate, tail, wait, dry_run):
-    run_action(c, fleet.action_jobs_add, recreate, tail, wait, dry_run)
+    if not tail or c.raw:
+        run_action(c, fleet.action_jobs_add, recreate, tail, wait, dry_run)
+        return
+    # --tail without --raw: stream the file's text as it is (the reference streams the task file to the terminal), then the summary
+    try:
+        out = fleet.action_jobs_add(c.ctx, recreate, tail, wait, dry_run)
+    except (KeyError, ValueError, RuntimeError, OSError) as e:
+        click.echo(f"ERROR: {e}", err=True)
+        sys.exit(1)
+    for jid, rec in out.items():
+        if isinstance(rec, dict):
+            text = rec.pop("tail", None)
+            err = rec.pop("stderr_tail", None)
+            if text is not None:
+                click.echo(f"--- {jid}: {tail} ---")
+                click.echo(text, nl=not str(text).endswith("\n"))
+            if err:
+                click.echo(f"--- {jid}: stderr (tail) ---", err=True)
+                click.echo(err, err=True, nl=not str(err).endswith("\n"))
+    emit(c, out)
 
 
 @_jobs_cmd(jobs, "list", "List jobs", [click.option("--jobid"), click.option("--jobscheduleid")], need=())
