@@ -512,9 +512,15 @@ def action_jobs_tasks_list(ctx: Context, all_jobs=False, jobid=None, poll_until_
             from .jobs.submit import wait_for_tasks
             _kick_agent(ctx, ctx.b.get_job(jid)["pool_id"])
             wait_for_tasks(ctx.b, jid)
+        def iso(ts):
+            return None if not ts else time.strftime("%Y-%m-%dT%H:%M:%S", time.gmtime(ts)) + ("%.3f" % (ts % 1))[1:] + "Z"
+
         out[jid] = [{"task_id": t["id"], "state": t["state"], "result": t.get("result"), "exit_code": t.get("exit_code"),
                      "node_ids": t.get("node_ids"), "retry_count": t.get("retry_count"),
                      "start_time": t.get("start_time"), "end_time": t.get("end_time"),
+                     # the reference prints creation / start / end timestamps and the duration of every task
+                     "created_utc": iso(t.get("created")), "start_time_utc": iso(t.get("start_time")), "end_time_utc": iso(t.get("end_time")),
+                     "duration_s": (round(t["end_time"] - t["start_time"], 3) if t.get("start_time") and t.get("end_time") else None),
                      "multi_instance": bool(t.get("multi_instance")), "command": t.get("command"),
                      "failure_info": t.get("failure_info")}
                     for t in ctx.b.list_tasks(jid) if not taskid or t["id"] == taskid]
