@@ -307,3 +307,25 @@ def test_no_command_leaks_a_traceback(tmp_path, monkeypatch):
             leaked.append((" ".join(path), f"exit code {res.exit_code}"))
     assert leaked == [], leaked
     assert len(leaves) == 105
+
+
+def test_quickstart_guide_example_runs_as_written(tmp_path, monkeypatch):
+    """docs/quickstart.md: the four YAML snippets are split into files exactly as the comments say, then pool add / jobs add --tail."""
+    import re
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "docs", "quickstart.md")).read()
+    block = re.search(r"```yaml\n(# credentials\.yaml.*?)```", doc, flags=re.S).group(1)
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    parts = re.split(r"^# (\w+)\.yaml\n", block, flags=re.M)[1:]
+    names = parts[0::2]
+    assert names == ["credentials", "config", "pool", "jobs"]
+    for name, body in zip(names, parts[1::2]):
+        (cfg / f"{name}.yaml").write_text(body)
+    monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
+    monkeypatch.setenv("SHIPYARD_INLINE_AGENT", "1")
+    monkeypatch.setenv("SHIPYARD_FAKE_GPUS", "2")
+    r = CliRunner()
+    res = r.invoke(cli.cli, ["pool", "add", "--configdir", str(cfg), "-y"], obj=cli.CliContext())
+    assert res.exit_code == 0, res.output
+    res = r.invoke(cli.cli, ["jobs", "add", "--configdir", str(cfg), "--tail", "stdout.txt"], obj=cli.CliContext())
+    assert res.exit_code == 0 and "hello from gpu-" in res.output and "on GPU" in res.output, res.output
