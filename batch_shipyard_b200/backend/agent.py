@@ -447,6 +447,7 @@ def spawn_detached_agent(state_dir: str, pool_id: str, idle_timeout: float = 20.
                           "--pool", pool_id, "--idle-timeout", str(idle_timeout)],
                          stdout=log, stderr=log, stdin=subprocess.DEVNULL, start_new_session=True,
                          cwd=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    log.close()                               # the agent holds its own copy of the descriptor
     return p.pid
 
 

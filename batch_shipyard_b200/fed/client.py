@@ -205,6 +205,7 @@ def proxy_create(b, config: dict, state_dir: str) -> dict:
                          + (["--evaluate-autoscale"] if po.scheduling_after_success_evaluate_autoscale else []),
                          stdout=log, stderr=log, stdin=subprocess.DEVNULL, start_new_session=True,
                          cwd=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    log.close()                               # the daemon holds its own copy of the descriptor
     b.store.insert("service", "fedproxy", "", {"pid": p.pid, "state": "running", "started": time.time(), "log": os.path.join(d, po.log_filename)}, replace=True)
     return proxy_status(b)
 

@@ -63,6 +63,7 @@ def start(b, config: dict) -> dict:
     p = subprocess.Popen([sys.executable, "-m", "batch_shipyard_b200.monitor.exporter", "--state-dir", b.root, "--port", str(port),
                           "--polling-interval", str(ms.resource_polling_interval)], stdout=log, stderr=log, stdin=subprocess.DEVNULL,
                          start_new_session=True, cwd=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    log.close()                               # the exporter holds its own copy of the descriptor
     b.store.insert("service", "monitor", "", {"pid": p.pid, "port": port, "state": "running", "started": time.time(),
                                                "prometheus_port": ms.prometheus_port}, replace=True)
     return status(b)

@@ -4,6 +4,11 @@ Skipped when the reference checkout is not mounted (e.g. on the GPU box)."""
 import os
 import re
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import click
 import pytest
 
@@ -30,7 +35,7 @@ def _ours():
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not mounted")
 def test_every_reference_option_exists_on_the_same_command():
-    src = open(REF).read()
+    src = _read(REF)
     blocks = re.findall(r"@(\w+)\.command\('([\w-]+)'\)(.*?)\ndef (\w+)\(", src, flags=re.S)
     assert len(blocks) == 105
     ours = _ours()
@@ -53,12 +58,12 @@ def test_every_reference_option_exists_on_the_same_command():
 @pytest.mark.skipif(not os.path.exists("/root/reference/docs/20-batch-shipyard-usage.md"), reason="reference checkout not mounted")
 def test_raw_capable_commands_and_environment_variables_of_the_usage_guide_exist():
     """docs/20-batch-shipyard-usage.md lists the ~30 commands that support --raw and the SHIPYARD_* variables of the CLI."""
-    txt = open("/root/reference/docs/20-batch-shipyard-usage.md").read()
+    txt = _read("/root/reference/docs/20-batch-shipyard-usage.md")
     block = txt[txt.index("The following commands support this option:"):txt.index("`--show-config` will output")]
     listed = [tuple(m.split()) for m in re.findall(r"\* `([a-z \-]+)`", block)]
     assert len(listed) >= 30
     ours = _ours()
     assert [c for c in listed if c not in ours] == []
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "batch_shipyard_b200", "cli.py")).read()
-    env = set(re.findall(r"envvar='(SHIPYARD_[A-Z_]+)'", open(REF).read()))
+    env = set(re.findall(r"envvar='(SHIPYARD_[A-Z_]+)'", _read(REF)))
     assert len(env) >= 20 and sorted(e for e in env if e not in src) == []

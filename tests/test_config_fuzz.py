@@ -5,6 +5,11 @@ import copy
 import os
 import random
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import pytest
 import yaml
 
@@ -47,7 +52,7 @@ def _mutate(rng, cfg):
 def test_mutated_recipe_configs_fail_cleanly(recipe, tmp_path):
     rng = random.Random(sum(map(ord, recipe)))
     d = os.path.join(ROOT, "recipes", recipe, "config")
-    datas = {k: yaml.safe_load(open(os.path.join(d, k.value + ".yaml"))) for k in BATCH if os.path.exists(os.path.join(d, k.value + ".yaml"))}
+    datas = {k: yaml.safe_load(_read(os.path.join(d, k.value + ".yaml"))) for k in BATCH if os.path.exists(os.path.join(d, k.value + ".yaml"))}
     crashes = []
     for it in range(120):
         ds = copy.deepcopy(datas)
@@ -80,7 +85,7 @@ def test_mutated_reference_templates_fail_cleanly():
     rng = random.Random(7)
     kinds = {ConfigType.Pool: "pool", ConfigType.Global: "config", ConfigType.Credentials: "credentials", ConfigType.RemoteFS: "fs",
              ConfigType.Slurm: "slurm", ConfigType.Federation: "federation", ConfigType.Monitor: "monitor"}
-    datas = {k: yaml.safe_load(open(f"/root/reference/config_templates/{v}.yaml")) for k, v in kinds.items()}
+    datas = {k: yaml.safe_load(_read(f"/root/reference/config_templates/{v}.yaml")) for k, v in kinds.items()}
     crashes = []
     for _ in range(500):
         ds = copy.deepcopy(datas)

@@ -2,6 +2,11 @@
 import json
 import os
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import pytest
 from click.testing import CliRunner
 
@@ -214,10 +219,10 @@ def test_generated_docs_are_current():
     import os
     from batch_shipyard_b200 import cli
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    text = open(os.path.join(root, "docs", "cli.md")).read()
+    text = _read(os.path.join(root, "docs", "cli.md"))
     missing = [c for c in cli.leaf_commands() if f"### `shipyard {c}`" not in text]
     assert not missing, missing
-    cfg = open(os.path.join(root, "docs", "configuration.md")).read()
+    cfg = _read(os.path.join(root, "docs", "configuration.md"))
     for section in ("config.yaml", "credentials.yaml", "pool.yaml", "jobs.yaml", "fs.yaml", "federation.yaml", "monitor.yaml", "slurm.yaml"):
         assert f"## {section}" in cfg
 
@@ -324,8 +329,14 @@ def test_quickstart_guide_example_runs_as_written(tmp_path, monkeypatch):
     monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
     monkeypatch.setenv("SHIPYARD_INLINE_AGENT", "1")
     monkeypatch.setenv("SHIPYARD_FAKE_GPUS", "2")
-    r = CliRunner()
-    res = r.invoke(cli.cli, ["pool", "add", "--configdir", str(cfg), "-y"], obj=cli.CliContext())
-    assert res.exit_code == 0, res.output
-    res = r.invoke(cli.cli, ["jobs", "add", "--configdir", str(cfg), "--tail", "stdout.txt"], obj=cli.CliContext())
-    assert res.exit_code == 0 and "hello from gpu-" in res.output and "on GPU" in res.output, res.output
+    from batch_shipyard_b200.pool import topology
+    topology.probe(refresh=True)                       # the probe result is cached per process: re-read it under the fake-GPU setting
+    try:
+        r = CliRunner()
+        res = r.invoke(cli.cli, ["pool", "add", "--configdir", str(cfg), "-y"], obj=cli.CliContext())
+        assert res.exit_code == 0, res.output
+        res = r.invoke(cli.cli, ["jobs", "add", "--configdir", str(cfg), "--tail", "stdout.txt"], obj=cli.CliContext())
+        assert res.exit_code == 0 and "hello from gpu-" in res.output and "on GPU" in res.output, res.output
+    finally:
+        monkeypatch.delenv("SHIPYARD_FAKE_GPUS")
+        topology.probe(refresh=True)

@@ -5,6 +5,11 @@ Two examples contain typos that the reference's own schema rejects as well (`pol
 import os
 import re
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import pytest
 import yaml
 
@@ -31,7 +36,7 @@ def _strip_doc_typos(ct, data):
 @pytest.mark.skipif(not os.path.isdir(DOCS), reason="reference checkout not mounted")
 @pytest.mark.parametrize("doc,ct,roots", CASES, ids=[c[0][:2] for c in CASES])
 def test_reference_guide_examples_validate(doc, ct, roots):
-    blocks = re.findall(r"```yaml\n(.*?)```", open(os.path.join(DOCS, doc)).read(), flags=re.S)
+    blocks = re.findall(r"```yaml\n(.*?)```", _read(os.path.join(DOCS, doc)), flags=re.S)
     n = 0
     for b in blocks:
         try:

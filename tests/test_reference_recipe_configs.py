@@ -3,6 +3,11 @@ normalisation + strict validation unchanged — what a user gets when pointing `
 Skipped when the reference is not mounted."""
 import os
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import pytest
 import yaml
 
@@ -32,7 +37,7 @@ def test_all_reference_recipe_configs_validate():
     for p in files:
         kind = KINDS[os.path.splitext(os.path.basename(p))[0]]
         try:
-            validate(kind, loader.normalize(kind, yaml.safe_load(open(p))), source=p)
+            validate(kind, loader.normalize(kind, yaml.safe_load(_read(p))), source=p)
         except Exception as e:  # noqa: BLE001
             problems.append((os.path.relpath(p, ROOT), str(e)[:300]))
     assert problems == [], problems

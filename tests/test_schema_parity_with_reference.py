@@ -3,6 +3,11 @@
 Only key NAMES and nesting are compared (our notation for types / enums is different on purpose).  Skipped without the reference."""
 import os
 
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
 import pytest
 import yaml
 
@@ -42,8 +47,8 @@ def _our_paths(node, prefix=""):
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not mounted")
 @pytest.mark.parametrize("name", ["credentials", "config", "pool", "jobs", "fs", "monitor", "federation", "slurm"])
 def test_reference_schema_keys_are_accepted(name):
-    ref = _ref_paths(yaml.safe_load(open(os.path.join(REF, name + ".yaml"))))
-    ours = _our_paths(yaml.safe_load(open(os.path.join(OURS, name + ".yaml"))))
+    ref = _ref_paths(yaml.safe_load(_read(os.path.join(REF, name + ".yaml"))))
+    ours = _our_paths(yaml.safe_load(_read(os.path.join(OURS, name + ".yaml"))))
 
     def covered(p):                                   # a named key of the reference may be served by a "*" (any key) entry of ours
         parts = p.split(".")
@@ -93,8 +98,8 @@ def _our_specs(node, prefix="", out=None):
 def test_reference_enums_are_enums_here_with_at_least_the_same_values(name):
     """Where the reference restricts a key to an enumeration, so do we (strictness parity), and every reference value is accepted."""
     import re
-    ref = _ref_enums(yaml.safe_load(open(os.path.join(REF, name + ".yaml"))))
-    ours = _our_specs(yaml.safe_load(open(os.path.join(OURS, name + ".yaml"))))
+    ref = _ref_enums(yaml.safe_load(_read(os.path.join(REF, name + ".yaml"))))
+    ours = _our_specs(yaml.safe_load(_read(os.path.join(OURS, name + ".yaml"))))
     problems = []
     for path, values in ref.items():
         parts = path.split(".")
