@@ -59,6 +59,16 @@ def storage_root(state_dir: str, link: str) -> str:
     return os.path.join(state_dir, "storage", link)
 
 
+def remote_path(root: str, remote: str) -> str:
+    """`container/prefix` inside a storage root; a path that climbs out of the root (`..`) is refused — a storage account is a
+    directory here, and a job file must not be able to read or overwrite the rest of the box through it."""
+    p = os.path.normpath(os.path.join(root, remote.strip("/")))
+    base = os.path.normpath(root)
+    if p != base and not p.startswith(base + os.sep):
+        raise ValueError(f"remote path '{remote}' leaves the storage account directory")
+    return p
+
+
 def _log(name: str, msg: str) -> None:
     try:
         with open(os.path.join(os.environ.get("AZ_BATCH_TASK_DIR", "."), f"blobxfer-{name}.log"), "a") as f:
@@ -96,7 +106,11 @@ def main(argv=None) -> int:
             os.chmod(a.dest, int(str(a.mode), 8))
         return 0
     if a.cmd == "ingress":
-        src = os.path.join(storage_root(a.state_dir, a.link), a.remote.strip("/"))
+        try:
+            src = remote_path(storage_root(a.state_dir, a.link), a.remote)
+        except ValueError as e:
+            print(f"mover: {e}", file=sys.stderr)
+            return 1
         if not os.path.exists(src):
             print(f"mover: ingress source {src} does not exist", file=sys.stderr)
             return 1
@@ -109,7 +123,11 @@ def main(argv=None) -> int:
         if not want:
             _log("upload", f"egress skipped: condition {a.condition} not met (result={result})")
             return 0
-        dst = os.path.join(storage_root(a.state_dir, a.link), a.remote.strip("/"))
+        try:
+            dst = remote_path(storage_root(a.state_dir, a.link), a.remote)
+        except ValueError as e:
+            print(f"mover: {e}", file=sys.stderr)
+            return 1
         n, nb = copy_tree(a.local, dst, a.include, a.exclude + ["*.spec", ".shipyard.envlist", ".heartbeat"])
         _log("upload", f"egress {a.local} -> {a.link}:{a.remote}: {n} files, {nb} bytes")
         return 0

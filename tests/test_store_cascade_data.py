@@ -171,3 +171,26 @@ def test_perfgraph_coalesces_intervals(tmp_path):
     dat, gp = perfgraph.render_gnuplot(tl, str(tmp_path / "tl"))
     assert open(dat).read().count("\n") == 3 and "boxxyerrorbars" in open(gp).read()
     assert perfgraph.main(["--state-dir", str(tmp_path / "state"), "--pool", "p", "--format", "json"]) == 0
+
+
+def test_mover_refuses_remote_paths_that_leave_the_storage_root(tmp_path, capsys):
+    from batch_shipyard_b200.data import mover
+    sd = str(tmp_path / "state")
+    root = mover.storage_root(sd, "acct")
+    os.makedirs(os.path.join(root, "cont"), exist_ok=True)
+    with open(os.path.join(root, "cont", "a.txt"), "w") as f:
+        f.write("x")
+    secret = tmp_path / "secret.txt"
+    secret.write_text("s")
+    assert mover.remote_path(root, "cont/sub") == os.path.join(root, "cont", "sub")
+    assert mover.main(["ingress", "--state-dir", sd, "--link", "acct", "--remote", "cont", "--local", str(tmp_path / "in")]) == 0
+    assert (tmp_path / "in" / "a.txt").read_text() == "x"
+    rel = os.path.relpath(str(tmp_path), root)                                    # ../../.. up to the directory holding secret.txt
+    assert mover.main(["ingress", "--state-dir", sd, "--link", "acct", "--remote", rel, "--local", str(tmp_path / "leak")]) == 1
+    assert not (tmp_path / "leak").exists() and "leaves the storage account" in capsys.readouterr().err
+    os.environ["SHIPYARD_TASK_RESULT"] = "success"
+    try:
+        assert mover.main(["egress", "--state-dir", sd, "--link", "acct", "--remote", "../outside", "--local", str(tmp_path / "in")]) == 1
+    finally:
+        os.environ.pop("SHIPYARD_TASK_RESULT", None)
+    assert not os.path.exists(os.path.join(os.path.dirname(root), "outside"))
