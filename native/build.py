@@ -59,6 +59,7 @@ TARGETS = {
     "gpuprobe": ("nvcc-exe", "shipyard-gpuprobe", ["probe/gpuprobe.cpp"], [], ["-ldl"]),
     "mpibench": ("nvcc-exe", "shipyard-mpibench", ["bench/mpibench.cpp"],
                  ["-I", os.path.join(NATIVE, "include")], []),
+    "diskbench": ("cxx-exe", "shipyard-diskbench", ["bench/diskbench.cpp"], [], ["-lpthread"]),
 }
 # link-time dependencies between our own libraries
 DEPS = {"preload": ["coll"], "mpi": ["coll"], "mpibench": ["mpi"]}
@@ -137,7 +138,7 @@ def build_target(name: str, force: bool = False) -> str:
 
 
 def build_all(names: list[str] | None = None, force: bool = False, quiet: bool = False) -> None:
-    order = ["coll", "preload", "mpi", "gemm", "ops", "stage", "taskrun", "gpuprobe", "mpibench"]
+    order = ["coll", "preload", "mpi", "gemm", "ops", "stage", "taskrun", "gpuprobe", "mpibench", "diskbench"]
     names = names or order
     for n in order:
         if n in names:

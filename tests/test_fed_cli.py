@@ -289,6 +289,7 @@ def test_no_command_leaks_a_traceback(tmp_path, monkeypatch):
     monkeypatch.setenv("SHIPYARD_STATE_DIR", str(tmp_path / "state"))
     monkeypatch.setenv("SHIPYARD_INLINE_AGENT", "1")
     monkeypatch.setenv("SHIPYARD_FAKE_GPUS", "8")
+    monkeypatch.chdir(tmp_path)                                   # `cert create` & co. write relative to the working directory
     recipe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "recipes", "mpiBench-OpenMPI", "config")
     r = CliRunner()
     assert r.invoke(cli.cli, ["pool", "add", "--configdir", recipe, "--raw", "-y"], obj=cli.CliContext()).exit_code == 0
