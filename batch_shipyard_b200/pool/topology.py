@@ -20,8 +20,13 @@ def probe(refresh: bool = False) -> dict:
     global _CACHE
     if _CACHE is not None and not refresh:
         return _CACHE
-    from .._build import native_dir
+    from .._build import ensure_built, native_dir
     exe = os.path.join(native_dir(), "shipyard-gpuprobe")
+    if not os.path.exists(exe) and not os.environ.get("SHIPYARD_FAKE_GPUS"):
+        try:
+            ensure_built(["gpuprobe"])                                # built artefacts are not in the history; a checkout probes on first use
+        except Exception:  # noqa: BLE001 - no compiler: reported as "probe not built" below
+            pass
     info = {"gpus": [], "driver_version": 0, "runtime_version": 0, "error": "probe not built", "nvml": False}
     if os.environ.get("SHIPYARD_FAKE_GPUS"):
         n = int(os.environ["SHIPYARD_FAKE_GPUS"])

@@ -1,7 +1,7 @@
 """Packaging: `pip install -e .` builds the sm_100a native libraries in-tree first (native/build.py drives nvcc/g++).
 
 Reference counterpart: install.sh + Dockerfiles (/root/reference/install.sh:1-359) only set up a Python venv;
-here the native runtime (collectives, GEMM, fused ops, stager, task runner, probe, mpibench) is part of the package.
+here the native runtime (collectives, GEMM, fused ops, stager, task runner, probe, mpibench, diskbench) is part of the package.
 """
 import importlib.util
 import os
