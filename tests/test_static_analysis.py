@@ -3,6 +3,7 @@ its shell scripts (/root/reference/.travis.yml:17-20, appveyor.yml:57-61; SURVEY
 the F-class checks that matter (syntax, unused imports, redefinitions, `except:` without a class, mutable default arguments) are
 done with `ast`, shell scripts go through `bash -n`, and every YAML / JSON file in the tree must parse."""
 import ast
+import builtins
 import json
 import os
 import subprocess
@@ -80,6 +81,51 @@ def test_no_redefinitions_bare_excepts_or_mutable_defaults():
                     if isinstance(d, (ast.List, ast.Dict, ast.Set)):
                         bad.append(f"{rel}:{d.lineno}: mutable default argument")
     assert bad == [], "\n".join(bad)
+
+
+def _bound_names(tree):
+    b = set(dir(builtins)) | {"__file__", "__name__", "__doc__", "__builtins__", "__spec__", "__path__", "__class__"}
+    for n in ast.walk(tree):
+        if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+            b.add(n.name)
+        if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef, ast.Lambda)):
+            a = n.args
+            for x in a.posonlyargs + a.args + a.kwonlyargs + ([a.vararg] if a.vararg else []) + ([a.kwarg] if a.kwarg else []):
+                b.add(x.arg)
+        elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+            b.add(n.id)
+        elif isinstance(n, ast.Import):
+            b.update((x.asname or x.name).split(".")[0] for x in n.names)
+        elif isinstance(n, ast.ImportFrom):
+            b.update(x.asname or x.name for x in n.names)
+        elif isinstance(n, ast.ExceptHandler) and n.name:
+            b.add(n.name)
+        elif isinstance(n, (ast.Global, ast.Nonlocal)):
+            b.update(n.names)
+        elif isinstance(n, ast.MatchAs) and n.name:
+            b.add(n.name)
+    return b
+
+
+def test_no_undefined_names():
+    """flake8 F821, scope-insensitive: a name that is read somewhere in a module must be bound somewhere in that module (or be a
+    builtin) - catches the NameError hiding in a branch no test walks through."""
+    bad = []
+    for p in PY:
+        _, tree = _tree(p)
+        if any(isinstance(n, ast.ImportFrom) and any(a.name == "*" for a in n.names) for n in ast.walk(tree)):
+            continue
+        bound = _bound_names(tree)
+        bad += [f"{os.path.relpath(p, ROOT)}:{n.lineno}: undefined name '{n.id}'" for n in ast.walk(tree)
+                if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in bound]
+    assert bad == [], "\n".join(bad)
+
+
+def test_the_checks_themselves_fire_on_a_bad_module():
+    tree = ast.parse("import os\ndef f(a=[]):\n    try:\n        return undefined_thing\n    except:\n        pass\n")
+    assert "undefined_thing" not in _bound_names(tree) and "os" in _bound_names(tree)
+    assert any(isinstance(n, ast.ExceptHandler) and n.type is None for n in ast.walk(tree))
+    assert any(isinstance(d, ast.List) for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) for d in n.args.defaults)
 
 
 def test_shell_scripts_pass_bash_syntax_check():
