@@ -17,12 +17,13 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 import uuid
 from typing import Optional
 
 from ..state.store import NotFound
-from .local import BackendError, LocalBackend, _now
+from .local import BackendError, LocalBackend, _now, pid_alive, proc_start_ticks
 from . import runspec
 
 LEASE_S = 15.0
@@ -37,6 +38,7 @@ class NodeAgent:
         self._last_autoscale = 0.0
         self._last_sample = 0.0
         self.metrics = None
+        self.lease_lost = False
 
     # ------------------------------------------------------------------ lease
     def acquire(self) -> bool:
@@ -46,15 +48,45 @@ class NodeAgent:
         self.b.store.release_lease(self.lease_name, self.holder)
 
     # ------------------------------------------------------------------ main loop
+    def _lease_keeper(self, stop: threading.Event) -> None:
+        """Renew the pool lease from a thread of its own: job preparation / release commands run synchronously inside the scheduling
+        loop and may take longer than the lease; losing it silently would let a second agent schedule the same tasks."""
+        from ..state.store import Store
+        st = Store(self.b.store.root)          # sqlite connections are per thread
+        while not stop.wait(LEASE_S / 3.0):
+            try:
+                ok = st.renew_lease(self.lease_name, self.holder, LEASE_S) or st.acquire_lease(self.lease_name, self.holder, LEASE_S)
+            except Exception:  # noqa: BLE001 - a locked database is retried on the next beat
+                continue
+            if not ok:
+                self.lease_lost = True
+                return
+
+    def _ensure_lease(self) -> bool:
+        """Renew (or re-acquire after an expiry nobody used); False means another agent owns the pool now."""
+        if self.lease_lost:
+            return False
+        st = self.b.store
+        if st.renew_lease(self.lease_name, self.holder, LEASE_S) or st.acquire_lease(self.lease_name, self.holder, LEASE_S):
+            return True
+        self.lease_lost = True
+        return False
+
     def run(self, until_idle: bool = True, idle_timeout: float = 0.0, max_seconds: Optional[float] = None) -> None:
         if not self.acquire():
             raise BackendError(f"another agent holds pool {self.pool_id}")
         t0, idle_since = time.time(), None
+        stop = threading.Event()
+        keeper = threading.Thread(target=self._lease_keeper, args=(stop,), daemon=True, name="lease-keeper")
+        keeper.start()
         try:
             self.recover_orphans()
             while True:
+                if not self._ensure_lease():
+                    # single-agent guarantee lost (lease expired and somebody else took it): stop scheduling.  The runners this agent
+                    # started keep running; the new owner adopts them through recover_orphans().
+                    raise BackendError(f"agent {self.holder} lost the lease of pool {self.pool_id}; another agent took over")
                 progressed = self.tick()
-                self.b.store.renew_lease(self.lease_name, self.holder, LEASE_S)
                 busy = bool(self.procs) or progressed
                 if busy:
                     idle_since = None
@@ -69,6 +101,8 @@ class NodeAgent:
                     return
                 time.sleep(self.poll if busy else max(self.poll, 0.1))
         finally:
+            stop.set()
+            keeper.join(timeout=2.0)
             self.release()
 
     def has_pending_work(self) -> bool:
@@ -96,6 +130,7 @@ class NodeAgent:
         except BackendError:
             return False
         progressed = self._reap()
+        progressed |= self._sweep_stale_slots()
         progressed |= self._run_schedules()
         progressed |= self._finish_jobs()
         progressed |= self._schedule()
@@ -110,15 +145,31 @@ class NodeAgent:
             if rc is None:
                 continue
             del self.procs[key]
-            self._complete(key[0], key[1], rc)
+            self._complete(key[0], key[1], None if rc == _AdoptedProc.EXIT_UNKNOWN else rc)
             progressed = True
         return progressed
 
-    def _complete(self, job_id: str, task_id: str, rc: int) -> None:
+    def _sweep_stale_slots(self) -> bool:
+        """Node slots whose task row no longer exists (deleted while running) or is not running any more and has no runner here."""
+        swept = False
+        for n in self.b.list_nodes(self.pool_id):
+            for jt in list(n.get("running_tasks") or []):
+                j, t = jt[0], jt[1]
+                if (j, t) in self.procs:
+                    continue
+                row = self.b.store.try_get("task", j, t)
+                if row is None or row.get("state") not in ("running", "preparing"):
+                    swept |= self.b.release_task_slots(self.pool_id, j, t, ok=False) > 0
+        return swept
+
+    def _complete(self, job_id: str, task_id: str, rc: Optional[int]) -> None:
+        """`rc` is the runner's wait status, or None when it is unknown (adopted runner that disappeared)."""
         try:
             t = self.b.get_task(job_id, task_id)
             job = self.b.get_job(job_id)
         except BackendError:
+            # the task or job row was deleted while the runner was alive: the slots must still come back
+            self.b.release_task_slots(self.pool_id, job_id, task_id, ok=False)
             return
         tdir = self.b.task_dir(job["pool_id"], job_id, task_id)
         result = None
@@ -127,6 +178,14 @@ class NodeAgent:
                 result = json.load(f)
         except Exception:  # noqa: BLE001 - runner died before writing the result
             result = None
+        if result is None and rc is None and not t.get("terminate_requested"):
+            # an adopted runner vanished without a result (SIGKILL, OOM): its exit status is unknowable, so the task did NOT
+            # succeed.  Same treatment as recover_orphans(): free the slots and run it again.
+            for nid in t.get("node_ids") or []:
+                self._release_slot(nid, job_id, task_id, False)
+            self.b.update_task(job_id, task_id, state="active", pid=None, pid_start=None, node_ids=[],
+                               requeue_count=int(t.get("requeue_count") or 0) + 1, last_exit_code=None)
+            return
         exit_code = result["exit_code"] if result else (rc if rc is not None else -1)
         for nid in t.get("node_ids") or []:
             self._release_slot(nid, job_id, task_id, exit_code == 0)
@@ -181,6 +240,8 @@ class NodeAgent:
             if job["state"] == "active" and job.get("auto_complete"):
                 tasks = self.b.list_tasks(jid)
                 if tasks and all(t["state"] == "completed" for t in tasks):
+                    if not job.get("job_release"):
+                        self.b.clean_mi_containers(jid)
                     self.b.set_job_state(jid, "terminating" if job.get("job_release") else "completed",
                                          terminate_reason="AllTasksComplete")
                     progressed = True
@@ -192,6 +253,7 @@ class NodeAgent:
                     for nid in job.get("prep_nodes") or []:
                         self._run_aux(job, "jobrelease", job["job_release"]["command"], nid)
                     self.b.update_job(jid, release_done=True)
+                self.b.clean_mi_containers(jid)        # job release also removes the daemonised coordination "containers"
                 self.b.set_job_state(jid, "completed")
                 progressed = True
         return progressed
@@ -204,7 +266,9 @@ class NodeAgent:
         except BackendError:
             node = {"id": node_id, "gpu_index": None, "dedicated": True}
         spec, tdir = runspec.build_aux_spec(self.b, pool, job, kind, command, node)
-        rc = subprocess.call([runspec.runner_path(), "--spec", spec], cwd=tdir)
+        self._ensure_lease()
+        rc = subprocess.call([runspec.runner_path(), "--spec", spec], cwd=tdir)      # the lease keeper thread renews meanwhile
+        self._ensure_lease()
         return rc
 
     # -- dependencies ------------------------------------------------------------------
@@ -307,8 +371,8 @@ class NodeAgent:
         p = subprocess.Popen([runspec.runner_path(), "--spec", spec], cwd=tdir, env=env,
                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, start_new_session=True)
         self.procs[(jid, tid)] = p
-        self.b.update_task(jid, tid, state="running", pid=p.pid, node_ids=[n["id"] for n in nodes],
-                           start_time=_now(), agent=self.holder)
+        self.b.update_task(jid, tid, state="running", pid=p.pid, pid_start=proc_start_ticks(p.pid),
+                           node_ids=[n["id"] for n in nodes], start_time=_now(), agent=self.holder)
         return True
 
     # -- crash recovery ---------------------------------------------------------------------
@@ -320,14 +384,8 @@ class NodeAgent:
                 if t["state"] not in ("running", "preparing") or (job["id"], t["id"]) in self.procs:
                     continue
                 pid = t.get("pid")
-                alive = False
-                if pid:
-                    try:
-                        os.kill(int(pid), 0); alive = True
-                    except (ProcessLookupError, PermissionError):
-                        alive = False
-                if alive:
-                    self.procs[(job["id"], t["id"])] = _AdoptedProc(int(pid))
+                if pid and pid_alive(pid, t.get("pid_start")):
+                    self.procs[(job["id"], t["id"])] = _AdoptedProc(int(pid), t.get("pid_start"))
                     continue
                 tdir = self.b.task_dir(job["pool_id"], job["id"], t["id"])
                 if os.path.exists(os.path.join(tdir, "result.json")):
@@ -419,19 +477,15 @@ class NodeAgent:
 
 
 class _AdoptedProc:
-    """poll()-compatible handle for a runner started by a previous agent process."""
+    """poll()-compatible handle for a runner started by a previous agent process.  It is not our child, so its exit status cannot
+    be read: poll() returns None while it runs and EXIT_UNKNOWN afterwards; result.json is then the only source of truth."""
+    EXIT_UNKNOWN = "unknown"
 
-    def __init__(self, pid: int):
-        self.pid = pid
+    def __init__(self, pid: int, start_ticks=None):
+        self.pid, self.start_ticks = pid, start_ticks
 
     def poll(self):
-        try:
-            os.kill(self.pid, 0)
-            return None
-        except ProcessLookupError:
-            return 0
-        except PermissionError:
-            return None
+        return None if pid_alive(self.pid, self.start_ticks) else self.EXIT_UNKNOWN
 
 
 def spawn_detached_agent(state_dir: str, pool_id: str, idle_timeout: float = 20.0) -> Optional[int]:

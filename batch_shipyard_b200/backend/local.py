@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import datetime
 import os
+import re
 import shutil
 import signal
 import time
@@ -32,6 +33,40 @@ MAX_REBOOT_RETRIES = 5
 
 class BackendError(RuntimeError):
     pass
+
+
+# Azure Batch enforces this server-side (the reference never had to); here ids become directory names and shell words, so the
+# backend is the gate: /root/reference/convoy/batch.py hands ids straight to the service, which rejects anything else.
+_ID_RE = re.compile(r"^[A-Za-z0-9_-]{1,64}$")
+
+
+def validate_id(kind: str, value) -> str:
+    if not isinstance(value, str) or not _ID_RE.match(value):
+        raise BackendError(f"invalid {kind} id {value!r}: must match [A-Za-z0-9_-]{{1,64}}")
+    return value
+
+
+def proc_start_ticks(pid: int):
+    """Kernel start time of `pid` (field 22 of /proc/<pid>/stat) or None: guards pid liveness checks against pid reuse."""
+    try:
+        with open(f"/proc/{int(pid)}/stat") as f:
+            st = f.read()
+        return int(st[st.rindex(")") + 2:].split()[19])
+    except (OSError, ValueError, IndexError):
+        return None
+
+
+def pid_alive(pid, start_ticks=None) -> bool:
+    """True while the process exists, is not a zombie and (when known) is still the process we started."""
+    try:
+        with open(f"/proc/{int(pid)}/stat") as f:
+            st = f.read()
+        fields = st[st.rindex(")") + 2:].split()
+        if fields[0] in ("Z", "X"):
+            return False
+        return start_ticks is None or int(fields[19]) == int(start_ticks)
+    except (OSError, ValueError, IndexError, TypeError):
+        return False
 
 
 def _now() -> float:
@@ -85,6 +120,7 @@ class LocalBackend:
     def create_pool(self, ps: S.PoolSettings, gpus: Optional[list] = None, total_nodes: Optional[int] = None,
                     metadata: Optional[dict] = None) -> dict:
         """Create the pool object and its nodes in state ``creating`` (provisioning is the provisioner's job)."""
+        validate_id("pool", ps.id)
         if self.pool_exists(ps.id):
             raise BackendError(f"pool {ps.id} already exists")
         gpus = list(gpus) if gpus is not None else []
@@ -167,6 +203,7 @@ class LocalBackend:
                 "current_low_priority": sum(1 for n in nodes if not n["dedicated"])}
 
     def delete_pool(self, pool_id: str) -> None:
+        validate_id("pool", pool_id)
         self.get_pool(pool_id)
         for j in self.list_jobs(pool_id=pool_id):
             if j["state"] not in ("completed", "deleting"):
@@ -268,6 +305,13 @@ class LocalBackend:
         return [j for j in jobs if pool_id is None or j.get("pool_id") == pool_id]
 
     def add_job(self, job: dict) -> dict:
+        jid = job.get("id")
+        if job.get("schedule_id") and isinstance(jid, str) and jid.startswith(job["schedule_id"] + ":job-"):
+            validate_id("job schedule", job["schedule_id"])          # "<schedule id>:job-<n>", generated by the agent
+            if not jid[len(job["schedule_id"]) + 5:].isdigit():
+                raise BackendError(f"invalid job id {jid!r}")
+        else:
+            validate_id("job", jid)
         pool = self.get_pool(job["pool_id"])
         from ..utils.versions import check_metadata_compat
         check_metadata_compat(pool.get("metadata", {}))
@@ -296,12 +340,76 @@ class LocalBackend:
         for t in self.list_tasks(job_id):
             if t["state"] != "completed":
                 self.terminate_task(job_id, t["id"], reason="job terminated")
-        self.set_job_state(job_id, "terminating" if job.get("job_release") and not job.get("release_done") else "completed",
-                           terminate_reason=reason)
+        to_release = bool(job.get("job_release")) and not job.get("release_done")
+        if not to_release:
+            self.clean_mi_containers(job_id)          # otherwise the agent does it after the job release command
+        self.set_job_state(job_id, "terminating" if to_release else "completed", terminate_reason=reason)
+
+    # ------------------------------------------------------------------ named "containers"
+    @staticmethod
+    def _session_pids(sid: int) -> list[int]:
+        out = []
+        for d in os.listdir("/proc"):
+            if not d.isdigit():
+                continue
+            try:
+                with open(f"/proc/{d}/stat") as f:
+                    st = f.read()
+                if int(st[st.rindex(")") + 2:].split()[3]) == sid:
+                    out.append(int(d))
+            except (OSError, ValueError, IndexError):
+                continue
+        return out
+
+    def clean_mi_containers(self, job_id: str) -> list[str]:
+        """Kill what the multi-instance coordination commands of a job left running (the `docker run -d` containers the reference
+        removes in job release / `jobs cmi`, /root/reference/convoy/batch.py:2322-2380, 5329-5334).  The runner records the session
+        id of every coordination command under <pool>/containers/<name>.coord; returns the names cleaned."""
+        try:
+            job = self.get_job(job_id)
+        except BackendError:
+            return []
+        cdir = os.path.join(self.pool_root(job["pool_id"]), "containers")
+        cleaned = []
+        for t in self.list_tasks(job_id):
+            if not t.get("multi_instance"):
+                continue
+            name = re.sub(r"[^A-Za-z0-9_.-]", "_", str((t.get("sandbox") or {}).get("name") or t["id"]))[:128]
+            path = os.path.join(cdir, name + ".coord")
+            try:
+                with open(path) as f:
+                    sids = [int(x) for x in f.read().split()]
+            except (OSError, ValueError):
+                continue
+            for sid in sids:
+                for sig in (signal.SIGTERM, signal.SIGKILL):
+                    pids = [p for p in self._session_pids(sid) if p != os.getpid()]
+                    if not pids:
+                        break
+                    for p in pids:
+                        try:
+                            os.kill(p, sig)
+                        except (ProcessLookupError, PermissionError):
+                            pass
+                    time.sleep(0.05)
+            try:
+                os.remove(path)
+            except OSError:
+                pass
+            cleaned.append(name)
+        return cleaned
 
     def delete_job(self, job_id: str) -> None:
+        """Terminate, wait for the runners to exit, give the node slots back, then drop rows and files (in that order: the agent
+        finalises a task through its row, so rows may only disappear once nothing is running any more)."""
         job = self.get_job(job_id)
-        self.terminate_job(job_id, reason="job deleted")
+        self.set_job_state(job_id, "deleting")
+        for t in self.list_tasks(job_id):
+            if t["state"] != "completed":
+                self.terminate_task(job_id, t["id"], reason="job deleted")
+        for t in self.list_tasks(job_id):
+            self._reap_task_runner(job, t)
+        self.clean_mi_containers(job_id)
         self.store.delete("task", job_id)
         self.store.delete("job", job_id, "")
         shutil.rmtree(os.path.dirname(self.job_dir(job["pool_id"], job_id)), ignore_errors=True)
@@ -349,6 +457,7 @@ class LocalBackend:
                        "exit_code": None, "result": None, "node_ids": [], "start_time": None, "end_time": None,
                        "pid": None, "failure_info": None, "requeue_count": 0}
                 rec.update(t)
+                validate_id("task", rec.get("id"))
                 if rec["id"] in seen:
                     raise BackendError(f"task {rec['id']} already exists in job {job_id}")
                 seen.add(rec["id"])
@@ -387,15 +496,22 @@ class LocalBackend:
 
     def terminate_task(self, job_id: str, task_id: str, reason: str = "terminated", requeue: bool = False,
                        force: bool = False) -> None:
+        """SIGTERM to the runner, which tears its ranks down (SIGTERM, 5 s, SIGKILL per rank process group), runs the epilogue and
+        writes result.json.  The runner itself is never SIGKILLed here: its ranks live in their own process groups and would survive
+        it.  ``force`` (the reference's `docker kill` side channel, /root/reference/convoy/batch.py:2722-2742) additionally SIGKILLs
+        the rank process groups right away instead of waiting for the runner's 5 s grace period."""
         t = self.get_task(job_id, task_id)
         if t["state"] == "completed":
             return
         pid = t.get("pid")
         if t["state"] in ("running", "preparing") and pid:
-            try:
-                os.kill(int(pid), signal.SIGKILL if force else signal.SIGTERM)   # runner reaps its ranks
-            except (ProcessLookupError, PermissionError):
-                pass
+            if pid_alive(pid, t.get("pid_start")):
+                try:
+                    os.kill(int(pid), signal.SIGTERM)
+                except (ProcessLookupError, PermissionError):
+                    pass
+                if force:
+                    self._kill_rank_groups(self.get_job(job_id), t)
             self.update_task(job_id, task_id, terminate_requested=True, terminate_reason=reason, requeue_on_exit=requeue)
             return
         if requeue:
@@ -404,11 +520,66 @@ class LocalBackend:
             self.update_task(job_id, task_id, state="completed", result="failure", exit_code=None, end_time=_now(),
                              failure_info={"category": "usererror", "code": "TaskEnded", "message": reason})
 
+    def release_task_slots(self, pool_id: str, job_id: str, task_id: str, ok: bool = False) -> int:
+        """Remove [job, task] from every node of the pool that lists it (idempotent); returns the number of slots released."""
+        released = 0
+        for n in self.store.query("node", pool_id):
+            if not any(list(x) == [job_id, task_id] for x in n.get("running_tasks") or []):
+                continue
+
+            def fn(x):
+                x["running_tasks"] = [y for y in x["running_tasks"] if list(y) != [job_id, task_id]]
+                x["total_tasks_run"] = int(x.get("total_tasks_run") or 0) + 1
+                x["total_tasks_succeeded"] = int(x.get("total_tasks_succeeded") or 0) + (1 if ok else 0)
+                if x["state"] == "running" and not x["running_tasks"]:
+                    x["state"] = "idle"; x["state_transition_time"] = _now()
+                elif x["state"] == "leaving_pool" and not x["running_tasks"]:
+                    x["state"] = "offline"
+            try:
+                m = self.store.mutate("node", pool_id, n["id"], fn)
+                if m["state"] == "offline":
+                    self.store.delete("node", pool_id, n["id"])
+                released += 1
+            except NotFound:
+                pass
+        return released
+
+    def _kill_rank_groups(self, job: dict, t: dict) -> None:
+        """SIGKILL every rank process group the runner recorded in <taskdir>/ranks.pid."""
+        tdir = self.task_dir(job["pool_id"], job["id"], t["id"])
+        try:
+            with open(os.path.join(tdir, "ranks.pid")) as f:
+                pgids = [int(x) for x in f.read().split()]
+        except (OSError, ValueError):
+            pgids = []
+        for g in pgids:
+            if g > 1:
+                try:
+                    os.killpg(g, signal.SIGKILL)
+                except (ProcessLookupError, PermissionError):
+                    pass
+
+    def _reap_task_runner(self, job: dict, t: dict, grace: float = 12.0) -> None:
+        """Wait for a terminated task's runner to exit; escalate to the rank process groups, then the runner; free its slots."""
+        pid, start = t.get("pid"), t.get("pid_start")
+        if t["state"] in ("running", "preparing") and pid:
+            deadline = time.time() + grace          # the runner escalates to SIGKILL on its ranks after 5 s, then runs the epilogue
+            while pid_alive(pid, start) and time.time() < deadline:
+                time.sleep(0.02)
+            if pid_alive(pid, start):
+                self._kill_rank_groups(job, t)
+                try:
+                    os.kill(int(pid), signal.SIGKILL)
+                except (ProcessLookupError, PermissionError):
+                    pass
+        self.release_task_slots(job["pool_id"], job["id"], t["id"], ok=False)
+
     def delete_task(self, job_id: str, task_id: str) -> None:
         t = self.get_task(job_id, task_id)
-        self.terminate_task(job_id, task_id, reason="task deleted", force=True)
-        self.store.delete("task", job_id, task_id)
         job = self.get_job(job_id)
+        self.terminate_task(job_id, task_id, reason="task deleted")
+        self._reap_task_runner(job, self.get_task(job_id, task_id))
+        self.store.delete("task", job_id, task_id)
         shutil.rmtree(self.task_dir(job["pool_id"], job_id, t["id"]), ignore_errors=True)
 
     def job_stats(self, job_id: Optional[str] = None) -> dict:
@@ -472,6 +643,7 @@ class LocalBackend:
 
     # ------------------------------------------------------------------ job schedules
     def add_job_schedule(self, sched: dict) -> dict:
+        validate_id("job schedule", sched.get("id"))
         rec = {"state": "active", "created": _now(), "last_run": None, "runs": 0, "active_job_id": None}
         rec.update(sched)
         try:

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import json
 import os
+import re
 import shlex
 import sys
 import zlib
@@ -123,6 +124,46 @@ def data_commands(b, t: dict, env: dict) -> tuple[list[str], list[str]]:
     return pro, epi
 
 
+def _size_bytes(v) -> int:
+    """docker --shm-size notation: <number>[b|k|m|g] (default bytes)."""
+    m = re.match(r"^\s*(\d+(?:\.\d+)?)\s*([bkmgBKMG]?)[bB]?\s*$", str(v))
+    if not m:
+        return 0
+    return int(float(m.group(1)) * {"": 1, "b": 1, "k": 1 << 10, "m": 1 << 20, "g": 1 << 30}[m.group(2).lower()])
+
+
+def containers_dir(b, pool_id: str) -> str:
+    """Registry of named "containers" (running tasks, daemonised multi-instance coordination sessions) of a pool."""
+    return os.path.join(b.pool_root(pool_id), "containers")
+
+
+def sandbox_items(b, pool: dict, t: dict, tdir: str, env: dict) -> list[tuple[str, str]]:
+    """Spec keys that make ``shipyard-taskrun`` run the task in a process sandbox with the container semantics of the job:
+    volume binds, restrict_default_bind_mounts, user_identity, --shm-size, --rm, --name
+    (/root/reference/convoy/settings.py:3875-3901, 3919-4051).  ``SHIPYARD_SANDBOX`` = off | auto | require overrides the mode."""
+    sbx = t.get("sandbox")
+    mode = os.environ.get("SHIPYARD_SANDBOX_MODE", "auto")
+    if not sbx or mode == "off":
+        return []
+    scratch = os.path.join(tdir, ".container")
+    items = [("sandbox", mode), ("container_scratch", scratch), ("private_tmp", os.path.join(scratch, "tmp")),
+             ("rm", "1" if sbx.get("remove_after_exit", True) else "0"),
+             ("name", re.sub(r"[^A-Za-z0-9_.-]", "_", str(sbx.get("name") or t["id"]))[:128]),
+             ("containers_dir", containers_dir(b, pool["id"])), ("node_root", b.pool_root(pool["id"]))]
+    for src, dst, opts, vname in sbx.get("binds") or []:
+        src = _expand(src, env) if src else os.path.join(scratch, "volumes", re.sub(r"[^A-Za-z0-9_.-]", "_", vname))
+        dst = _expand(dst, env)
+        os.makedirs(src, exist_ok=True)
+        items.append(("bind", f"{src}:{dst}" + (":ro" if "ro" in str(opts).split(",") else "")))
+    if sbx.get("restrict_default_bind_mounts"):
+        items += [("restrict_root", b.pool_root(pool["id"])), ("keep", tdir)]
+    if sbx.get("uid") is not None:
+        items += [("uid", str(int(sbx["uid"]))), ("gid", str(int(sbx.get("gid") if sbx.get("gid") is not None else sbx["uid"])))]
+    if sbx.get("shm_size"):
+        items.append(("shm_bytes", str(_size_bytes(sbx["shm_size"]))))
+    return items
+
+
 def build_task_spec(b, pool: dict, job: dict, t: dict, nodes: list[dict]) -> tuple[str, str]:
     """Write the runner spec for task `t` placed on `nodes`; returns (spec path, task dir)."""
     pid, jid, tid = pool["id"], job["id"], t["id"]
@@ -185,6 +226,7 @@ def build_task_spec(b, pool: dict, job: dict, t: dict, nodes: list[dict]) -> tup
     if t.get("max_wall_time_s"):
         items.append(("wall_time_s", str(int(float(t["max_wall_time_s"])))))
     items.append(("user_cmd", command))
+    items += sandbox_items(b, pool, t, tdir, env)
     for k, v in env.items():
         items.append(("env", f"{k}={v}"))
     spec = os.path.join(tdir, "task.spec")

@@ -13,7 +13,6 @@ import hashlib
 import os
 import shutil
 import subprocess
-import tempfile
 from typing import Optional
 
 
@@ -77,32 +76,52 @@ def get_sha1_thumbprint(path: str, passphrase: Optional[str] = None) -> str:
         return hashlib.sha1(f.read()).hexdigest()
 
 
+class EncryptionError(RuntimeError):
+    """Raised when encryption was requested but cannot be performed (never degrade to a reversible encoding)."""
+
+
+_RSA_CHUNK = 190          # bytes of plaintext per RSA block: fits OAEP (214) and PKCS#1 v1.5 (245) with a 2048-bit key
+
+
 def encrypt_string(enabled: bool, value: Optional[str], public_key_pem: Optional[str] = None) -> Optional[str]:
-    """RSA-encrypt `value` for a node when encryption is enabled; pass-through otherwise."""
+    """RSA-encrypt `value` for a node when encryption is enabled; pass-through otherwise.
+
+    Same surface as /root/reference/convoy/crypto.py:603-615 (``encrypt_string(enabled, string, config)``).  Values longer than
+    one RSA block are encrypted block-wise (``rsa:<b64>,<b64>,...``).  When `enabled` is true and the value cannot be
+    encrypted (no openssl, no certificate, openssl failure) this raises :class:`EncryptionError`: a credential the user asked
+    to protect is never stored in a reversible encoding.
+    """
     if not enabled or value is None:
         return value
-    if public_key_pem and _have("openssl") and os.path.exists(public_key_pem):
-        with tempfile.NamedTemporaryFile("w", delete=False) as f:
-            f.write(value)
-        try:
-            p = subprocess.run(["openssl", "pkeyutl", "-encrypt", "-certin", "-inkey", public_key_pem, "-in", f.name],
-                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
-            if p.returncode == 0:
-                return "rsa:" + base64.b64encode(p.stdout).decode()
-        finally:
-            os.remove(f.name)
-    return "b64:" + base64.b64encode(value.encode()).decode()
+    if not public_key_pem or not os.path.exists(public_key_pem):
+        raise EncryptionError(f"encryption is enabled but the public certificate {public_key_pem!r} does not exist")
+    if not _have("openssl"):
+        raise EncryptionError("encryption is enabled but openssl is not installed")
+    raw = value.encode()
+    blocks = []
+    for i in range(0, max(len(raw), 1), _RSA_CHUNK):
+        p = subprocess.run(["openssl", "pkeyutl", "-encrypt", "-certin", "-inkey", public_key_pem],
+                           input=raw[i:i + _RSA_CHUNK], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if p.returncode != 0:
+            raise EncryptionError("openssl pkeyutl -encrypt failed: " + p.stderr.decode(errors="replace").strip()[:200])
+        blocks.append(base64.b64encode(p.stdout).decode())
+    return "rsa:" + ",".join(blocks)
 
 
 def decrypt_string(value: Optional[str], private_key_pem: Optional[str] = None) -> Optional[str]:
     if value is None:
         return None
-    if value.startswith("b64:"):
+    if value.startswith("b64:"):          # values written by earlier versions with encryption disabled
         return base64.b64decode(value[4:]).decode()
-    if value.startswith("rsa:") and private_key_pem:
-        p = subprocess.run(["openssl", "pkeyutl", "-decrypt", "-inkey", private_key_pem], input=base64.b64decode(value[4:]),
-                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
-        if p.returncode == 0:
-            return p.stdout.decode()
-        raise RuntimeError("cannot decrypt value with the given private key")
+    if value.startswith("rsa:"):
+        if not private_key_pem:
+            raise EncryptionError("value is RSA-encrypted but no private key was given")
+        out = b""
+        for blk in value[4:].split(","):
+            p = subprocess.run(["openssl", "pkeyutl", "-decrypt", "-inkey", private_key_pem], input=base64.b64decode(blk),
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            if p.returncode != 0:
+                raise EncryptionError("cannot decrypt value with the given private key")
+            out += p.stdout
+        return out.decode()
     return value

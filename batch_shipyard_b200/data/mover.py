@@ -70,8 +70,13 @@ def remote_path(root: str, remote: str) -> str:
 
 
 def _log(name: str, msg: str) -> None:
+    """Per-task transfer log (the reference's blobxfer-{download,upload}.log, scripts/shipyard_blobxfer.sh:69).  Written only inside a
+    task directory: outside a task (tests, ad-hoc CLI use) there is no log file, so nothing lands in the current directory."""
+    tdir = os.environ.get("AZ_BATCH_TASK_DIR")
+    if not tdir or not os.path.isdir(tdir):
+        return
     try:
-        with open(os.path.join(os.environ.get("AZ_BATCH_TASK_DIR", "."), f"blobxfer-{name}.log"), "a") as f:
+        with open(os.path.join(tdir, f"blobxfer-{name}.log"), "a") as f:
             f.write(f"{time.strftime('%Y-%m-%dT%H:%M:%S')} {msg}\n")
     except OSError:
         pass

@@ -455,6 +455,8 @@ def action_jobs_cmi(ctx: Context, delete=False) -> dict:
     for jid in _job_ids(ctx):
         if not ctx.b.job_exists(jid):
             continue
+        for name in ctx.b.clean_mi_containers(jid):          # kill daemonised coordination sessions by container name
+            cleaned.append([jid, "container:" + name])
         for t in ctx.b.list_tasks(jid):
             if t.get("multi_instance") and t["state"] == "completed":
                 tdir = ctx.b.task_dir(ctx.b.get_job(jid)["pool_id"], jid, t["id"])

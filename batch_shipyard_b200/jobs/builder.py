@@ -64,6 +64,8 @@ class TaskRecord:
     name: Optional[str] = None
     labels: list = field(default_factory=list)
     is_merge_task: bool = False
+    # container semantics the native runner enforces with a process sandbox (mount namespace): see runspec.sandbox_items
+    sandbox: Optional[dict] = None
 
     def to_dict(self) -> dict:
         return asdict(self)
@@ -146,6 +148,25 @@ def _infiniband(task: dict, jobspec: dict, pool: S.PoolSettings) -> bool:
     if v is None:
         return S.is_rdma_pool(pool.vm_size) and pool.inter_node_communication_enabled and not pool.is_windows
     return bool(v)
+
+
+def sandbox_binds(config: dict, task: dict, jobspec: dict) -> list:
+    """[source, destination, options] for every data / shared data volume of the task: what the runner bind-mounts inside the
+    task's mount namespace (the same volumes `_volume_binds` renders as -v / -B strings).  A data volume without host_path is an
+    anonymous volume: source None, materialised under the task's container scratch by the runner spec."""
+    gs = S.global_settings(config)
+    out = []
+    for vname in list(jobspec.get("data_volumes") or []) + list(task.get("data_volumes") or []):
+        dv = gs.data_volumes.get(vname)
+        if dv is None:
+            raise ValueError(f"data volume '{vname}' is not defined in global_resources.volumes.data_volumes")
+        out.append([dv.host_path or None, dv.container_path, dv.bind_options or "", vname])
+    for vname in list(jobspec.get("shared_data_volumes") or []) + list(task.get("shared_data_volumes") or []):
+        sv = gs.shared_data_volumes.get(vname)
+        if sv is None:
+            raise ValueError(f"shared data volume '{vname}' is not defined in global_resources.volumes.shared_data_volumes")
+        out.append([shared_volume_host_path(sv), sv.container_path, sv.bind_options or "", vname])
+    return out
 
 
 def _volume_binds(config: dict, task: dict, jobspec: dict, singularity: bool) -> list:
@@ -295,6 +316,11 @@ def build_task(config: dict, pool: S.PoolSettings, jobspec: dict, task: dict, ta
                      runtime="singularity" if singularity else "docker", native_shape=pool.native,
                      run_options=run_opts, env=env, gpus=gpus, infiniband=ib, working_dir=wd, user_identity=ident,
                      name=name, labels=list(task.get("labels") or []), is_merge_task=is_merge)
+
+    rec.sandbox = {"binds": sandbox_binds(config, task, jobspec),
+                   "restrict_default_bind_mounts": bool(jobspec.get("restrict_default_bind_mounts", False)),
+                   "remove_after_exit": bool(rm), "shm_size": shm or None, "name": name or task_id,
+                   "uid": (ident or {}).get("uid"), "gid": (ident or {}).get("gid")}
 
     # retries / wall / retention: task overrides job
     rec.max_task_retries = int(task.get("max_task_retries", S.job_max_task_retries(jobspec)) or 0)

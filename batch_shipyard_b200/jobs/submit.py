@@ -13,10 +13,11 @@ hand-off.
 from __future__ import annotations
 
 import datetime
+import shlex
 import time
 from typing import Optional
 
-from ..backend.local import LocalBackend
+from ..backend.local import BackendError, LocalBackend, validate_id
 from ..config import settings as S
 from ..utils import util
 from . import builder as B
@@ -56,7 +57,7 @@ def _auto_scratch_task(pool: S.PoolSettings, jobspec: dict, counts: dict) -> Opt
     n = S.resolve_num_instances(a.num_instances, counts["current_dedicated"], counts["current_low_priority"],
                                 pool.vm_dedicated, pool.vm_low_priority)
     jid = S.job_id(jobspec)
-    scratch = f"$AZ_BATCH_NODE_SHARED_DIR/auto_scratch/{jid}"
+    scratch = f"$AZ_BATCH_NODE_SHARED_DIR/auto_scratch/{shlex.quote(jid)}"
     return {"id": a.task_id, "job_id": jid, "command": ":", "image": None, "runtime": "process", "native_shape": False,
             "multi_instance": {"num_instances": n, "coordination_command": f"mkdir -p {scratch} && chmod 1777 {scratch}",
                                "processes_per_node": 1, "mpi": None, "pre_execution_command": None, "resource_files": []},
@@ -76,6 +77,12 @@ def add_jobs(b: LocalBackend, config: dict, recreate: bool = False, tail: Option
     out: dict = {}
     for jobspec in S.job_specifications(config):
         jid = S.job_id(jobspec)
+        try:
+            validate_id("job schedule" if S.job_recurrence(jobspec) is not None else "job", jid)
+        except BackendError as e:          # ids become directory names and shell words (the Batch service enforced this for the reference)
+            if not dry_run:
+                raise JobSubmissionError(str(e)) from None
+            logger.warning("dry run: %s (a real submission is rejected)", e)     # templates carry placeholders such as '<job id>'
         recurrence = S.job_recurrence(jobspec)
         auto_scratch = S.job_auto_scratch(jobspec)
         if recurrence is not None and auto_scratch is not None:
@@ -138,12 +145,12 @@ def add_jobs(b: LocalBackend, config: dict, recreate: bool = False, tail: Option
         # ---- job-level pieces -----------------------------------------------------------------------
         prep_cmds = []
         if not pool.native and (gs.docker_images or gs.singularity_images_unsigned or gs.singularity_images_signed):
-            prep_cmds.append(f"$SHIPYARD_PYTHON -m batch_shipyard_b200.pool.wait_images --state-dir $SHIPYARD_STATE_DIR --pool {pool_id}")
+            prep_cmds.append(f"$SHIPYARD_PYTHON -m batch_shipyard_b200.pool.wait_images --state-dir $SHIPYARD_STATE_DIR --pool {shlex.quote(pool_id)}")
         if S.job_preparation_command(jobspec):
             prep_cmds.append(S.job_preparation_command(jobspec))
         rel_cmds = []
         if auto_scratch is not None:
-            rel_cmds.append(f"rm -rf $AZ_BATCH_NODE_SHARED_DIR/auto_scratch/{jid}")
+            rel_cmds.append(f"rm -rf $AZ_BATCH_NODE_SHARED_DIR/auto_scratch/{shlex.quote(jid)}")
         if S.job_release_command(jobspec):
             rel_cmds.append(S.job_release_command(jobspec))
         job_rec = {

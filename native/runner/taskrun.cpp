@@ -13,12 +13,18 @@
 // LOCAL_RANK, MASTER_*, OMPI_*/PMI_* compat, AZ_BATCH_*) and the collectives shim preloaded.
 //
 // Spec file: one `key<TAB>value` per line; value escapes \n \t \\ ; repeated keys form lists.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <errno.h>
 #include <fcntl.h>
+#include <grp.h>
+#include <sched.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mount.h>
 #include <sys/stat.h>
 #include <sys/time.h>
 #include <sys/types.h>
@@ -86,13 +92,210 @@ static int open_append(const std::string& p) {
   return fd;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Process sandbox: the container semantics of the reference's `docker run` option synthesis
+// (/root/reference/convoy/settings.py:3919-4051 user identity / working dir / default + volume binds, :3875-3901 --rm / --shm-size /
+// --name, :4374-4443 daemonised multi-instance coordination container) modelled without a container runtime:
+//   * a private mount namespace per rank (root: CLONE_NEWNS; unprivileged: CLONE_NEWUSER|CLONE_NEWNS with an identity uid map)
+//   * `bind src:dst[:ro]`            -> recursive bind mounts (data volumes, shared data volumes, the env file ...)
+//   * `restrict_root` + `keep`       -> restrict_default_bind_mounts: the node root is replaced by an empty tmpfs in which only the
+//                                       task directory (and the explicitly bound volumes) are visible
+//   * `shm_bytes`                    -> private tmpfs on /dev/shm of that size (--shm-size)
+//   * `private_tmp`                  -> the task's own /tmp ("writable layer"); deleted after the task when `rm` is set (--rm)
+//   * `uid` / `gid`                  -> setgroups/setgid/setuid after the mounts (user_identity.specific_user, -u uid:gid)
+//   * `name` + `containers_dir`      -> a registry entry <name>.json (runner pid, rank process groups) while the task runs, and
+//                                       <name>.coord with the session ids of the coordination commands: what `docker run -d` leaves
+//                                       behind and job release / `jobs cmi` kill by name
+// Modes: "mountns" (root), "userns" (unprivileged), "none" (no namespace support: binds degrade to symlinks where the destination
+// does not exist; `sandbox require` turns that into a task failure with exit code 125).
+struct Bind { std::string src, dst; bool ro = false; };
+struct Sandbox {
+  std::string want = "off";            // off | auto | require
+  std::vector<Bind> binds;
+  std::string restrict_root;
+  std::vector<std::string> keep;
+  long uid = -1, gid = -1;
+  long long shm_bytes = 0;
+  std::string private_tmp;
+  std::string node_root;               // stays visible when it lives under /tmp and /tmp becomes private
+  bool active() const { return want != "off"; }
+};
+
+static int mkdir_p(const std::string& path, mode_t mode = 0755) {
+  std::string cur;
+  for (size_t i = 0; i < path.size(); ++i) {
+    cur += path[i];
+    if ((path[i] == '/' && i > 0) || i + 1 == path.size()) {
+      if (mkdir(cur.c_str(), mode) != 0 && errno != EEXIST) return -1;
+    }
+  }
+  return 0;
+}
+
+static bool write_file(const char* path, const std::string& v) {
+  int fd = open(path, O_WRONLY | O_CLOEXEC);
+  if (fd < 0) return false;
+  bool ok = write(fd, v.data(), v.size()) == (ssize_t)v.size();
+  close(fd);
+  return ok;
+}
+
+// try to enter a private mount namespace; returns the mode achieved
+static const char* sandbox_unshare() {
+  if (geteuid() == 0) {
+    if (unshare(CLONE_NEWNS) == 0) return "mountns";
+    return "none";
+  }
+  const uid_t u = getuid(); const gid_t g = getgid();
+  if (unshare(CLONE_NEWUSER | CLONE_NEWNS) != 0) return "none";
+  write_file("/proc/self/setgroups", "deny");
+  if (!write_file("/proc/self/uid_map", std::to_string(u) + " " + std::to_string(u) + " 1\n") ||
+      !write_file("/proc/self/gid_map", std::to_string(g) + " " + std::to_string(g) + " 1\n")) return "none";
+  return "userns";
+}
+
+// one fork probes which mode this box allows (the answer is the same for every rank of the task)
+static std::string sandbox_probe() {
+  pid_t pid = fork();
+  if (pid == 0) {
+    const char* m = sandbox_unshare();
+    if (!strcmp(m, "none")) _exit(2);
+    if (mount(nullptr, "/", nullptr, MS_REC | MS_PRIVATE, nullptr) != 0) _exit(2);
+    _exit(!strcmp(m, "mountns") ? 0 : 1);
+  }
+  int st = 0;
+  if (pid < 0 || waitpid(pid, &st, 0) < 0 || !WIFEXITED(st)) return "none";
+  return WEXITSTATUS(st) == 0 ? "mountns" : WEXITSTATUS(st) == 1 ? "userns" : "none";
+}
+
+static bool is_dir(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+
+// Runs in the child, before exec.  Returns 0 or an errno-style failure (the child then exits 125).
+static int sandbox_enter(const Sandbox& sb, const std::string& mode) {
+  if (!sb.active()) return 0;
+  if (mode == "none") {
+    if (sb.want == "require") { fprintf(stderr, "taskrun: sandbox required but this box allows neither mount nor user namespaces\n"); return EPERM; }
+    // degraded: a bind whose destination does not exist becomes a symlink; everything else is left as is
+    for (auto& b : sb.binds) {
+      struct stat st;
+      if (b.src == b.dst || lstat(b.dst.c_str(), &st) == 0) continue;
+      size_t slash = b.dst.rfind('/');
+      if (slash != std::string::npos && slash > 0) mkdir_p(b.dst.substr(0, slash));
+      if (symlink(b.src.c_str(), b.dst.c_str()) != 0)
+        fprintf(stderr, "taskrun: sandbox (degraded): cannot link %s -> %s: %s\n", b.dst.c_str(), b.src.c_str(), strerror(errno));
+    }
+    if (!sb.private_tmp.empty()) { mkdir_p(sb.private_tmp, 01777); setenv("TMPDIR", sb.private_tmp.c_str(), 1); }
+    return 0;
+  }
+  const char* m = sandbox_unshare();
+  if (strcmp(m, mode.c_str()) != 0) { fprintf(stderr, "taskrun: sandbox: unshare failed: %s\n", strerror(errno)); return EPERM; }
+  if (mount(nullptr, "/", nullptr, MS_REC | MS_PRIVATE, nullptr) != 0) { perror("taskrun: sandbox: make-rprivate /"); return errno; }
+  // sources are pinned by descriptor first: restrict_root may hide them from the path namespace below
+  std::vector<int> src_fd(sb.binds.size(), -1);
+  for (size_t i = 0; i < sb.binds.size(); ++i) {
+    const Bind& b = sb.binds[i];
+    struct stat st;
+    if (stat(b.src.c_str(), &st) != 0 && mkdir_p(b.src) != 0) {
+      fprintf(stderr, "taskrun: sandbox: bind source %s: %s\n", b.src.c_str(), strerror(errno)); return ENOENT;
+    }
+    src_fd[i] = open(b.src.c_str(), O_PATH | O_CLOEXEC);
+    if (src_fd[i] < 0) { fprintf(stderr, "taskrun: sandbox: open %s: %s\n", b.src.c_str(), strerror(errno)); return errno; }
+  }
+  if (!sb.private_tmp.empty()) {
+    // the task's own /tmp.  A node root that itself lives under /tmp (state dir of a test run) is re-attached at the same path.
+    int root_fd = -1;
+    if (sb.node_root.compare(0, 5, "/tmp/") == 0) root_fd = open(sb.node_root.c_str(), O_PATH | O_CLOEXEC);
+    mkdir_p(sb.private_tmp, 01777); chmod(sb.private_tmp.c_str(), 01777);
+    const int tmp_fd = open(sb.private_tmp.c_str(), O_PATH | O_CLOEXEC);
+    const std::string via = "/proc/self/fd/" + std::to_string(tmp_fd);
+    if (tmp_fd < 0 || mount(via.c_str(), "/tmp", nullptr, MS_BIND, nullptr) != 0)
+      fprintf(stderr, "taskrun: sandbox: private /tmp: %s (keeping the host's)\n", strerror(errno));
+    else if (root_fd >= 0) {
+      const std::string rvia = "/proc/self/fd/" + std::to_string(root_fd);
+      if (mkdir_p(sb.node_root) != 0 || mount(rvia.c_str(), sb.node_root.c_str(), nullptr, MS_BIND | MS_REC, nullptr) != 0) {
+        fprintf(stderr, "taskrun: sandbox: re-attach %s under the private /tmp: %s\n", sb.node_root.c_str(), strerror(errno)); return errno;
+      }
+    }
+    if (tmp_fd >= 0) close(tmp_fd);
+    if (root_fd >= 0) close(root_fd);
+  }
+  if (!sb.restrict_root.empty() && is_dir(sb.restrict_root)) {
+    char stage[] = "/tmp/.sy-sbx-XXXXXX";
+    if (!mkdtemp(stage)) { perror("taskrun: sandbox: mkdtemp"); return errno; }
+    if (mount("tmpfs", stage, "tmpfs", MS_NOSUID | MS_NODEV, "mode=0755,size=16m") != 0) { perror("taskrun: sandbox: tmpfs"); return errno; }
+    const std::string root = sb.restrict_root.back() == '/' ? sb.restrict_root.substr(0, sb.restrict_root.size() - 1) : sb.restrict_root;
+    for (auto& k : sb.keep) {
+      if (k.compare(0, root.size() + 1, root + "/") != 0) continue;
+      const std::string dst = std::string(stage) + k.substr(root.size());
+      if (mkdir_p(dst) != 0 || mount(k.c_str(), dst.c_str(), nullptr, MS_BIND | MS_REC, nullptr) != 0) {
+        fprintf(stderr, "taskrun: sandbox: keep %s: %s\n", k.c_str(), strerror(errno)); return errno;
+      }
+    }
+    if (mount(stage, root.c_str(), nullptr, MS_BIND | MS_REC, nullptr) != 0) { perror("taskrun: sandbox: restrict node root"); return errno; }
+    umount2(stage, MNT_DETACH);
+    rmdir(stage);
+  }
+  for (size_t i = 0; i < sb.binds.size(); ++i) {
+    const Bind& b = sb.binds[i];
+    struct stat st;
+    const bool src_is_dir = fstat(src_fd[i], &st) == 0 && S_ISDIR(st.st_mode);
+    if (stat(b.dst.c_str(), &st) != 0) {
+      int rc = 0;
+      if (src_is_dir) rc = mkdir_p(b.dst);
+      else {
+        size_t slash = b.dst.rfind('/');
+        if (slash != std::string::npos && slash > 0) rc = mkdir_p(b.dst.substr(0, slash));
+        int fd = open(b.dst.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC, 0644);
+        if (fd >= 0) close(fd); else rc = -1;
+      }
+      if (rc != 0) { fprintf(stderr, "taskrun: sandbox: cannot create mount point %s: %s\n", b.dst.c_str(), strerror(errno)); return errno; }
+    }
+    const std::string via = "/proc/self/fd/" + std::to_string(src_fd[i]);
+    if (mount(via.c_str(), b.dst.c_str(), nullptr, MS_BIND | MS_REC, nullptr) != 0) {
+      fprintf(stderr, "taskrun: sandbox: bind %s -> %s: %s\n", b.src.c_str(), b.dst.c_str(), strerror(errno)); return errno;
+    }
+    if (b.ro && mount(nullptr, b.dst.c_str(), nullptr, MS_BIND | MS_REMOUNT | MS_RDONLY | MS_REC, nullptr) != 0) {
+      fprintf(stderr, "taskrun: sandbox: read-only remount of %s: %s\n", b.dst.c_str(), strerror(errno)); return errno;
+    }
+    close(src_fd[i]);
+  }
+  if (sb.shm_bytes > 0) {
+    const std::string opt = "mode=1777,size=" + std::to_string(sb.shm_bytes);
+    if (mount("tmpfs", "/dev/shm", "tmpfs", MS_NOSUID | MS_NODEV, opt.c_str()) != 0)
+      fprintf(stderr, "taskrun: sandbox: --shm-size tmpfs on /dev/shm: %s (keeping the host's)\n", strerror(errno));
+  }
+  if (sb.gid >= 0 || sb.uid >= 0) {
+    if (mode == "mountns") {
+      gid_t g = (gid_t)(sb.gid >= 0 ? sb.gid : getgid());
+      if (setgroups(1, &g) != 0 || setgid(g) != 0) { perror("taskrun: sandbox: setgid"); return errno; }
+      if (sb.uid >= 0 && setuid((uid_t)sb.uid) != 0) { perror("taskrun: sandbox: setuid"); return errno; }
+    } else if ((sb.uid >= 0 && (uid_t)sb.uid != getuid()) || (sb.gid >= 0 && (gid_t)sb.gid != getgid())) {
+      fprintf(stderr, "taskrun: sandbox: user_identity %ld:%ld needs root; running as %d:%d\n", sb.uid, sb.gid, (int)getuid(), (int)getgid());
+      if (sb.want == "require") return EPERM;
+    }
+  }
+  return 0;
+}
+
+static void rm_rf(const std::string& path) {
+  pid_t pid = fork();
+  if (pid == 0) { execl("/bin/rm", "rm", "-rf", "--one-file-system", path.c_str(), (char*)nullptr); _exit(127); }
+  int st; if (pid > 0) waitpid(pid, &st, 0);
+}
+
 // run `cmd` through the shell with extra env; stdout/stderr to the given fds; returns exit code
 static int run_shell(const std::string& shell, const std::string& cmd, const std::vector<std::string>& extra_env,
-                     int out_fd, int err_fd, const std::string& cwd) {
+                     int out_fd, int err_fd, const std::string& cwd, const Sandbox* sb = nullptr, const std::string& sb_mode = "none",
+                     pid_t* session_out = nullptr) {
   if (cmd.empty()) return 0;
   pid_t pid = fork();
   if (pid < 0) return 127;
   if (pid == 0) {
+    if (session_out) setsid();           // whatever the command leaves running stays findable by session id
+    if (out_fd >= 0) dup2(out_fd, 1);
+    if (err_fd >= 0) dup2(err_fd, 2);
+    if (sb && sandbox_enter(*sb, sb_mode) != 0) _exit(125);
     if (!cwd.empty() && chdir(cwd.c_str()) != 0) _exit(126);
     for (auto& e : extra_env) putenv(strdup(e.c_str()));
     if (out_fd >= 0) dup2(out_fd, 1);
@@ -100,6 +303,7 @@ static int run_shell(const std::string& shell, const std::string& cmd, const std
     execl(shell.c_str(), shell.c_str(), "-c", cmd.c_str(), (char*)nullptr);
     _exit(127);
   }
+  if (session_out) *session_out = pid;
   int st = 0;
   while (waitpid(pid, &st, 0) < 0 && errno == EINTR) { if (g_term) kill(pid, SIGTERM); }
   return WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
@@ -170,6 +374,29 @@ int main(int argc, char** argv) {
   const std::string master_port = sp.get("master_port", "29400");
   const auto& gpus = sp.list("gpu");
 
+  Sandbox sb;
+  sb.want = sp.get("sandbox", "off");
+  for (auto& b : sp.list("bind")) {          // docker syntax: src:dst[:ro|rw]
+    Bind bd; size_t c1 = b.find(':');
+    if (c1 == std::string::npos) { bd.src = bd.dst = b; }
+    else {
+      bd.src = b.substr(0, c1); size_t c2 = b.find(':', c1 + 1);
+      bd.dst = b.substr(c1 + 1, c2 == std::string::npos ? std::string::npos : c2 - c1 - 1);
+      if (c2 != std::string::npos) bd.ro = b.substr(c2 + 1).find("ro") != std::string::npos;
+    }
+    if (!bd.src.empty() && !bd.dst.empty()) sb.binds.push_back(bd);
+  }
+  sb.restrict_root = sp.get("restrict_root");
+  sb.keep = sp.list("keep");
+  sb.uid = sp.geti("uid", -1); sb.gid = sp.geti("gid", -1);
+  sb.shm_bytes = atoll(sp.get("shm_bytes", "0").c_str());
+  sb.private_tmp = sp.get("private_tmp");
+  sb.node_root = sp.get("node_root");
+  const bool rm_after_exit = sp.geti("rm", 0) != 0;
+  const std::string ctr_name = sp.get("name"), ctr_dir = sp.get("containers_dir"), ctr_scratch = sp.get("container_scratch");
+  const std::string sb_mode = sb.active() ? sandbox_probe() : "none";
+  if (sb.active()) setenv("SHIPYARD_SANDBOX", sb_mode.c_str(), 1);
+
   struct sigaction sa = {};
   sa.sa_handler = on_term;
   sigaction(SIGTERM, &sa, nullptr);
@@ -177,6 +404,12 @@ int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
 
   mkdir(workdir.c_str(), 0755);
+  if (sb.active() && sb.uid >= 0 && geteuid() == 0) {
+    // user_identity.specific_user: the task user owns its working and task directories (as on a Batch node)
+    const gid_t g = (gid_t)(sb.gid >= 0 ? sb.gid : sb.uid);
+    if (chown(workdir.c_str(), (uid_t)sb.uid, g) != 0 || chown(taskdir.c_str(), (uid_t)sb.uid, g) != 0)
+      fprintf(stderr, "taskrun: chown of the task directories to %ld:%ld failed: %s\n", sb.uid, sb.gid, strerror(errno));
+  }
   for (auto& e : sp.list("env")) putenv(strdup(e.c_str()));
   int out_fd = open_append(out_path), err_fd = open_append(err_path);
   const double t_start = wall_s();
@@ -211,7 +444,14 @@ int main(int argc, char** argv) {
     for (long i = 0; i < ninst && rc == 0; ++i) {
       std::vector<std::string> env = {"SHIPYARD_INSTANCE=" + std::to_string(i),
                                       std::string("AZ_BATCH_IS_CURRENT_NODE_MASTER=") + (i == 0 ? "true" : "false")};
-      rc = run_shell(shell, coord, env, out_fd, err_fd, workdir);
+      pid_t sid = 0;
+      rc = run_shell(shell, coord, env, out_fd, err_fd, workdir, &sb, sb_mode, &sid);
+      if (sid > 0 && !ctr_dir.empty() && !ctr_name.empty()) {
+        // like `docker run -d`: whatever the coordination command daemonised outlives this task; job release / `jobs cmi` find it here
+        mkdir_p(ctr_dir);
+        FILE* cf = fopen((ctr_dir + "/" + ctr_name + ".coord").c_str(), "a");
+        if (cf) { fprintf(cf, "%d\n", (int)sid); fclose(cf); }
+      }
     }
   }
 
@@ -235,7 +475,6 @@ int main(int argc, char** argv) {
       if (pid < 0) { rc = 127; break; }
       if (pid == 0) {
         setpgid(0, 0);
-        if (chdir(workdir.c_str()) != 0) _exit(126);
         const long local = r % rpi, inst = r / rpi;
         auto set = [](const std::string& k, const std::string& v) { setenv(k.c_str(), v.c_str(), 1); };
         set("RANK", std::to_string(r)); set("WORLD_SIZE", std::to_string(world));
@@ -263,11 +502,29 @@ int main(int argc, char** argv) {
         }
         if (o >= 0) dup2(o, 1);
         if (e >= 0) dup2(e, 2);
+        if (sandbox_enter(sb, sb_mode) != 0) _exit(125);
+        if (chdir(workdir.c_str()) != 0) _exit(126);
         execl(shell.c_str(), shell.c_str(), "-c", user_cmd.c_str(), (char*)nullptr);
         _exit(127);
       }
       setpgid(pid, pid);
       pids[r] = pid;
+    }
+    {
+      // rank process groups: `jobs tasks term --force` / `jobs del` kill these if the runner itself has to be killed
+      FILE* pf = fopen((taskdir + "/ranks.pid").c_str(), "w");
+      if (pf) { for (auto p : pids) if (p > 0) fprintf(pf, "%d\n", (int)p); fclose(pf); }
+      if (!ctr_dir.empty() && !ctr_name.empty()) {
+        mkdir_p(ctr_dir);
+        FILE* cf = fopen((ctr_dir + "/" + ctr_name + ".json").c_str(), "w");
+        if (cf) {
+          fprintf(cf, "{\"name\": \"%s\", \"runner_pid\": %d, \"sandbox\": \"%s\", \"taskdir\": \"%s\", \"rank_pgids\": [",
+                  json_escape(ctr_name).c_str(), (int)getpid(), sb_mode.c_str(), json_escape(taskdir).c_str());
+          bool first = true;
+          for (auto p : pids) if (p > 0) { fprintf(cf, "%s%d", first ? "" : ", ", (int)p); first = false; }
+          fprintf(cf, "]}\n"); fclose(cf);
+        }
+      }
     }
     // ---- watchdog loop --------------------------------------------------------------
     const double t0 = now_s();
@@ -325,15 +582,19 @@ int main(int argc, char** argv) {
   int erc = run_shell(shell, sp.get("system_epilogue"), {"SHIPYARD_TASK_RESULT=" + result}, out_fd, err_fd, workdir);
   if (erc != 0) fprintf(stderr, "taskrun: system epilogue exited with %d\n", erc);
 
+  unlink((taskdir + "/ranks.pid").c_str());
+  if (!ctr_dir.empty() && !ctr_name.empty()) unlink((ctr_dir + "/" + ctr_name + ".json").c_str());
+  if (rm_after_exit && !ctr_scratch.empty()) rm_rf(ctr_scratch);      // --rm: the "container" (private /tmp, anonymous volumes) goes away
+
   const std::string rf = sp.get("result_file");
   if (!rf.empty()) {
     std::string tmp = rf + ".tmp";
     FILE* f = fopen(tmp.c_str(), "w");
     if (f) {
       fprintf(f, "{\"exit_code\": %d, \"result\": \"%s\", \"phase\": \"%s\", \"start\": %.3f, \"end\": %.3f, "
-                 "\"timed_out\": %s, \"terminated\": %s, \"world\": %ld, \"rank_exit_codes\": [",
+                 "\"timed_out\": %s, \"terminated\": %s, \"world\": %ld, \"sandbox\": \"%s\", \"rank_exit_codes\": [",
               rc, result.c_str(), json_escape(phase).c_str(), t_start, wall_s(), timed_out ? "true" : "false",
-              terminated ? "true" : "false", world);
+              terminated ? "true" : "false", world, sb.active() ? sb_mode.c_str() : "off");
       for (size_t i = 0; i < codes.size(); ++i) fprintf(f, "%s%d", i ? ", " : "", codes[i]);
       fprintf(f, "]}\n");
       fclose(f);
