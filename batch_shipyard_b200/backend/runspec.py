@@ -146,10 +146,16 @@ def sandbox_items(b, pool: dict, t: dict, tdir: str, env: dict) -> list[tuple[st
     if not sbx or mode == "off":
         return []
     scratch = os.path.join(tdir, ".container")
-    items = [("sandbox", mode), ("container_scratch", scratch), ("private_tmp", os.path.join(scratch, "tmp")),
+    # The task's own temporary directory is always handed over as TMPDIR.  Mounting it OVER /tmp (what a container has) is opt-in
+    # (SHIPYARD_SANDBOX_PRIVATE_TMP=1): tasks here are host programs, and interpreters, checkouts or datasets that live under
+    # /tmp would vanish from their view.  The node root and SHIPYARD_HOME are re-attached when they live under /tmp.
+    private = os.environ.get("SHIPYARD_SANDBOX_PRIVATE_TMP", "0") not in ("0", "", "off", "false")
+    env["TMPDIR"] = os.path.join(scratch, "tmp")
+    os.makedirs(env["TMPDIR"], exist_ok=True)
+    items = [("sandbox", mode), ("container_scratch", scratch)] + ([("private_tmp", os.path.join(scratch, "tmp"))] if private else []) + [
              ("rm", "1" if sbx.get("remove_after_exit", True) else "0"),
              ("name", re.sub(r"[^A-Za-z0-9_.-]", "_", str(sbx.get("name") or t["id"]))[:128]),
-             ("containers_dir", containers_dir(b, pool["id"])), ("node_root", b.pool_root(pool["id"]))]
+             ("containers_dir", containers_dir(b, pool["id"])), ("node_root", b.pool_root(pool["id"])), ("keep_tmp", _REPO_ROOT)]
     for src, dst, opts, vname in sbx.get("binds") or []:
         src = _expand(src, env) if src else os.path.join(scratch, "volumes", re.sub(r"[^A-Za-z0-9_.-]", "_", vname))
         dst = _expand(dst, env)

@@ -57,7 +57,12 @@ class ConvBN(nn.Module):
             y, stats = _conv.conv_bn_input(x, self.weight, self.stride)
         elif self.k == 7 and x.shape[1] == 16:
             # space-to-depth stem: the 7x7/s2/p3 conv as a dense 4x4/s1 conv over the 16-channel s2d input
-            y = F.conv2d(x, _fused.stem_weight_s2d(self.weight).contiguous(memory_format=torch.channels_last))
+            w2 = _fused.stem_weight_s2d(self.weight).contiguous(memory_format=torch.channels_last)
+            if fast and self.use_tc_gemm and self.cout == 64 and _conv.stem_native() and _gemm.stem_s2d_ok(x, w2):
+                # own tcgen05 kernels (fprop with BN statistics in the epilogue, wgrad); cuDNN needs ~5x longer on C = 16
+                y, stats = _gemm.stem_conv_s2d(x, w2, True)
+            else:
+                y = F.conv2d(x, w2)
         else:
             y = F.conv2d(x, self.weight, None, self.stride, self.k // 2)
         if fast:

@@ -48,6 +48,20 @@ class ConvPlan:
     timings_us: Optional[dict] = None
 
 
+_STEM = os.environ.get("SHIPYARD_STEM_IMPL", "tc").lower()          # "tc": native/gemm/stem_s2d.inc; "cudnn": F.conv2d on the s2d input
+
+
+def stem_native() -> bool:
+    """The s2d stem runs on the repo's tcgen05 kernels unless SHIPYARD_STEM_IMPL=cudnn or the dispatcher is forced to cuDNN."""
+    return _STEM != "cudnn" and _MODE != "cudnn"
+
+
+def set_stem(impl: str) -> None:
+    global _STEM
+    assert impl in ("tc", "cudnn")
+    _STEM = impl
+
+
 def set_mode(mode: str) -> None:
     global _MODE
     assert mode in ("auto", "tc", "cudnn")

@@ -53,6 +53,9 @@ def load() -> C.CDLL:
         lib.sy_conv3x3_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         lib.sy_conv3x3_halo_rows.argtypes = [C.c_int, C.c_int]
         lib.sy_conv3x3_wgrad_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_stem_s2d_fprop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        lib.sy_stem_s2d_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p]
         _LIB = lib
         try:
             from ..parallel.ddp import register_launch_counter
@@ -553,3 +556,73 @@ class _ConvNHWC(torch.autograd.Function):
 
 def conv_nhwc(x: torch.Tensor, w: torch.Tensor, stride: int = 1, pad: int = 1, want_stats: bool = False):
     return _ConvNHWC.apply(x, w, stride, pad, want_stats)
+
+
+# ---- ResNet stem: dense 4x4 convolution over the 16-channel space-to-depth input (native/gemm/stem_s2d.inc) --------------------------
+def stem_s2d_ok(x: torch.Tensor, w2: torch.Tensor) -> bool:
+    """x: [N,16,Hp,Wp] channels_last bf16 (the s2d input of ops.fused.u8_to_s2d_norm), w2: [64,16,4,4]."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 16 and tuple(w2.shape) == (64, 16, 4, 4)
+            and 4 <= x.shape[3] <= 128 and x.shape[2] >= 4)
+
+
+def stem_s2d_fprop(x: torch.Tensor, w2: torch.Tensor, stats: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+    """y[N,64,Hp-3,Wp-3] (channels_last) = conv2d(x, w2) on the tcgen05 stem kernel: one output row per tile, the 16 filter taps as
+    row-shifted 32-byte-swizzle descriptors over four TMA-loaded input rows, weights stationary in shared memory.
+    stats: zero-initialised float32[128] receiving the per-channel sum / sum of squares of y (train-mode BatchNorm statistics)."""
+    n, _, hp, wp = x.shape
+    xs, ws_ = _nhwc_storage(x), _nhwc_storage(w2)
+    y = torch.empty((n, hp - 3, wp - 3, 64), dtype=torch.bfloat16, device=x.device)
+    lib = load()
+    rc = lib.sy_stem_s2d_fprop(C.c_void_p(xs.data_ptr()), C.c_void_p(ws_.data_ptr()), C.c_void_p(y.data_ptr()), n, hp, wp,
+                               C.c_void_p(stats.data_ptr() if stats is not None else 0), max_ctas,
+                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_stem_s2d_fprop failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return y.permute(0, 3, 1, 2)
+
+
+def stem_s2d_wgrad(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+                   max_ctas: int = 0) -> torch.Tensor:
+    """dW2[64,16,4,4] (stored [64][4][4][16]) of the stem convolution: X rows as MN-major operands whose slabs are one pixel apart (the
+    four horizontal taps of a filter row come out of ONE buffer), dY rows as the B operand, accumulators resident in TMEM for all
+    tiles of a CTA, cross-CTA reduction through the fp32 workspace (last CTA converts to bf16)."""
+    n, _, hp, wp = x.shape
+    xs, dys = _nhwc_storage(x), _nhwc_storage(dy)
+    assert tuple(dys.shape) == (n, hp - 3, wp - 3, 64), dys.shape
+    if out is None:
+        out = torch.empty((64, 4, 4, 16), dtype=torch.bfloat16, device=x.device)
+        accumulate = False
+    assert out.is_contiguous() and tuple(out.shape) == (64, 4, 4, 16) and out.dtype == torch.bfloat16
+    ws, tickets = _workspace(x.device)
+    lib = load()
+    rc = lib.sy_stem_s2d_wgrad(C.c_void_p(xs.data_ptr()), C.c_void_p(dys.data_ptr()), C.c_void_p(out.data_ptr()), n, hp, wp,
+                               C.c_void_p(ws.data_ptr()), C.c_void_p(tickets.data_ptr()), 1 if accumulate else 0, max_ctas,
+                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_stem_s2d_wgrad failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return out.permute(0, 3, 1, 2)
+
+
+class _StemS2D(torch.autograd.Function):
+    """Stem convolution on the s2d input: fprop (+ BatchNorm statistics) and wgrad on tcgen05; the input needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w2, want_stats):
+        stats = torch.zeros(128, dtype=torch.float32, device=x.device) if want_stats else None
+        y = stem_s2d_fprop(x, w2, stats=stats)
+        ctx.save_for_backward(x)
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        (x,) = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        return None, stem_s2d_wgrad(x, dy), None
+
+
+def stem_conv_s2d(x: torch.Tensor, w2: torch.Tensor, want_stats: bool = True):
+    """(y, stats) of the s2d stem convolution; stats is None when not requested."""
+    return _StemS2D.apply(x, w2, want_stats)

@@ -10,6 +10,10 @@ torchrun, one rank per GPU).  Prints ONE JSON line on rank 0.
 * ``e2e``        the same metric through the public API with, every step, the H2D
                  copy of that step's uint8 batch from pinned host memory and the
                  D2H read of the loss.
+* ``baseline_same_run``  stock PyTorch (torchvision + DDP/NCCL + cuDNN, zero shipyard imports: bench/stock_baseline.py) measured in
+                 THIS process on THIS lease right before the shipyard arm, in two flavours (stock-eager, stock-tuned), each
+                 device-timed and end to end with its own clocks; ``vs_stock_eager`` / ``vs_stock_tuned`` are value ratios.
+* ``collectives`` (N > 1) 256 MB all-reduce bus bandwidth and 8 B all-reduce latency, shipyard kernels vs NCCL, same run.
 * ``--impl reference``  the unmodified reference cannot be installed offline
                  (no setup.py/pyproject; imports azure.* at module load) -> prints
                  ``{"impl": "reference", "unavailable": ...}``.
@@ -41,6 +45,8 @@ def parse():
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-baseline", action="store_true", help="skip the same-run stock-PyTorch arms (bench/stock_baseline.py)")
+    ap.add_argument("--no-coll", action="store_true", help="skip the same-run collective block (N > 1)")
     return ap.parse_args()
 
 
@@ -144,12 +150,17 @@ def run_shipyard(args, rank, world, local):
     from batch_shipyard_b200.parallel.ddp import FusedDataParallelTrainer
 
     dev = torch.device("cuda", local)
+    B = args.batch
+    baselines = None
+    if not args.no_baseline and args.model == "resnet50":
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        import stock_baseline
+        baselines = stock_baseline.run_both(B, args.steps, max(3, args.warmup), rank, world, local, lambda: ClockSampler(local))
     torch.manual_seed(1234)
     torch.backends.cudnn.benchmark = True
     comm = Communicator(rank, world, session=f"bench-{os.environ.get('MASTER_PORT', '0')}-{os.getppid() if world > 1 else os.getpid()}",
                         device=local, heap_bytes=1 << 30)
     model = resnet50() if args.model == "resnet50" else resnet_tiny(1000)
-    B = args.batch
     tr = FusedDataParallelTrainer(model, comm, (B, 3, 224, 224), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4,
                                   use_graph=not args.no_graph)
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
@@ -209,7 +220,53 @@ def run_shipyard(args, rank, world, local):
     base = _baseline_number(world)
     if base:
         out["vs_baseline"] = round(out["value"] / base, 4)
+    if baselines is not None:
+        out["baseline_same_run"] = baselines
+        for key, name in (("vs_stock_eager", "stock_eager"), ("vs_stock_tuned", "stock_tuned")):
+            b = baselines.get(name) or {}
+            if b.get("value"):
+                out[key] = {"device_timed": round(out["value"] / b["value"], 4),
+                            "e2e": round(e2e["value"] / b["e2e"]["value"], 4) if (e2e and b.get("e2e", {}).get("value")) else None}
+    if world > 1 and not args.no_coll:
+        try:
+            out["collectives"] = _collective_block(comm, rank, world, dev)
+        except Exception as e:  # noqa: BLE001 - secondary block: never take the headline down
+            out["collectives"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     comm.close()
+    return out
+
+
+def _collective_block(comm, rank, world, dev) -> dict:
+    """A number the collectives actually limit: 256 MB fp32 all-reduce bus bandwidth and 8 B all-reduce latency, shipyard kernels
+    (symmetric buffers, in place) vs NCCL through torch.distributed on the same stream, device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def time_us(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); e1.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e3 / iters, world, dev)
+
+    out = {}
+    for label, nbytes, iters, warm in (("allreduce_256MB", 256 << 20, 20, 5), ("allreduce_8B", 8, 200, 20)):
+        n = nbytes // 4
+        sym = comm.alloc(n, torch.float32); sym.fill_(1.0)
+        plain = torch.ones(n, dtype=torch.float32, device=dev)
+        ours = time_us(lambda: comm.all_reduce(sym, sym, scale=1.0 / world), iters, warm)
+        nccl = time_us(lambda: dist.all_reduce(plain, op=dist.ReduceOp.AVG), iters, warm)
+        row = {"shipyard_us": round(ours, 2), "nccl_us": round(nccl, 2), "speedup": round(nccl / ours, 3)}
+        if nbytes >= (1 << 20):
+            f = 2.0 * (world - 1) / world * nbytes
+            row["shipyard_busbw_gbs"] = round(f / ours / 1e3, 1); row["nccl_busbw_gbs"] = round(f / nccl / 1e3, 1)
+            row["frac_of_770gbs_link"] = round(f / ours / 1e3 / 770.0, 3)
+        out[label] = row
+    comm.check_status()
     return out
 
 

@@ -359,7 +359,17 @@ extern "C" int sy_reduce(sy_comm* c, const void* in, void* out, size_t count, in
   cudaStream_t s = (cudaStream_t)stream;
   size_t in_off; const size_t bytes = count * sy_dtype_size(dt);
   if (!sym_off(c, in, &in_off)) {
-    if (bytes > c->stage_bytes / 2) { sy_set_error("reduce: input larger than staging"); return SY_ERR_NOMEM; }
+    if (bytes > c->stage_bytes / 2) {
+      // plain input larger than the staging half: reduce it in element chunks (each chunk is an independent rooted reduction)
+      const size_t es = sy_dtype_size(dt), maxe = (c->stage_bytes / 2 / es) / 64 * 64;
+      if (maxe == 0) { sy_set_error("reduce: no staging space"); return SY_ERR_NOMEM; }
+      for (size_t b = 0; b < count; b += maxe) {
+        const size_t n = count - b < maxe ? count - b : maxe;
+        int rc2 = sy_reduce(c, (const char*)in + b * es, out ? (char*)out + b * es : nullptr, n, dt, op, root, stream);
+        if (rc2) return rc2;
+      }
+      return SY_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(stage_half(c, 0), in, bytes, cudaMemcpyDeviceToDevice, s));
     in_off = stage_half_off(c, 0);
   }
@@ -375,7 +385,18 @@ extern "C" int sy_gather(sy_comm* c, const void* in, void* out, size_t count, in
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
   // every rank must agree on the destination offset: non-roots cannot know the root's `out`,
   // so the rooted gather always lands in the staging half and the root copies out
-  if (bytes * c->world > c->stage_bytes / 2) { sy_set_error("gather: larger than staging"); return SY_ERR_NOMEM; }
+  if (bytes * c->world > c->stage_bytes / 2) {
+    // column chunks: gather [world x n] pieces into the staging half, the root scatters them into place with a strided copy
+    const size_t piece = (c->stage_bytes / 2 / c->world) & ~(size_t)255;
+    if (piece == 0) { sy_set_error("gather: no staging space"); return SY_ERR_NOMEM; }
+    for (size_t off = 0; off < bytes; off += piece) {
+      const size_t n = bytes - off < piece ? bytes - off : piece;
+      int rc2 = k_gather(c, (const char*)in + off, stage_half_off(c, 1), n, root, stream);
+      if (rc2) return rc2;
+      if (c->rank == root) CUDA_TRY(cudaMemcpy2DAsync((char*)out + off, bytes, stage_half(c, 1), n, n, c->world, cudaMemcpyDeviceToDevice, s));
+    }
+    return SY_OK;
+  }
   int rc = k_gather(c, in, stage_half_off(c, 1), bytes, root, stream);
   if (rc) return rc;
   if (c->rank == root) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes * c->world, cudaMemcpyDeviceToDevice, s));
@@ -389,7 +410,17 @@ extern "C" int sy_scatter(sy_comm* c, const void* in, void* out, size_t count, i
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
-  if (bytes * c->world > c->stage_bytes / 2) { sy_set_error("scatter: larger than staging"); return SY_ERR_NOMEM; }
+  if (bytes * c->world > c->stage_bytes / 2) {
+    const size_t piece = (c->stage_bytes / 2 / c->world) & ~(size_t)255;
+    if (piece == 0) { sy_set_error("scatter: no staging space"); return SY_ERR_NOMEM; }
+    for (size_t off = 0; off < bytes; off += piece) {
+      const size_t n = bytes - off < piece ? bytes - off : piece;
+      if (c->rank == root) CUDA_TRY(cudaMemcpy2DAsync(stage_half(c, 0), n, (const char*)in + off, bytes, n, c->world, cudaMemcpyDeviceToDevice, s));
+      int rc2 = k_scatter(c, stage_half_off(c, 0), (char*)out + off, n, root, stream);
+      if (rc2) return rc2;
+    }
+    return SY_OK;
+  }
   if (c->rank == root) CUDA_TRY(cudaMemcpyAsync(stage_half(c, 0), in, bytes * c->world, cudaMemcpyDeviceToDevice, s));
   return k_scatter(c, stage_half_off(c, 0), out, bytes, root, stream);
 }

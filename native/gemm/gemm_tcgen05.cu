@@ -1470,6 +1470,7 @@ int launch(const void* A, const void* B, void* Cc, int M, int N, int K, int lda,
 
 #include "conv_halo.inc"
 #include "wgrad_halo.inc"
+#include "stem_s2d.inc"
 
 extern "C" const char* sy_gemm_last_error() { return g_err; }
 extern "C" unsigned long long sy_gemm_launch_count() { return g_launches.load(); }

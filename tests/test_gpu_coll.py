@@ -74,3 +74,19 @@ def test_flag_protocol_litmus_over_nvlink():
     ok, outs = run_ranks("_litmus_worker.py", 2, extra=["--rounds", "500"], gpu=True, timeout=300)
     assert ok, "\n".join(o[-3000:] for o in outs)
     assert all("transport=gpu" in o for o in outs)
+
+
+@pytest.mark.multigpu
+def test_data_parallel_trainer_equals_single_gpu(tmp_path):
+    """N ranks x the same batch: the averaged gradient equals the 1-GPU gradient, so the parameters after 3 steps of the fused
+    all-reduce + SGD kernel must equal the 1-GPU run (full ResNet-50, CUDA graph, NVLS / P2P transport).  Different per-rank data is
+    not comparable with a single large batch (BatchNorm statistics are per rank); the collectives' numerics with different data per
+    rank are covered by test_multi_gpu_collectives."""
+    _need_multi()
+    world = min(_ngpu(), 8)
+    ref = str(tmp_path / "ref.pt")
+    ok, outs = run_ranks("_trainer_worker.py", 1, extra=["--ref", ref], gpu=True, timeout=600)
+    assert ok, outs[0][-3000:]
+    ok, outs = run_ranks("_trainer_worker.py", world, extra=["--ref", ref], gpu=True, timeout=900,
+                         env={"SHIPYARD_COLL_TIMEOUT_MS": "180000"})
+    assert ok, "\n".join(o[-3000:] for o in outs)

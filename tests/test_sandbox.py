@@ -28,7 +28,8 @@ def _result(b, job, task):
 
 
 @needs_ns
-def test_data_volume_bind_and_private_tmp(tmp_path):
+def test_data_volume_bind_and_private_tmp(tmp_path, monkeypatch):
+    monkeypatch.setenv("SHIPYARD_SANDBOX_PRIVATE_TMP", "1")          # a container's own /tmp (opt-in; TMPDIR is always private)
     host = tmp_path / "hostdata"
     host.mkdir()
     (host / "in.txt").write_text("payload")
@@ -62,7 +63,7 @@ def test_data_volume_bind_and_private_tmp(tmp_path):
 
 @needs_ns
 def test_keep_container_scratch_without_rm(tmp_path):
-    tasks = [{"id": "t", "docker_image": "busybox", "remove_container_after_exit": False, "command": "echo keep > /tmp/kept"}]
+    tasks = [{"id": "t", "docker_image": "busybox", "remove_container_after_exit": False, "command": "echo keep > $TMPDIR/kept"}]
     cfg, b = make(tmp_path, tasks=tasks)
     up(cfg, b)
     run(cfg, b)
@@ -89,7 +90,9 @@ def test_restrict_default_bind_mounts_hides_node_root(tmp_path):
 
 
 @pytest.mark.skipif(os.geteuid() != 0 or MODE != "mountns", reason="user_identity switching needs root")
-def test_user_identity_specific_user(tmp_path):
+def test_user_identity_specific_user(tmp_path, monkeypatch):
+    # pytest's base directory under /tmp is 0700 root: with the task's own /tmp the state dir is re-attached below fresh 0755 directories
+    monkeypatch.setenv("SHIPYARD_SANDBOX_PRIVATE_TMP", "1")
     tasks = [{"id": "t", "docker_image": "busybox", "command": 'echo "uid=$(id -u) gid=$(id -g)"; echo mine > "$AZ_BATCH_TASK_WORKING_DIR/f"'}]
     cfg, b = make(tmp_path, tasks=tasks, job={"user_identity": {"specific_user": {"uid": 12345, "gid": 23456}}})
     os.chmod(tmp_path, 0o755)
