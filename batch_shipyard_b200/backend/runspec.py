@@ -65,6 +65,7 @@ def base_env(b, pool: dict, job: dict, task_id: str, tdir: str, nodes: list[dict
         "SHIPYARD_POOL_ID": pid, "SHIPYARD_STATE_DIR": b.root, "SHIPYARD_GPUS": ",".join(gpu_ids),
         "SHIPYARD_NUM_GPUS": str(len(gpu_ids)), "SHIPYARD_NUM_INSTANCES": str(max(1, len(nodes))),
         "SHIPYARD_PYTHON": sys.executable, "SHIPYARD_HOME": _REPO_ROOT,
+        "SHIPYARD_STAGE_MANIFEST": os.path.join(tdir, ".shipyard.stage.json"),
         "PYTHONPATH": _REPO_ROOT + (os.pathsep + os.environ["PYTHONPATH"] if os.environ.get("PYTHONPATH") else ""),
     }
     if gpu_ids and len(nodes) == 1:

@@ -12,6 +12,7 @@ egress), /root/reference/cargo/task_file_mover.py:87-141, /root/reference/convoy
 from __future__ import annotations
 
 import argparse
+from typing import Optional
 import fnmatch
 import os
 import shutil
@@ -28,12 +29,15 @@ def _match(rel: str, include: Iterable[str], exclude: Iterable[str]) -> bool:
     return not any(fnmatch.fnmatch(rel, p) for p in exclude)
 
 
-def copy_tree(src: str, dst: str, include=(), exclude=()) -> tuple[int, int]:
-    """Copy files under `src` (or the single file `src`) to `dst`; returns (files, bytes)."""
+def copy_tree(src: str, dst: str, include=(), exclude=(), collect: Optional[list] = None) -> tuple[int, int]:
+    """Copy files under `src` (or the single file `src`) to `dst`; returns (files, bytes); `collect` receives the written paths."""
     n = nb = 0
     if os.path.isfile(src):
         os.makedirs(dst, exist_ok=True)
-        shutil.copy2(src, os.path.join(dst, os.path.basename(src)))
+        out = os.path.join(dst, os.path.basename(src))
+        shutil.copy2(src, out)
+        if collect is not None:
+            collect.append(out)
         return 1, os.path.getsize(src)
     for d, _, fs in os.walk(src):
         for fn in fs:
@@ -44,8 +48,33 @@ def copy_tree(src: str, dst: str, include=(), exclude=()) -> tuple[int, int]:
             out = os.path.join(dst, rel)
             os.makedirs(os.path.dirname(out), exist_ok=True)
             shutil.copy2(p, out)
+            if collect is not None:
+                collect.append(out)
             n += 1; nb += os.path.getsize(p)
     return n, nb
+
+
+def record_stage_manifest(paths: list, source: str) -> Optional[str]:
+    """Append ingressed files to the task's staging manifest ($SHIPYARD_STAGE_MANIFEST, set by the runner spec): the list the
+    task-side stager (ops.stage.stage_task_inputs) pushes file -> pinned arena -> HBM while the first step runs."""
+    mpath = os.environ.get("SHIPYARD_STAGE_MANIFEST")
+    if not mpath or not paths:
+        return None
+    import json
+    try:
+        with open(mpath) as f:
+            man = json.load(f)
+    except (OSError, ValueError):
+        man = {"version": 1, "files": []}
+    known = {e["path"] for e in man["files"]}
+    for p in paths:
+        if p not in known:
+            man["files"].append({"path": p, "bytes": os.path.getsize(p), "source": source})
+    tmp = mpath + ".tmp"
+    with open(tmp, "w") as f:
+        json.dump(man, f, indent=1)
+    os.replace(tmp, mpath)
+    return mpath
 
 
 def storage_root(state_dir: str, link: str) -> str:
@@ -119,7 +148,9 @@ def main(argv=None) -> int:
         if not os.path.exists(src):
             print(f"mover: ingress source {src} does not exist", file=sys.stderr)
             return 1
-        n, nb = copy_tree(src, a.local, a.include, a.exclude)
+        written: list = []
+        n, nb = copy_tree(src, a.local, a.include, a.exclude, collect=written)
+        record_stage_manifest(written, f"{a.link}:{a.remote}")
         _log("download", f"ingress {a.link}:{a.remote} -> {a.local}: {n} files, {nb} bytes")
         return 0
     if a.cmd == "egress":

@@ -39,6 +39,10 @@ def _bind(lib):
     lib._hpcg_bound = True
 
 
+class HPCGValidityError(RuntimeError):
+    """The run failed its validity gate: no GFLOP/s figure may be reported for it."""
+
+
 @dataclass
 class Level:
     nx: int
@@ -251,6 +255,57 @@ class HPCG:
         norms.append(float(st["rnorm2"].sqrt()))
         return norms
 
+    # -- validity gate (HPCG's TestSymmetry / TestCG, applied to THIS run before anything is timed) ------------------------
+    def symmetry_departure(self) -> dict:
+        """|x'Ay - y'Ax| and |x'M^-1 y - y'M^-1 x|, scaled as in HPCG's TestSymmetry: both the operator and the multigrid
+        preconditioner must be symmetric for CG to be valid.  Distributed: the dot products are global."""
+        L = self.levels[0]
+        g = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        n = L.nx * L.ny * L.nz
+        x = torch.rand(n, dtype=torch.float64, generator=g).to(self.dev)
+        y = torch.rand(n, dtype=torch.float64, generator=g).to(self.dev)
+        ax, ay = torch.empty_like(x), torch.empty_like(x)
+        self.spmv(0, x, ax); self.spmv(0, y, ay)
+        xn, yn = float(self.dot(x, x).sqrt()), float(self.dot(y, y).sqrt())
+        eps = 2.220446049250313e-16
+        d_spmv = abs(float(self.dot(x, ay)) - float(self.dot(y, ax))) / ((xn * float(self.dot(ay, ay).sqrt()) + yn * float(self.dot(ax, ax).sqrt())) * eps)
+        mx, my = torch.empty_like(x), torch.empty_like(x)
+        self.mg(0, x, mx); mx = mx.clone()
+        self.mg(0, y, my)
+        d_mg = abs(float(self.dot(x, my)) - float(self.dot(y, mx))) / ((xn * float(self.dot(my, my).sqrt()) + yn * float(self.dot(mx, mx).sqrt())) * eps)
+        return {"spmv_departure_in_eps": d_spmv, "mg_departure_in_eps": d_mg}
+
+    def validate(self, b: torch.Tensor, iters: int = 50, sym_tol_eps: float = 1e4) -> dict:
+        """Gate for `benchmark`: (1) SpMV and MG symmetric to within `sym_tol_eps` machine epsilons (scaled), (2) the optimised
+        path that will be timed (CUDA graph, device-resident scalars) reproduces the residual of the plain eager fp64 path after
+        the same `iters` iterations, (3) CG actually reduces the residual.  Raises HPCGValidityError instead of letting a broken run
+        print a GFLOP/s figure (round 1 reported numbers at 256^3 without any such check)."""
+        out = self.symmetry_departure()
+        x = torch.zeros_like(b)
+        eager = self.cg(b, x, iters=iters, graph=False)
+        red_eager = eager[-1] / max(eager[0], 1e-300)
+        out.update(iterations=iters, eager_reduction=red_eager, eager_monotone_fraction=sum(1 for u, v in zip(eager, eager[1:]) if v <= u * 1.0000001) / max(1, len(eager) - 1))
+        red_graph = None
+        if self.cuda and iters % 2 == 0 and iters >= 4:
+            x.zero_()
+            gn = self.cg(b, x, iters=iters, graph=True)
+            red_graph = gn[-1] / max(gn[0], 1e-300)
+            out["graph_reduction"] = red_graph
+        problems = []
+        if out["spmv_departure_in_eps"] > sym_tol_eps:
+            problems.append(f"SpMV is not symmetric ({out['spmv_departure_in_eps']:.3g} eps)")
+        if out["mg_departure_in_eps"] > sym_tol_eps:
+            problems.append(f"the MG preconditioner is not symmetric ({out['mg_departure_in_eps']:.3g} eps)")
+        if not (red_eager < 1.0):
+            problems.append(f"CG does not reduce the residual (eager reduction {red_eager:.3g})")
+        if red_graph is not None and abs(red_graph - red_eager) > 1e-3 * red_eager + 1e-14:
+            problems.append(f"the CUDA-graph path differs from the eager path after {iters} iterations ({red_graph:.6g} vs {red_eager:.6g})")
+        out["passed"] = not problems
+        out["problems"] = problems
+        if problems:
+            raise HPCGValidityError("; ".join(problems))
+        return out
+
     def flops_per_iteration(self) -> float:
         def nnz(L, gz):
             return (3 * L.nx - 2) * (3 * L.ny - 2) * (3 * gz - 2)
@@ -264,7 +319,7 @@ class HPCG:
     def benchmark(self, seconds: float = 10.0, iters_per_set: int = 50) -> dict:
         b = self.rhs()
         x = torch.zeros_like(b)
-        norms = self.cg(b, x, iters=min(10, iters_per_set))            # warm-up + validity
+        validity = self.validate(b, iters=iters_per_set)                # raises: an invalid run reports no GFLOP/s
         self._sync(); self.comm.barrier(); self._sync()
         t0 = time.time(); sets = 0; total_iters = 0
         l0 = self._launches(); r0 = getattr(self, "_replays", 0) * getattr(self, "_graph_launches", 0)
@@ -289,4 +344,6 @@ class HPCG:
                 "local_grid": [self.levels[0].nx, self.levels[0].ny, self.levels[0].nz],
                 "own_kernel_launches": self._launches() - l0 + getattr(self, "_replays", 0) * getattr(self, "_graph_launches", 0) - r0,
                 "cuda_graph": bool(getattr(self, "_graph", None) is not None),
-                "transport": self.comm.transport}
+                "transport": self.comm.transport, "validity": validity,
+                "note": "fixed 50-iteration CG sets as in HPCG: max_error_vs_ones is informative (the 4-level V-cycle leaves the 32^3 coarse "
+                        "grid unsolved, so 50 iterations do not converge the 256^3 problem); validity = symmetry + graph == eager fp64"}

@@ -8,7 +8,6 @@ state store, and a ready-to-use ``prometheus.yml`` + Grafana dashboard are writt
 """
 from __future__ import annotations
 
-import json
 import os
 import signal
 import subprocess
@@ -32,21 +31,6 @@ def _alive(pid) -> bool:
         return False
 
 
-def _dashboard() -> dict:
-    def panel(i, title, expr, unit="short"):
-        return {"id": i, "title": title, "type": "timeseries", "gridPos": {"h": 8, "w": 12, "x": (i % 2) * 12, "y": (i // 2) * 8},
-                "targets": [{"expr": expr, "legendFormat": "{{gpu}}{{pool}}{{job}} {{state}}"}], "fieldConfig": {"defaults": {"unit": unit}}}
-    return {"title": "Shipyard B200", "uid": "shipyard-b200", "schemaVersion": 36, "refresh": "10s", "panels": [
-        panel(0, "GPU utilisation", "shipyard_gpu_utilization_percent", "percent"),
-        panel(1, "GPU power", "shipyard_gpu_power_watts", "watt"),
-        panel(2, "GPU memory used", "shipyard_gpu_memory_used_bytes", "bytes"),
-        panel(3, "SM clock", "shipyard_gpu_sm_clock_mhz"),
-        panel(4, "Pool nodes by state", "shipyard_pool_nodes"),
-        panel(5, "Task slot utilisation", "shipyard_pool_slot_utilization_percent", "percent"),
-        panel(6, "Tasks by state", "shipyard_job_tasks"),
-        panel(7, "Timing events", "shipyard_timing_events_total")]}
-
-
 def start(b, config: dict) -> dict:
     st = b.store.try_get("service", "monitor", "") or {}
     if _alive(st.get("pid")):
@@ -54,11 +38,8 @@ def start(b, config: dict) -> dict:
     ms = S.monitoring_services(config) if config.get("monitoring") else S.MonitoringServices()
     port = int(os.environ.get("SHIPYARD_EXPORTER_PORT", "9100"))
     d = _dir(b)
-    with open(os.path.join(d, "prometheus.yml"), "w") as f:
-        f.write(f"global:\n  scrape_interval: {ms.prometheus_scrape_interval}s\nscrape_configs:\n  - job_name: shipyard\n"
-                f"    file_sd_configs:\n      - files: ['{os.path.join(d, 'file_sd.json')}']\n")
-    with open(os.path.join(d, "grafana_dashboard.json"), "w") as f:
-        json.dump(_dashboard(), f, indent=1)
+    from . import stack
+    stack.write_stack(d, int(ms.prometheus_scrape_interval), port, int(ms.prometheus_port))     # prometheus.yml, compose, grafana provisioning + dashboard
     log = open(os.path.join(d, "exporter.log"), "ab")
     p = subprocess.Popen([sys.executable, "-m", "batch_shipyard_b200.monitor.exporter", "--state-dir", b.root, "--port", str(port),
                           "--polling-interval", str(ms.resource_polling_interval)], stdout=log, stderr=log, stdin=subprocess.DEVNULL,

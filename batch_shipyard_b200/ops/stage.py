@@ -33,6 +33,9 @@ def load() -> C.CDLL:
         lib.sy_stage_destroy.argtypes = [vp]
         lib.sy_stage_submit_file.argtypes = [vp, C.c_char_p, vp, sz, sz]; lib.sy_stage_submit_file.restype = lg
         lib.sy_stage_submit_host.argtypes = [vp, vp, sz, vp]; lib.sy_stage_submit_host.restype = lg
+        lib.sy_stage_submit_pinned.argtypes = [vp, vp, sz, vp, vp]; lib.sy_stage_submit_pinned.restype = lg
+        lib.sy_stage_pinned_alloc.argtypes = [vp, sz]; lib.sy_stage_pinned_alloc.restype = vp
+        lib.sy_stage_pinned_free.argtypes = [vp, vp]
         lib.sy_stage_wait.argtypes = [vp, lg, db]
         lib.sy_stage_stream_wait.argtypes = [vp, lg, vp]
         lib.sy_stage_ptr.argtypes = [vp, lg]; lib.sy_stage_ptr.restype = vp
@@ -93,6 +96,14 @@ class Stager:
             raise StageError(self.lib.sy_stage_last_error().decode())
         return int(t)
 
+    def submit_pinned(self, host_ptr: int, nbytes: int, dptr: int, wait_event: int = 0) -> int:
+        """Page-locked source -> device with ONE cudaMemcpyAsync on a worker copy stream (no bounce through the arena); the copy
+        stream first waits for `wait_event` (a raw cudaEvent_t, e.g. ``torch.cuda.Event.cuda_event``) when given."""
+        t = self.lib.sy_stage_submit_pinned(self._h, C.c_void_p(host_ptr), nbytes, C.c_void_p(dptr), C.c_void_p(wait_event or 0))
+        if t < 0:
+            raise StageError(self.lib.sy_stage_last_error().decode())
+        return int(t)
+
     def wait(self, ticket: int, timeout: float = -1.0) -> bool:
         rc = self.lib.sy_stage_wait(self._h, ticket, float(timeout))
         if rc == 1:
@@ -129,3 +140,59 @@ class Stager:
         self.lib.sy_stage_stats(self._h, out, C.byref(busy))
         return {"bytes_staged": int(out[0]), "memcpy_calls": int(out[1]), "arena_bytes": int(out[2]),
                 "chunk_bytes": int(out[3]), "busy_seconds": float(busy.value)}
+
+
+class StagedInputs:
+    """Task input files on their way to (or in) HBM: ``tensors[path]`` is a uint8 CUDA tensor over the stager-owned buffer, valid
+    for kernels enqueued after :meth:`chain` on that stream (or after :meth:`wait` on the host)."""
+
+    def __init__(self, stager: Stager, entries: list):
+        self.stager, self.entries = stager, entries          # entries: (path, ticket, nbytes)
+        self.t_submit = __import__("time").time()
+
+    def chain(self, cuda_stream: int) -> None:
+        """Event-chain `cuda_stream` behind every copy (sy_stage_stream_wait): the host does not block on the transfers."""
+        for _, t, _ in self.entries:
+            self.stager.stream_wait(t, cuda_stream)
+
+    def wait(self) -> None:
+        for _, t, _ in self.entries:
+            self.stager.wait(t)
+
+    def done(self) -> bool:
+        return all(self.stager.query(t).state in ("done", "failed") for _, t, _ in self.entries)
+
+    @property
+    def nbytes(self) -> int:
+        return sum(n for _, _, n in self.entries)
+
+    def tensors(self) -> dict:
+        import torch
+        out = {}
+        for path, t, n in self.entries:
+            view = type("_V", (), {})()
+            view.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (self.stager.ptr(t), False), "version": 3, "strides": None}
+            view._owner = self
+            out[path] = torch.as_tensor(view, device=f"cuda:{self.stager.device}")
+        return out
+
+    def summary(self) -> dict:
+        secs = max((self.stager.query(t).transfer_seconds for _, t, _ in self.entries), default=0.0)
+        return {"files": len(self.entries), "bytes": self.nbytes, "slowest_ticket_s": round(secs, 4)}
+
+
+def stage_task_inputs(device: int, manifest: Optional[str] = None, stager: Optional[Stager] = None, concurrency: int = 4) -> Optional[StagedInputs]:
+    """Push every file of the task's ``input_data`` (the manifest the ingress prologue wrote, $SHIPYARD_STAGE_MANIFEST) through
+    file -> pinned arena -> HBM tickets and return immediately; the caller runs its first step(s) and chains the consumer stream
+    behind the tickets when it needs the data.  Reference counterpart: blobxfer downloads in the task prologue
+    (/root/reference/convoy/data.py:219-291, scripts/shipyard_blobxfer.sh) — data only ever reached the node's disk."""
+    import json
+    manifest = manifest or os.environ.get("SHIPYARD_STAGE_MANIFEST")
+    if not manifest or not os.path.exists(manifest):
+        return None
+    with open(manifest) as f:
+        files = [e for e in json.load(f).get("files", []) if e.get("bytes", 0) > 0 and os.path.exists(e["path"])]
+    if not files:
+        return None
+    st = stager or Stager(device, arena_bytes=concurrency * 2 * (16 << 20), concurrency=concurrency)
+    return StagedInputs(st, [(e["path"], st.submit_file(e["path"]), int(e["bytes"])) for e in files])

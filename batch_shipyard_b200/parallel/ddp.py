@@ -206,8 +206,12 @@ class FusedDataParallelTrainer:
 
 
 class InputStager:
-    """Pinned uint8 NHWC host batches -> device, double-buffered on a copy stream,
-    converted to normalised bf16 by our kernel right before the step."""
+    """Pinned uint8 NHWC host batches -> device through ``libshipyard_stage`` (native/stage/stage.cpp): every prefetch is a ticket on
+    the stager's copy stream (ONE cudaMemcpyAsync straight from the pinned batch, issued only after the step that last read the
+    slot has finished — an event dependency, the host never blocks), and the training stream is event-chained behind the ticket
+    (``sy_stage_stream_wait``) right before our conversion kernel.  The same mover stages files (task ``input_data``, artefacts)
+    file -> pinned arena -> HBM; K12 of SURVEY.md §2E, the data path the reference delegates to blobxfer containers
+    (/root/reference/convoy/data.py:567-876, scripts/shipyard_blobxfer.sh)."""
 
     def __init__(self, tr: FusedDataParallelTrainer, depth: int = 2):
         self.tr, self.depth = tr, depth
@@ -221,12 +225,17 @@ class InputStager:
         self.host_loss = [torch.zeros((), dtype=torch.float32, pin_memory=pin) for _ in range(depth)]
         self.h2d_bytes = self.host_x[0].numel() + self.host_y[0].numel() * 8
         self.d2h_bytes = 4
+        self.native = None
+        self._tickets: list = [None] * depth
         if tr.is_cuda:
-            self.copy_stream = torch.cuda.Stream(dev)
-            self.copied = [torch.cuda.Event() for _ in range(depth)]
+            from ..ops.stage import Stager          # no torch fallback on a GPU box: a missing extension must fail loudly
+            self.native = Stager(dev.index if dev.index is not None else torch.cuda.current_device(), arena_bytes=8 << 20, concurrency=1)
             self.consumed = [torch.cuda.Event() for _ in range(depth)]
             self.loss_ready = [torch.cuda.Event() for _ in range(depth)]
         self._issued = [False] * depth
+        self.transfer_seconds = 0.0
+        self.transfers = 0
+        self.staging_summary_cached = {"path": "host (cpu)"}
 
     def fill_synthetic(self, seed: int = 0) -> None:
         g = torch.Generator().manual_seed(seed)
@@ -239,20 +248,33 @@ class InputStager:
         if not tr.is_cuda:
             self.dev_x[slot].copy_(self.host_x[slot]); self.dev_y[slot].copy_(self.host_y[slot])
             return
-        with torch.cuda.stream(self.copy_stream):
-            if self._issued[slot]:
-                self.copy_stream.wait_event(self.consumed[slot])   # the step that read this slot is done with it
-            self.dev_x[slot].copy_(self.host_x[slot], non_blocking=True)
-            self.dev_y[slot].copy_(self.host_y[slot], non_blocking=True)
-            self.copied[slot].record(self.copy_stream)
+        self._reap(slot)
+        # the copy may only overwrite the slot once the step that read it is done: an event the copy stream waits for
+        wait_ev = self.consumed[slot].cuda_event if self._issued[slot] else 0
+        hx, hy = self.host_x[slot], self.host_y[slot]
+        self._tickets[slot] = (self.native.submit_pinned(hx.data_ptr(), hx.numel(), self.dev_x[slot].data_ptr(), wait_ev),
+                               self.native.submit_pinned(hy.data_ptr(), hy.numel() * 8, self.dev_y[slot].data_ptr(), wait_ev))
         self._issued[slot] = True
+
+    def _reap(self, slot: int) -> None:
+        """Release the finished tickets of a slot (their bookkeeping; the device buffers are ours) and account their time."""
+        ts = self._tickets[slot]
+        if ts is None:
+            return
+        for t in ts:
+            self.native.wait(t)
+            self.transfer_seconds += self.native.query(t).transfer_seconds
+            self.native.release(t)
+        self.transfers += 1
+        self._tickets[slot] = None
 
     def run_step(self, slot: int) -> None:
         """Consume a prefetched slot: convert, train one step, start the loss read-back."""
         tr = self.tr
         if tr.is_cuda:
             cur = torch.cuda.current_stream(tr.dev)
-            cur.wait_event(self.copied[slot])
+            for t in self._tickets[slot]:
+                self.native.stream_wait(t, cur.cuda_stream)         # event-chain the step behind the H2D ticket
             if tr.s2d:
                 _fused.u8_to_s2d_norm(self.dev_x[slot], tr._x_store)
             else:
@@ -268,6 +290,22 @@ class InputStager:
             tr.static_y.copy_(self.dev_y[slot])
             tr.step()
             self.host_loss[slot].copy_(tr.static_loss)
+
+    def staging_summary(self) -> dict:
+        """What moved the inputs (for the bench record)."""
+        if self.native is None:
+            return {"path": "host (cpu)"}
+        st = self.native.stats()
+        return {"path": "libshipyard_stage: pinned -> HBM tickets on the stager's copy stream, step event-chained behind the ticket",
+                "tickets": self.transfers * 2, "memcpy_calls": st["memcpy_calls"], "bytes_staged": st["bytes_staged"]}
+
+    def close(self) -> None:
+        if self.native is not None:
+            for s in range(self.depth):
+                self._reap(s)
+            self.staging_summary_cached = self.staging_summary()
+            self.native.close()
+            self.native = None
 
     def read_loss(self, slot: int) -> float:
         if self.tr.is_cuda:

@@ -97,21 +97,24 @@ class Cascade:
 
     # -- pulling --------------------------------------------------------------------------------
     def _stage_bytes(self, path: str) -> int:
-        """Stream the artefact through the pinned arena (HBM when a device is set, page cache otherwise)."""
+        """Read the artefact through the native stager's pinned arena with bounded concurrency (page cache warm + integrity of every
+        file proven by a full read; HBM when a device is set).  A stager failure is a pull failure: it surfaces in the resource's
+        error column and counts against the retry budget — it is never replaced by a silent os.path.getsize()."""
+        from ..ops.stage import Stager
         files = [path] if os.path.isfile(path) else [os.path.join(d, f) for d, _, fs in os.walk(path) for f in fs]
-        total = 0
-        try:
-            from ..ops.stage import Stager
-            with self._lock:
-                if self._stager is None:
-                    self._stager = Stager(self.device, arena_bytes=64 << 20, concurrency=min(4, self.concurrency))
-            tickets = [(self._stager.submit_file(f), f) for f in files if os.path.getsize(f) > 0]
-            for t, f in tickets:
+        total, t0 = 0, time.time()
+        with self._lock:
+            if self._stager is None:
+                self._stager = Stager(self.device, arena_bytes=64 << 20, concurrency=min(4, self.concurrency))
+        tickets = [(self._stager.submit_file(f), f) for f in files if os.path.getsize(f) > 0]
+        for t, f in tickets:
+            try:
                 self._stager.wait(t)
                 total += self._stager.query(t).bytes
+            finally:
                 self._stager.release(t)
-        except Exception:  # noqa: BLE001 - staging is an optimisation; sizes still count
-            total = sum(os.path.getsize(f) for f in files)
+        dt = max(time.time() - t0, 1e-9)
+        self._event("stage", f"path={path},bytes={total},seconds={dt:.4f},mb_per_s={total / dt / 1e6:.1f},device={self.device}")
         return total
 
     def _default_pull(self, resource: str) -> int:

@@ -201,7 +201,19 @@ def run_shipyard(args, rank, world, local):
         e2e = {"value": round(B * world / (ms_e2e / 1e3), 2), "unit": "images/sec", "ms_per_step": round(ms_e2e, 3),
                "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
                "last_loss": round(losses[-1], 4)}
+        st.close()
+        e2e["input_staging"] = st.staging_summary_cached
     comm.check_status()
+    if os.environ.get("SHIPYARD_BENCH_RERACE"):
+        # diagnostic: run the dispatcher's race again AFTER the benchmark for the first shapes and print both tables
+        from batch_shipyard_b200.ops import conv as _cv
+        import torch.nn.functional as _F   # noqa: F401
+        for key in list(_cv._PLANS)[:int(os.environ["SHIPYARD_BENCH_RERACE"])]:
+            n_, cin, h, w_, cout, k, stride = key
+            xx = (torch.randn(n_, cin, h, w_, device=dev) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ww = (torch.randn(cout, cin, k, k, device=dev) * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            again = _cv._autotune(xx, ww, stride)
+            print(json.dumps({"rerace": "x".join(map(str, key)), "first": _cv._PLANS[key].timings_us, "again": again.timings_us}), file=sys.stderr)
     own = tr.kernels_per_step
     out = {
         "metric": "resnet50_train_images_per_sec", "value": round(B * world / (ms / 1e3), 2), "unit": "images/sec",
@@ -281,6 +293,19 @@ def _conv_summary():
             out[pas + "_tc_2cta"] = sum(1 for v in tab.values() if v[pas] in ("tc2", "th2"))
             out[pas + "_halo"] = sum(1 for v in tab.values() if v[pas].startswith("th"))
         out["fprop_fused_bn_stats"] = sum(1 for v in tab.values() if v["stats"])
+        out["stem"] = "tc (native/gemm/stem_s2d.inc)" if _conv.stem_native() else "cudnn"
+        out["tie_band"] = _conv._TIE
+        # the race itself, compact: per shape and pass [library us, best own us, winner]
+        race = {}
+        for key, v in tab.items():
+            t = v.get("timings_us") or {}
+            row = {}
+            for pas in ("fprop", "dgrad", "wgrad"):
+                lib = t.get(pas + "_cudnn")
+                own = [x for k, x in t.items() if k.startswith(pas + "_") and "cudnn" not in k]
+                row[pas] = [lib, min(own) if own else None, v[pas]]
+            race[key] = row
+        out["race_us"] = race
         out["halo"] = _conv.halo_state()
         if os.environ.get("SHIPYARD_CONV_PLAN_DUMP"):
             os.makedirs("gpurun_out", exist_ok=True)

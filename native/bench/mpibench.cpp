@@ -7,10 +7,15 @@
 // Extension: -d runs on device buffers (cudaMalloc), which routes the MPI_* calls to the
 // sm_100a collective kernels through libshipyard_mpi.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <mpi.h>
+#include <nccl.h>
+#include <algorithm>
+#include "sy_coll.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -20,8 +25,150 @@ static size_t parse_size(const char* s) {
   return (size_t)v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// --compare: every operation and size on the shipyard kernels AND on the real NCCL library, in this one process, with one harness:
+// device buffers, >= 20 warm-up calls, >= 20 individually timed calls (CUDA events on the collective's own stream, an L2 flush and a
+// cross-rank barrier before each, so ranks enter together and no call finds its input in L2), the MEDIAN per rank and the MAX over
+// ranks.  NCCL is dlopen'ed (the library PyTorch bundles when present, else the system one) and called at the C level; its
+// communicator is bootstrapped with the unique id broadcast through MPI.  One JSON line per (op, size).
+struct Nccl {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  std::string path;
+  bool load() {
+    std::vector<std::string> cands;
+    if (const char* e = getenv("SHIPYARD_NCCL_LIB")) cands.push_back(e);
+    if (const char* py = getenv("SHIPYARD_PYTHON")) {           // <venv>/bin/python -> <venv>/lib/python*/site-packages/nvidia/nccl/lib
+      std::string p = py; size_t s = p.rfind("/bin/");
+      if (s != std::string::npos) {
+        const std::string cmd = "ls " + p.substr(0, s) + "/lib/python*/site-packages/nvidia/nccl/lib/libnccl.so.2 2>/dev/null | head -1";
+        if (FILE* f = popen(cmd.c_str(), "r")) { char b[1024]; if (fgets(b, sizeof b, f)) { std::string l = b; while (!l.empty() && (l.back() == '\n' || l.back() == ' ')) l.pop_back(); if (!l.empty()) cands.push_back(l); } pclose(f); }
+      }
+    }
+    cands.push_back("libnccl.so.2"); cands.push_back("libnccl.so");
+    for (auto& c : cands) { h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL); if (h) { path = c; break; } }
+    if (!h) return false;
+#define SYM(n) n = (decltype(n))dlsym(h, "nccl" #n); if (!n) return false
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(AllGather); SYM(ReduceScatter); SYM(Broadcast);
+    SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetVersion);
+#undef SYM
+    return true;
+  }
+};
+
+static int run_compare(size_t beg, size_t end, int factor, int iters, int warm, const std::vector<std::string>& ops_in, int rank, int world) {
+  std::vector<std::string> ops = ops_in;
+  if (ops.empty()) ops = {"allreduce", "allgather", "reduce_scatter", "alltoall", "broadcast", "allreduce_fp8"};
+  sy_comm* sc = (sy_comm*)MPIX_Shipyard_comm();
+  cudaStream_t st = (cudaStream_t)MPIX_Device_stream();
+  MPIX_Set_device_async(1);
+  Nccl nc; ncclComm_t ncomm = nullptr; int nver = 0;
+  const bool have_nccl = nc.load();
+  if (have_nccl) {
+    ncclUniqueId id; memset(&id, 0, sizeof id);
+    if (rank == 0) nc.GetUniqueId(&id);
+    MPI_Bcast(&id, (int)sizeof id, MPI_BYTE, 0, MPI_COMM_WORLD);          // host buffer: the shared-memory face
+    if (nc.CommInitRank(&ncomm, world, id, rank) != ncclSuccess) { fprintf(stderr, "mpibench: ncclCommInitRank failed\n"); ncomm = nullptr; }
+    nc.GetVersion(&nver);
+  }
+  const size_t maxb = end;                                               // total bytes of the per-rank buffer (NCCL-tests convention)
+  // symmetric buffers (zero-copy path of the shipyard kernels) and plain cudaMalloc buffers (what an unmodified program passes)
+  char* sym_in = (char*)MPIX_Sym_alloc(maxb + 256); char* sym_out = (char*)MPIX_Sym_alloc(maxb + 256);
+  char *pl_in = nullptr, *pl_out = nullptr, *flush = nullptr; const size_t flush_bytes = 256ul << 20;
+  void *q8 = nullptr, *q8s = nullptr;
+  cudaMalloc(&pl_in, maxb + 256); cudaMalloc(&pl_out, maxb + 256); cudaMalloc(&flush, flush_bytes);
+  cudaMalloc(&q8, maxb / 2 + 256); cudaMalloc(&q8s, maxb / 64 + 256);
+  if (!sym_in || !sym_out || !pl_in || !pl_out || !flush) { fprintf(stderr, "mpibench: buffer allocation failed (raise SHIPYARD_COLL_HEAP for --compare up to %zu bytes)\n", maxb); return 2; }
+  cudaMemsetAsync(sym_in, 0, maxb, st); cudaMemsetAsync(pl_in, 0, maxb, st); cudaStreamSynchronize(st);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  char tr[16]; MPIX_Query_shipyard_transport(tr, sizeof tr);
+  if (rank == 0) printf("{\"bench\": \"shipyard-mpibench --compare\", \"world\": %d, \"transport\": \"%s\", \"nccl\": \"%s\", \"nccl_version\": %d, "
+                        "\"warmup\": %d, \"iters\": %d, \"timing\": \"cuda events per call, L2 flush + barrier before each, median per rank, max over ranks\"}\n",
+                        world, tr, have_nccl ? nc.path.c_str() : "unavailable", nver, warm, iters);
+  auto measure = [&](const std::function<void()>& fn, size_t bytes) -> double {
+    for (int i = 0; i < warm; ++i) fn();
+    cudaStreamSynchronize(st);
+    std::vector<float> ts;
+    for (int i = 0; i < iters; ++i) {
+      if (bytes >= (1ul << 20)) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);     // evict the operands from L2
+      sy_barrier(sc, st);                                                             // ranks enter together (device-side flag barrier)
+      cudaEventRecord(e0, st); fn(); cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ts.push_back(ms * 1e3f);
+    }
+    std::sort(ts.begin(), ts.end());
+    double med = ts[ts.size() / 2], mx = 0;
+    MPI_Allreduce(&med, &mx, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+    return mx;
+  };
+  for (auto& op : ops) {
+    for (size_t total = beg; total <= end; total *= (size_t)factor) {
+      const size_t n = std::max<size_t>((size_t)world, total / 4 / world * world);     // fp32 elements of the per-rank buffer
+      const size_t bytes = n * 4, per = n / world;
+      double busf = op == "allreduce" || op == "allreduce_fp8" ? 2.0 * (world - 1) / world : op == "broadcast" ? 1.0 : (double)(world - 1) / world;
+      std::function<void()> f_sym, f_plain, f_nccl;
+      if (op == "allreduce") {
+        f_sym = [&] { sy_allreduce(sc, sym_in, sym_out, n, SY_F32, SY_F32, 1.0f, SY_SUM, SY_ALGO_AUTO, st); };
+        f_plain = [&] { sy_allreduce(sc, pl_in, pl_out, n, SY_F32, SY_F32, 1.0f, SY_SUM, SY_ALGO_AUTO, st); };
+        if (ncomm) f_nccl = [&] { nc.AllReduce(pl_in, pl_out, n, ncclFloat32, ncclSum, ncomm, st); };
+      } else if (op == "allreduce_fp8") {
+        // block-scaled fp8 output (e4m3 + one e8m0 scale per 32 elements) from bf16 input; NCCL comparator: the bf16 all-reduce it replaces
+        f_sym = [&] { sy_allreduce_fp8_blockscaled(sc, sym_in, SY_BF16, q8, q8s, n * 2, 1.0f, st); };
+        if (ncomm) f_nccl = [&] { nc.AllReduce(pl_in, pl_out, n * 2, ncclBfloat16, ncclSum, ncomm, st); };
+      } else if (op == "allgather") {
+        f_sym = [&] { sy_allgather(sc, sym_in, sym_out, per * 4, SY_U8, st); };
+        f_plain = [&] { sy_allgather(sc, pl_in, pl_out, per * 4, SY_U8, st); };
+        if (ncomm) f_nccl = [&] { nc.AllGather(pl_in, pl_out, per, ncclFloat32, ncomm, st); };
+      } else if (op == "reduce_scatter") {
+        f_sym = [&] { sy_reduce_scatter(sc, sym_in, sym_out, per, SY_F32, SY_F32, 1.0f, SY_SUM, st); };
+        f_plain = [&] { sy_reduce_scatter(sc, pl_in, pl_out, per, SY_F32, SY_F32, 1.0f, SY_SUM, st); };
+        if (ncomm) f_nccl = [&] { nc.ReduceScatter(pl_in, pl_out, per, ncclFloat32, ncclSum, ncomm, st); };
+      } else if (op == "alltoall") {
+        f_sym = [&] { sy_alltoall(sc, sym_in, sym_out, per * 4, SY_U8, st); };
+        f_plain = [&] { sy_alltoall(sc, pl_in, pl_out, per * 4, SY_U8, st); };
+        if (ncomm) f_nccl = [&] {
+          nc.GroupStart();
+          for (int r = 0; r < world; ++r) { nc.Send(pl_in + (size_t)r * per * 4, per, ncclFloat32, r, ncomm, st); nc.Recv(pl_out + (size_t)r * per * 4, per, ncclFloat32, r, ncomm, st); }
+          nc.GroupEnd();
+        };
+      } else if (op == "broadcast") {
+        f_sym = [&] { sy_broadcast(sc, sym_in, sym_in, bytes, SY_U8, 0, st); };
+        f_plain = [&] { sy_broadcast(sc, pl_in, pl_in, bytes, SY_U8, 0, st); };
+        if (ncomm) f_nccl = [&] { nc.Broadcast(pl_in, pl_in, n, ncclFloat32, 0, ncomm, st); };
+      } else { if (rank == 0) fprintf(stderr, "mpibench: unknown --compare op %s\n", op.c_str()); break; }
+      const double t_sym = f_sym ? measure(f_sym, bytes) : -1, t_plain = f_plain ? measure(f_plain, bytes) : -1, t_nccl = f_nccl ? measure(f_nccl, bytes) : -1;
+      MPIX_Device_sync();
+      if (rank == 0) {
+        const double best = t_plain > 0 && t_plain < t_sym ? t_plain : t_sym;
+        printf("{\"op\": \"%s\", \"bytes\": %zu, \"world\": %d, \"sy_sym_us\": %.2f, \"sy_plain_us\": %.2f, \"nccl_us\": %.2f, \"speedup_sym_vs_nccl\": %.3f, "
+               "\"speedup_plain_vs_nccl\": %.3f, \"sy_busbw_gbs\": %.1f, \"nccl_busbw_gbs\": %.1f, \"frac_of_770gbs\": %.3f}\n",
+               op.c_str(), bytes, world, t_sym, t_plain, t_nccl, t_nccl > 0 ? t_nccl / t_sym : 0.0, t_nccl > 0 && t_plain > 0 ? t_nccl / t_plain : 0.0,
+               bytes * busf / best / 1e3, t_nccl > 0 ? bytes * busf / t_nccl / 1e3 : 0.0, bytes * busf / best / 1e3 / 770.0);
+        fflush(stdout);
+      }
+    }
+  }
+  MPIX_Device_sync();
+  if (ncomm) nc.CommDestroy(ncomm);
+  MPIX_Set_device_async(0);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   size_t beg = 8, end = 1024; int iters = 100; bool device = false; bool check = false;
+  bool compare = false; int factor = 2, warm = 20;
   std::vector<std::string> ops;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "-b") && i + 1 < argc) beg = parse_size(argv[++i]);
@@ -29,6 +176,9 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-i") && i + 1 < argc) iters = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-d")) device = true;
     else if (!strcmp(argv[i], "-c")) check = true;
+    else if (!strcmp(argv[i], "--compare")) { compare = true; device = true; if (iters == 100) iters = 25; }
+    else if (!strcmp(argv[i], "--factor") && i + 1 < argc) factor = atoi(argv[++i]) < 2 ? 2 : atoi(argv[i]);
+    else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warm = atoi(argv[++i]);
     else if (argv[i][0] != '-') ops.push_back(argv[i]);
   }
   // the LLNL mpiBench operation set; the vector variants run with uniform counts (host buffers only in this MPI face)
@@ -44,6 +194,12 @@ int main(int argc, char** argv) {
     int ndev = 0; cudaGetDeviceCount(&ndev);
     if (ndev == 0) { if (rank == 0) fprintf(stderr, "mpibench: -d requested but no GPU visible\n"); MPI_Finalize(); return 3; }
     cudaSetDevice(g ? atoi(g) % ndev : rank % ndev);
+  }
+  if (compare) {
+    if (world < 2) { if (rank == 0) fprintf(stderr, "mpibench: --compare needs at least 2 ranks\n"); MPI_Finalize(); return 3; }
+    const int rc = run_compare(beg < 1024 ? 1024 : beg, end, factor, iters < 20 ? 20 : iters, warm < 20 ? 20 : warm, ops, rank, world);
+    MPI_Finalize();
+    return rc;
   }
   const size_t maxb = end * (size_t)world;
   void *sbuf = nullptr, *rbuf = nullptr;

@@ -58,7 +58,7 @@ TARGETS = {
     "taskrun": ("cxx-exe", "shipyard-taskrun", ["runner/taskrun.cpp"], [], ["-lpthread"]),
     "gpuprobe": ("nvcc-exe", "shipyard-gpuprobe", ["probe/gpuprobe.cpp"], [], ["-ldl"]),
     "mpibench": ("nvcc-exe", "shipyard-mpibench", ["bench/mpibench.cpp"],
-                 ["-I", os.path.join(NATIVE, "include")], []),
+                 ["-I", os.path.join(NATIVE, "include"), "-I", os.path.join(NATIVE, "coll")], ["-ldl", "-lshipyard_coll"]),
     "diskbench": ("cxx-exe", "shipyard-diskbench", ["bench/diskbench.cpp"], [], ["-lpthread"]),
 }
 # link-time dependencies between our own libraries

@@ -126,6 +126,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "nvls_min_bytes")) c->nvls_min_bytes = v;
   else if (!strcmp(k, "timeout_ms")) c->timeout_ms = v;
   else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
+  else if (!strcmp(k, "bcast_sag_min_bytes")) c->bcast_sag_min_bytes = v;
   else if (!strcmp(k, "nvls_min_world")) c->nvls_min_world = v;
   else return SY_ERR_ARG;
   return SY_OK;
@@ -139,6 +140,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "nvls_min_bytes")) return c->nvls_min_bytes;
   if (!strcmp(k, "timeout_ms")) return c->timeout_ms;
   if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
+  if (!strcmp(k, "bcast_sag_min_bytes")) return c->bcast_sag_min_bytes;
   if (!strcmp(k, "nvls_min_world")) return c->nvls_min_world;
   return -1;
 }

@@ -62,6 +62,7 @@ struct sy_comm {
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
   long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
+  long bcast_sag_min_bytes = 8 << 20;   // broadcasts from this size on run as pipelined scatter + all-gather (world >= 4, multicast)
   // VMM handles (opaque to other TUs)
   void* impl = nullptr;
   // stub transport state

@@ -773,6 +773,39 @@ k_broadcast_k(const __grid_constant__ CommDev c, const void* in, size_t out_off,
   epoch_store(c, ep);
 }
 
+// Large broadcast (K7) as a pipelined scatter + all-gather in ONE kernel.  A single source cannot drive multimem.st above ~290 GB/s
+// (profiles/coll_sweeps.md: 256 MB at 8 GPUs took 925 us, NCCL 473 us), but it can drive its NVLink egress with plain P2P stores:
+// the root deals shard j (bytes / world) to rank j, and every rank re-broadcasts its own shard through the switch (multimem.st),
+// so all eight egress links carry the all-gather while the root's link carries the scatter.  The data is cut into chunks; block b
+// owns chunks b, b + grid, ...; per chunk: root scatters -> block barrier (same block index on every rank) -> every rank multicasts its
+// piece.  While the other ranks multicast chunk k the root is already scattering chunk k + 1, so its link never idles:
+// ~ bytes / link bandwidth in total instead of 2x.  Requires bytes % (world * 16) == 0 and 16-byte aligned buffers.
+__global__ void __launch_bounds__(512)
+k_broadcast_sag_k(const __grid_constant__ CommDev c, const void* in, size_t out_off, size_t bytes, int root, size_t chunk) {
+  uint32_t ep = epoch_load(c);
+  block_barrier(c, ep);                                   // nobody still reads `out`; the root's input is ready
+  const size_t shard = bytes / (size_t)c.world;
+  const size_t nchunks = (shard + chunk - 1) / chunk;
+  for (size_t k = blockIdx.x; k < nchunks; k += gridDim.x) {
+    const size_t o = k * chunk, n = shard - o < chunk ? shard - o : chunk;
+    if (c.rank == root) {
+      for (int j = 0; j < c.world; ++j) {                 // piece (j, k) -> rank j's own shard region (its own heap for j == root)
+        int p = root + 1 + j; if (p >= c.world) p -= c.world;          // start with the next rank: all egress queues fill evenly
+        char* dst = c.heap[p] + out_off + (size_t)p * shard + o;
+        const char* src = (const char*)in + (size_t)p * shard + o;
+        if (dst != src) copy_bytes_block(dst, src, n, threadIdx.x, blockDim.x, false);
+      }
+    }
+    block_barrier(c, ep);                                 // piece (rank, k) has landed in my heap (release/acquire at system scope)
+    copy_bytes_block(c.mc + out_off + (size_t)c.rank * shard + o, c.heap[c.rank] + out_off + (size_t)c.rank * shard + o, n,
+                     threadIdx.x, blockDim.x, true);
+  }
+  // blocks with fewer chunks than the others still have to take part in the per-chunk barriers of their block index only, so no
+  // cross-block coupling exists; one last barrier makes every multicast store visible before anybody returns
+  block_barrier(c, ep);
+  epoch_store(c, ep);
+}
+
 // all-to-all: block p of `in` -> offset rank*bytes of out in peer p (K4: uniform NVSwitch,
 // so no ring schedule; all peers are written concurrently)
 __global__ void __launch_bounds__(512)
@@ -1321,6 +1354,19 @@ int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt
   return SY_OK;
 }
 int k_broadcast(sy_comm* c, const void* in, size_t out_off, size_t bytes, int root, bool nvls, void* stream) {
+  // (the choice must be identical on every rank: it may only depend on symmetric quantities, never on the root's input pointer)
+  if (nvls && c->has_mc && c->world >= 4 && bytes >= (size_t)c->bcast_sag_min_bytes && bytes % ((size_t)c->world * 16) == 0 &&
+      (out_off & 15) == 0) {
+    // every block must see the same number of per-chunk barriers on every rank: the chunk schedule depends only on (bytes, world, grid)
+    const size_t shard = bytes / (size_t)c->world;
+    size_t chunk = 128ul << 10;
+    int blocks = (int)c->max_blocks < 64 ? (int)c->max_blocks : 64;
+    const size_t nchunks = (shard + chunk - 1) / chunk;
+    if ((size_t)blocks > nchunks) blocks = (int)nchunks;
+    k_broadcast_sag_k<<<blocks, 512, 0, (cudaStream_t)stream>>>(devof(c), in, out_off, bytes, root, chunk);
+    LAUNCH_CHECK(c);
+    return SY_OK;
+  }
   int g = grid_for(c, bytes / 16 + 1, (int)c->threads, 2);
   if (!nvls && g < c->world && bytes >= (64u << 10)) g = c->world;
   k_broadcast_k<<<g, (int)c->threads, 0, (cudaStream_t)stream>>>(devof(c), in, out_off, bytes, root, nvls ? 1 : 0);

@@ -102,7 +102,9 @@ sy_comm* dev_comm() {
   cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking);
   return g.dev;
 }
+bool g_async = false;      // MPIX_Set_device_async(1): device-buffer collectives return after the enqueue (the caller times / syncs)
 void dev_sync() {
+  if (g_async) return;
   cudaError_t e = cudaStreamSynchronize(g.stream);
   if (e != cudaSuccess) die("stream sync: %s", cudaGetErrorString(e));
   if (sy_comm_status(g.dev) != 0) die("collective watchdog fired: a peer rank did not arrive");
@@ -387,5 +389,17 @@ int MPIX_Query_shipyard_transport(char* name, int len) {
   return MPI_SUCCESS;
 }
 void* MPIX_Sym_alloc(size_t bytes) { return sy_sym_alloc(dev_comm(), bytes); }
+// Extensions for device-timed benchmarking (bench/mpibench.cpp --compare): the stream the device-buffer collectives run on, an
+// asynchronous mode in which they return right after the kernel is enqueued, and the explicit synchronisation (with the watchdog check).
+void* MPIX_Device_stream(void) { dev_comm(); return (void*)g.stream; }
+int MPIX_Set_device_async(int on) { g_async = on != 0; return MPI_SUCCESS; }
+int MPIX_Device_sync(void) {
+  if (!g.dev) return MPI_SUCCESS;
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) die("stream sync: %s", cudaGetErrorString(e));
+  if (sy_comm_status(g.dev) != 0) die("collective watchdog fired: a peer rank did not arrive");
+  return MPI_SUCCESS;
+}
+void* MPIX_Shipyard_comm(void) { return (void*)dev_comm(); }
 
 }  // extern "C"

@@ -83,7 +83,11 @@ int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sdt, int dest,
 
 /* shipyard extensions */
 int MPIX_Query_shipyard_transport(char* name, int len);   /* "stub" | "p2p" | "nvls" for device buffers */
-void* MPIX_Sym_alloc(size_t bytes);                        /* symmetric device allocation (zero-copy collectives) */
+void* MPIX_Sym_alloc(size_t bytes);
+void* MPIX_Device_stream(void);                           /* cudaStream_t the device-buffer collectives run on */
+int MPIX_Set_device_async(int on);                        /* 1: device-buffer collectives return after the enqueue */
+int MPIX_Device_sync(void);                               /* synchronise that stream and check the collective watchdog */
+void* MPIX_Shipyard_comm(void);                           /* the sy_comm* behind the device-buffer collectives */                        /* symmetric device allocation (zero-copy collectives) */
 
 #ifdef __cplusplus
 }

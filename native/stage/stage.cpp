@@ -39,6 +39,8 @@ struct Ticket {
   long id = 0;
   std::string path;            // file source (empty => host memory source)
   const void* host_src = nullptr;
+  bool pinned_src = false;     // host_src is page-locked: one cudaMemcpyAsync straight from it, no bounce through the arena
+  cudaEvent_t wait_ev = nullptr;   // the copy stream waits for this event first (e.g. "the step that read dptr last is done")
   size_t offset = 0, bytes = 0;
   void* dptr = nullptr;        // destination (device, or host in host-only mode)
   bool own_dptr = false;
@@ -102,6 +104,22 @@ static void worker_main(sy_stage* s, int wi) {
     }
     size_t done = 0; int ci = 0;
     std::vector<bool> chunk_busy(s->chunks_per_worker, false);
+    if (ok && gpu && t->wait_ev) {
+      cudaError_t e = cudaStreamWaitEvent(stream, t->wait_ev, 0);
+      if (e != cudaSuccess) { ok = false; err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e); }
+    }
+    if (ok && t->pinned_src && t->bytes) {
+      // page-locked source (a pinned input batch): DMA straight from it, the arena is not involved
+      if (gpu) {
+        cudaError_t e = cudaMemcpyAsync(t->dptr, t->host_src, t->bytes, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) { ok = false; err = std::string("cudaMemcpyAsync(pinned): ") + cudaGetErrorString(e); }
+        s->memcpy_calls.fetch_add(1);
+      } else {
+        memcpy(t->dptr, t->host_src, t->bytes);
+      }
+      done = t->bytes;
+      { std::lock_guard<std::mutex> lk(s->mu); t->done_bytes = done; }
+    }
     while (ok && done < t->bytes) {
       const size_t n = t->bytes - done < s->chunk_bytes ? t->bytes - done : s->chunk_bytes;
       char* buf = slice + (size_t)ci * s->chunk_bytes;
@@ -224,6 +242,25 @@ extern "C" long sy_stage_submit_host(sy_stage* s, const void* host, size_t bytes
   t->host_src = host; t->bytes = bytes; t->dptr = dptr;
   return submit(s, t);
 }
+
+// Page-locked host source (cudaHostAlloc / cudaHostRegister / torch pin_memory): copied with ONE cudaMemcpyAsync on a worker's copy
+// stream, after `wait_event` (a cudaEvent_t, may be null) has completed on the device — the double-buffered input path of a
+// training loop: "copy batch i+1 into the slot as soon as step i-1, which read that slot, is done", without blocking the host.
+extern "C" long sy_stage_submit_pinned(sy_stage* s, const void* host_pinned, size_t bytes, void* dptr, void* wait_event) {
+  if (!dptr && s->device >= 0 && bytes == 0) { g_err = "empty transfer"; return -1; }
+  Ticket* t = new Ticket();
+  t->host_src = host_pinned; t->pinned_src = true; t->bytes = bytes; t->dptr = dptr; t->wait_ev = (cudaEvent_t)wait_event;
+  return submit(s, t);
+}
+
+// page-locked host memory from the stager (so callers without a CUDA framework can fill batches in place)
+extern "C" void* sy_stage_pinned_alloc(sy_stage* s, size_t bytes) {
+  void* p = nullptr;
+  if (s->device >= 0) { cudaSetDevice(s->device); if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; } }
+  else p = malloc(bytes);
+  return p;
+}
+extern "C" void sy_stage_pinned_free(sy_stage* s, void* p) { if (!p) return; if (s->device >= 0) cudaFreeHost(p); else free(p); }
 
 // 0 = done, 1 = timeout, 2 = failed, 3 = unknown ticket
 extern "C" int sy_stage_wait(sy_stage* s, long id, double timeout_s) {

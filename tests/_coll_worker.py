@@ -207,6 +207,21 @@ def main():
     comm.broadcast(sb, root=W - 1); sync()
     assert torch.equal(sb.cpu(), gen(W - 1, cnt, torch.float32, "cpu", salt=23)), "sym broadcast"
     checks += 3
+    if not a.quick or W >= 4:
+        # large broadcast: at world >= 4 with multicast this is the pipelined scatter + all-gather kernel (k_broadcast_sag_k); every root,
+        # in place on a symmetric buffer and from a plain (non-symmetric, deliberately 4-byte-misaligned) source into a plain destination
+        big_n = (24 << 20) // 4
+        lb = comm.alloc(big_n, torch.float32)
+        for root in sorted({0, W // 2, W - 1}):
+            lb.copy_(gen(R, big_n, torch.float32, dev, salt=61 + root)); sync(); comm.barrier(); sync()
+            comm.broadcast(lb, root=root); sync()
+            assert torch.equal(lb.cpu(), gen(root, big_n, torch.float32, "cpu", salt=61 + root)), f"large sym broadcast root={root}"
+            comm.barrier(); sync()
+        pl = torch.zeros(big_n + 1, dtype=torch.float32, device=dev)[1:]
+        pl.copy_(gen(R, big_n, torch.float32, dev, salt=67)); sync()
+        comm.broadcast(pl, root=1 % W); sync()
+        assert torch.equal(pl.cpu(), gen(1 % W, big_n, torch.float32, "cpu", salt=67)), "large plain broadcast"
+        checks += 2
     comm.barrier(); sync()
     comm.reset_heap()
     # ---- put / wait signal ---------------------------------------------------

@@ -52,7 +52,7 @@ def test_halo_candidates_are_gated_and_self_checked():
 
 
 def test_experimental_variant_table():
-    """Which not-yet-validated kernel variants SHIPYARD_CONV_EXPERIMENTAL=1 would add per ResNet-50 layer shape (pure shape logic)."""
+    """Which additional halo variants take part in the race per ResNet-50 layer shape (pure shape logic)."""
     e = conv.experimental_impls
     assert e(256, 64, 56, 56, 64, 3, 1) == {"fprop": ["tha", "th264", "th264a"], "dgrad": ["tha"], "wgrad": ["th"]}
     assert e(256, 128, 28, 28, 128, 3, 1) == {"fprop": ["th2w"], "dgrad": ["th2w"], "wgrad": ["th"]}
@@ -62,4 +62,13 @@ def test_experimental_variant_table():
     assert e(256, 64, 56, 56, 256, 1, 1) == {"fprop": [], "dgrad": [], "wgrad": []}           # 1x1
     assert e(256, 128, 56, 56, 128, 3, 1)["fprop"] == []                                     # 56x56 box does not fit the 23 KB slots
     assert set(conv._HALO_KW) >= {"th", "th2", "tha", "th264", "th264a", "th2w"}
-    assert not conv._EXP                                                                     # off unless the environment asks for it
+    assert conv._EXP                                        # validated on hardware in round 2: in the race unless SHIPYARD_CONV_EXPERIMENTAL=0
+
+
+def test_race_tie_break_prefers_native_inside_the_noise_band():
+    t = {"dgrad_cudnn": 100.0, "dgrad_tc": 102.0, "dgrad_tc2": 110.0}
+    assert conv._pick(t, "dgrad_") == "dgrad_tc"            # 2 % slower: inside the 3 % repeatability of the race
+    t["dgrad_tc"] = 104.0
+    assert conv._pick(t, "dgrad_") == "dgrad_cudnn"         # outside the band the library wins
+    assert conv._pick({"wgrad_cudnn": 50.0}, "wgrad_") == "wgrad_cudnn"
+    assert conv._pick({"fprop_cudnn": 60.0, "fprop_tc_stats": 40.0, "fprop_th": 39.0}, "fprop_") == "fprop_th"

@@ -65,9 +65,6 @@ def test_k10_gemm_allreduce_fused(transport):
 
 
 @pytest.mark.multigpu
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="written after the last multi-GPU run of round 1 (the CPU/stub version runs in tests/test_coll_stub.py); "
-                           "set SHIPYARD_TEST_UNVERIFIED=1")
 def test_flag_protocol_litmus_over_nvlink():
     """Message-passing litmus on P2P-mapped flags (payload stores, release flag / acquire flag, payload loads), 500 ping-pong rounds."""
     _need_multi()

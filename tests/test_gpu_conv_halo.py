@@ -79,8 +79,6 @@ def test_halo_in_dispatcher_matches_library():
         conv.set_mode("auto")
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="variants written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1 to run them)")
 @pytest.mark.parametrize("variant", ["epi_alt", "weights_stationary", "pair64", "pair64_alt"])
 def test_halo_unverified_variants(variant):
     """Alternate-tile epilogue (BN = 64) and all-weights-stationary CTA pairs (128 channels, 28x28): same numerics as the base kernels."""
@@ -107,8 +105,6 @@ def test_halo_unverified_variants(variant):
     torch.testing.assert_close(dx.float(), dref, atol=0.05, rtol=2e-2)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="halo-load wgrad was written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1 to run it)")
 @pytest.mark.parametrize("n,cin,h,w,cout", [(4, 64, 56, 56, 64), (8, 128, 28, 28, 128), (8, 256, 14, 14, 128), (16, 128, 7, 7, 256), (6, 64, 12, 20, 64)])
 @pytest.mark.parametrize("splits", [0, 1, 3])
 def test_halo_wgrad_unverified(n, cin, h, w, cout, splits):

