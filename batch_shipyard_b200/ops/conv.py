@@ -49,9 +49,11 @@ class ConvPlan:
     timings_us: Optional[dict] = None
 
 
-# Tie-break of the race: an own kernel within this fraction of the library's time wins.  The race's own repeatability is ~2-3 %
-# (median of 5 graph replays of 4 launches), so inside that band "faster" is noise and the native kernel is preferred.
-_TIE = float(os.environ.get("SHIPYARD_CONV_TIE", "0.03"))
+# Tie-break of the race: an own kernel within this fraction of the library's time wins.  The race's own repeatability was measured by
+# running it twice in one process (gpurun_out/c6_bench.err, "rerace"): the SAME cuDNN kernel on the same shape differs by up to 3.6 %
+# between the two runs (158.7 vs 164.5 us), ours by up to 1.2 %.  Inside a 5 % band "faster" is therefore noise and the native kernel is
+# preferred; SHIPYARD_CONV_TIE=0 gives the strict race.
+_TIE = float(os.environ.get("SHIPYARD_CONV_TIE", "0.05"))
 
 
 def _pick(t: dict, prefix: str) -> str:
@@ -118,7 +120,9 @@ def _tc_caps(x: torch.Tensor, w: torch.Tensor, stride: int) -> dict:
         g = ok and cin % 8 == 0 and cout % 8 == 0
         return {"fprop": g, "dgrad": g, "wgrad": g}
     sup = ok and _gemm.conv_supported(x, w, stride, pad)
-    return {"fprop": sup, "wgrad": sup, "dgrad": sup and stride == 1 and cout % 64 == 0}
+    # 1x1 / stride-2 (downsample branches): the data gradient is a GEMM with a scattering epilogue (ops.gemm.conv1x1_s2_dgrad)
+    s2_1x1 = ok and k == 1 and stride == 2 and h % 2 == 0 and wd % 2 == 0 and cin % 8 == 0 and cout % 8 == 0
+    return {"fprop": sup, "wgrad": sup, "dgrad": (sup and stride == 1 and cout % 64 == 0) or s2_1x1}
 
 
 def _time(fn, iters: int = 5, reps: int = 4) -> float:
@@ -172,6 +176,8 @@ def _fprop_tc(x, w, stride, pad, stats, two_cta=False, impl=None):
 def _dgrad_tc(dy, x, w, stride, pad, two_cta=False, impl=None):
     if impl in _HALO_KW:
         return _gemm.conv3x3_halo(dy, w, True, **_HALO_KW[impl])
+    if w.shape[2] == 1 and stride == 2:
+        return _gemm.conv1x1_s2_dgrad(dy, w)
     if w.shape[2] == 1 and stride == 1:
         n, cin, h, wd = x.shape
         cout = w.shape[0]

@@ -53,6 +53,7 @@ def load() -> C.CDLL:
         lib.sy_conv3x3_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
         lib.sy_conv3x3_halo_rows.argtypes = [C.c_int, C.c_int]
         lib.sy_conv3x3_wgrad_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.sy_gemm_bf16_nn_scatter2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
         lib.sy_stem_s2d_fprop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         lib.sy_stem_s2d_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p]
@@ -167,6 +168,22 @@ def _workspace(dev: torch.device):
     if key not in _WS:
         _WS[key] = (torch.zeros(_WS_FLOATS, dtype=torch.float32, device=dev), torch.zeros(_WS_TICKETS, dtype=torch.int32, device=dev))
     return _WS[key]
+
+
+def conv1x1_s2_dgrad(dy: torch.Tensor, w: torch.Tensor, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """dX[N, Cin, 2P, 2Q] of a 1x1 / stride-2 convolution (the ResNet downsample branches) from dY[N, Cout, P, Q] (channels_last) and
+    W[Cout, Cin, 1, 1]: ONE tcgen05 GEMM (weights read in place as an MN-major operand) whose st.global epilogue scatters row (n, p, q)
+    to pixel (2p, 2q) and writes the zeros of the three pixels the forward pass skipped — no memset, no strided copy."""
+    n, cout, p, q = dy.shape
+    cin = w.shape[1]
+    dys, ws_ = _nhwc_storage(dy), _nhwc_storage(w)
+    dx = torch.empty((n, 2 * p, 2 * q, cin), dtype=torch.bfloat16, device=dy.device)
+    lib = load()
+    rc = lib.sy_gemm_bf16_nn_scatter2(C.c_void_p(dys.data_ptr()), C.c_void_p(ws_.data_ptr()), C.c_void_p(dx.data_ptr()), n, p, q, cout, cin,
+                                      block_n, max_ctas, C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"sy_gemm_bf16_nn_scatter2 failed ({rc}): {lib.sy_gemm_last_error().decode()}")
+    return dx.permute(0, 3, 1, 2)
 
 
 def gemm_nt_wgrad(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,

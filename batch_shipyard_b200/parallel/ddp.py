@@ -51,7 +51,10 @@ class FlatParameters:
         off, lay = 0, {}
         for n, p in named:
             lay[n] = (off, p.numel(), tuple(p.shape), p.dim() == 4)
-            off = _round_up(off + p.numel(), 8)
+            # every tensor starts on a 256-byte boundary.  Measured (gpurun_out/c5_bench.err, "rerace"): with 16-byte aligned weights
+            # the TMA loads of the weight operand (128-byte rows straddling two cache lines) slow the short-K 1x1 GEMMs down by up to
+            # 2x (64 -> 64 channels: dgrad 83 us vs 39 us with an aligned weight); cuDNN keeps its weights in registers and does not care.
+            off = _round_up(off + p.numel(), 128)
         total = _round_up(off, 8 * max(1, comm.world))
         self.layout = FlatLayout(total, lay)
         dev = comm.torch_device

@@ -266,13 +266,24 @@ def _collective_block(comm, rank, world, dev) -> dict:
         return max_over_ranks(e0.elapsed_time(e1) * 1e3 / iters, world, dev)
 
     out = {}
+    nv = _NvlinkCounters(dev.index if dev.index is not None else 0)
     for label, nbytes, iters, warm in (("allreduce_256MB", 256 << 20, 20, 5), ("allreduce_8B", 8, 200, 20)):
         n = nbytes // 4
         sym = comm.alloc(n, torch.float32); sym.fill_(1.0)
         plain = torch.ones(n, dtype=torch.float32, device=dev)
+        c0 = nv.read()
         ours = time_us(lambda: comm.all_reduce(sym, sym, scale=1.0 / world), iters, warm)
+        c1 = nv.read()
         nccl = time_us(lambda: dist.all_reduce(plain, op=dist.ReduceOp.AVG), iters, warm)
+        c2 = nv.read()
         row = {"shipyard_us": round(ours, 2), "nccl_us": round(nccl, 2), "speedup": round(nccl / ours, 3)}
+        if c0 and c1 and c2 and nbytes >= (1 << 20):
+            # NVML NVLink data counters of this GPU (KiB) over the warm-up + timed calls: bytes that really crossed the links per call
+            calls = iters + warm
+            row["nvlink_counters_rank0"] = {
+                "shipyard_tx_mb_per_call": round((c1[0] - c0[0]) / 1024.0 / calls, 1), "shipyard_rx_mb_per_call": round((c1[1] - c0[1]) / 1024.0 / calls, 1),
+                "nccl_tx_mb_per_call": round((c2[0] - c1[0]) / 1024.0 / calls, 1), "nccl_rx_mb_per_call": round((c2[1] - c1[1]) / 1024.0 / calls, 1),
+                "message_mb": nbytes >> 20, "note": "two-shot through the switch moves ~ message x (N-1)/N out and in per GPU; in-switch reduction (NVLS) shows as rx ~ message/N"}
         if nbytes >= (1 << 20):
             f = 2.0 * (world - 1) / world * nbytes
             row["shipyard_busbw_gbs"] = round(f / ours / 1e3, 1); row["nccl_busbw_gbs"] = round(f / nccl / 1e3, 1)
@@ -280,6 +291,37 @@ def _collective_block(comm, rank, world, dev) -> dict:
         out[label] = row
     comm.check_status()
     return out
+
+
+class _NvlinkCounters:
+    """NVML NVLink throughput counters (data TX / RX, KiB, summed over the links of one GPU) — the evidence that a collective's bytes
+    crossed NVLink, since ncu cannot replay a cross-rank kernel."""
+
+    def __init__(self, index: int):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:  # noqa: BLE001
+            self.h = None
+
+    def read(self):
+        if self.h is None:
+            return None
+        try:
+            nv = self.nv
+            ids = [nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+            vals = nv.nvmlDeviceGetFieldValues(self.h, ids)
+            out = []
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    return None
+                out.append(int(v.value.ullVal))
+            return out
+        except Exception:  # noqa: BLE001
+            return None
 
 
 def _conv_summary():

@@ -182,7 +182,7 @@ int main(int argc, char** argv) {
     else if (argv[i][0] != '-') ops.push_back(argv[i]);
   }
   // the LLNL mpiBench operation set; the vector variants run with uniform counts (host buffers only in this MPI face)
-  if (ops.empty()) {
+  if (ops.empty() && !compare) {
     ops = {"Barrier", "Bcast", "Alltoall", "Allgather", "Gather", "Scatter", "Allreduce", "Reduce"};
     if (!device) { ops.push_back("Alltoallv"); ops.push_back("Allgatherv"); ops.push_back("Gatherv"); }
   }

@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <type_traits>
 #include "device_sync.cuh"   // cross-GPU block barrier shared with libshipyard_coll
 
 namespace {
@@ -433,12 +434,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if constexpr (kDirect) {          // thread (rr = et / 8, sub = et % 8): 16-byte piece `sub` of rows rr, rr + 16, ...: full 128 B lines per 8 lanes
             const int sub = et & 7, rr = et >> 3;
             if (n0 + sub * 8 < N) {
+              if (!kConv && geom.stride == 2) {
+                // data gradient of a 1x1 / stride-2 convolution: GEMM row (n, p, q) lands on pixel (2p, 2q) of dX[N, 2P, 2Q, ldc] and the
+                // three pixels the forward pass skipped get their zeros from the same thread: dX is written exactly once, no memset
+                const int pq = geom.P * geom.Q, W2 = 2 * geom.Q;
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                  const int r = p * 16 + rr, mrow = m_blk * BM + r;
+                  if (mrow < M) {
+                    const int img = mrow / pq, rem = mrow - img * pq, py = rem / geom.Q, qx = rem - py * geom.Q;
+                    __nv_bfloat16* o = c_ptr + ((size_t)(img * 2 * geom.P + 2 * py) * W2 + 2 * qx) * (size_t)ldc + n0 + sub * 8;
+                    st_global_v4(o, *reinterpret_cast<const uint4*>(cbuf + r * 128 + ((sub ^ (r & 7)) << 4)));
+                    st_global_v4(o + ldc, z4);
+                    st_global_v4(o + (size_t)W2 * ldc, z4);
+                    st_global_v4(o + (size_t)(W2 + 1) * ldc, z4);
+                  }
+                }
+              } else {
 #pragma unroll
               for (int p = 0; p < 8; ++p) {
                 const int r = p * 16 + rr;
                 if (m_blk * BM + r < M)
                   st_global_v4(c_ptr + (size_t)(m_blk * BM + r) * (size_t)ldc + n0 + sub * 8,
                                *reinterpret_cast<const uint4*>(cbuf + r * 128 + ((sub ^ (r & 7)) << 4)));
+              }
               }
             }
           } else {
@@ -1717,6 +1737,46 @@ extern "C" int sy_gemm_bf16_nn(const void* A, const void* B, void* C, int M, int
     case 64: return launch<64>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
     case 128: return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
     case 256: return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, nullptr, nullptr, max_ctas, s, true);
+  }
+  snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
+  return 1;
+}
+
+// Data gradient of a 1x1 / stride-2 convolution (the ResNet downsample branches): dX[Nb, 2P, 2Q, Cin] from dY[Nb*P*Q, Cout] and
+// W[Cout, Cin] read in place (MN-major B).  One GEMM whose st.global epilogue scatters row (n, p, q) to pixel (2p, 2q) and writes the
+// zeros of the three skipped pixels itself.  Cin % 8 == 0, pointers 16-byte aligned.
+extern "C" int sy_gemm_bf16_nn_scatter2(const void* dY, const void* W, void* dX, int Nb, int P, int Q, int Cout, int Cin, int block_n,
+                                        int max_ctas, void* stream) {
+  const int M = Nb * P * Q, N = Cin, K = Cout;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((N | K) & 7 || ((uintptr_t)dY | (uintptr_t)W | (uintptr_t)dX) & 15) { snprintf(g_err, sizeof g_err, "scatter2: channels %% 8, 16B aligned pointers"); return 1; }
+  if (!load_encode()) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no driver?)"); return 6; }
+  if (block_n <= 0) block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  auto go = [&](auto bn_tag) -> int {
+    constexpr int BN = decltype(bn_tag)::value;
+    using C = Cfg<BN>;
+    CUtensorMap ta, tb, tc;
+    if (!make_map(&ta, dY, K, M, K, BK, BM) || !make_map(&tb, W, N, K, N, 64, BK) || !make_map(&tc, dX, N, M, N, kEpiChunk, BM)) return 3;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = tiles < sms ? tiles : sms;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    auto kern = gemm_bf16_tn_kernel<BN, false, false, true, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "smem attribute: %s", cudaGetErrorString(e)); return 4; }
+    ConvGeom g{P, Q, 1, 1, 0, 2, 0, 0};
+    kern<<<grid, kThreadsTN, C::kSmemBytes, (cudaStream_t)stream>>>(ta, tb, tc, M, N, K, (const __nv_bfloat16*)nullptr, (float*)nullptr, g,
+                                                                    (__nv_bfloat16*)dX, N);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "launch: %s", cudaGetErrorString(e)); return 5; }
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  switch (block_n) {
+    case 64: return go(std::integral_constant<int, 64>{});
+    case 128: return go(std::integral_constant<int, 128>{});
+    case 256: return go(std::integral_constant<int, 256>{});
   }
   snprintf(g_err, sizeof g_err, "block_n must be 64, 128 or 256");
   return 1;

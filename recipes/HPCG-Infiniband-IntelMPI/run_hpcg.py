@@ -14,7 +14,7 @@ sys.path.insert(0, os.environ.get("SHIPYARD_HOME") or os.path.dirname(os.path.di
 
 import torch  # noqa: E402
 
-from batch_shipyard_b200.models.hpcg import HPCG  # noqa: E402
+from batch_shipyard_b200.models.hpcg import HPCG, HPCGValidityError  # noqa: E402
 from batch_shipyard_b200.ops.coll import Communicator  # noqa: E402
 
 
@@ -32,7 +32,14 @@ def main():
         torch.cuda.set_device(dev_index)
     session = (os.environ.get("SHIPYARD_COLL_SESSION") or os.environ.get("TORCHELASTIC_RUN_ID") or f"hpcg-{os.getppid()}") + "-hpcg"
     comm = Communicator(rank, world, session, dev_index, heap_bytes=256 << 20)
-    res = HPCG(comm, a.n, a.n, a.n, levels=a.levels).benchmark(seconds=a.t)
+    try:
+        res = HPCG(comm, a.n, a.n, a.n, levels=a.levels).benchmark(seconds=a.t)
+    except HPCGValidityError as e:
+        # validity gate (symmetry of A and of the preconditioner, optimised path == eager fp64 path): no GFLOP/s for an invalid run
+        if rank == 0:
+            print(json.dumps({"valid": False, "error": str(e), "world": world, "local_grid": [a.n, a.n, a.n]}), flush=True)
+        comm.close()
+        sys.exit(1)
     if rank == 0:
         print(json.dumps({k: (round(v, 6) if isinstance(v, float) and k != "residual_reduction" else v) for k, v in res.items()}), flush=True)
     comm.close()

@@ -68,6 +68,25 @@ def main():
         ng = h.cg(b, xg, iters=iters, graph=True)
         assert len(ng) == 2 and abs(ng[-1] - norms[-1]) <= 1e-6 * norms[0] + 1e-3 * norms[-1], f"graph CG differs: {ng[-1]} vs {norms[-1]}"
         assert (xg - x).abs().max().item() < 1e-6
+    # the recipe's validity gate (HPCG TestSymmetry + optimised path == eager path) passes on a correct build ...
+    v = h.validate(b, iters=8)
+    assert v["passed"] and v["spmv_departure_in_eps"] < 1e4 and v["mg_departure_in_eps"] < 1e4, v
+    # ... and trips on a broken operator: an asymmetric perturbation of SpMV must be reported, not benchmarked
+    from batch_shipyard_b200.models.hpcg import HPCGValidityError
+    real_spmv = h.spmv
+
+    def skewed(li, xin, yout):
+        real_spmv(li, xin, yout)
+        if li == 0:
+            yout[1:].add_(0.05 * xin[:-1])          # adds a strictly lower-triangular term: A is no longer symmetric
+    h.spmv = skewed
+    try:
+        h.validate(b, iters=4)
+        raise AssertionError("validity gate accepted an asymmetric operator")
+    except HPCGValidityError as e:
+        assert "not symmetric" in str(e), e
+    finally:
+        h.spmv = real_spmv
     comm.check_status()
     print(f"rank {a.rank} HPCG OK reduction {norms[-1] / norms[0]:.2e} spmv_err {err:.1e}", flush=True)
     comm.close()

@@ -283,3 +283,21 @@ def test_direct_store_epilogue_variants_in_subprocess():
                             "matches_fp32 or bias_stats or two_cta or conv_implicit or nn_mn_major or conv1x1_and_linear"],
                            env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
         assert p.returncode == 0, (extra, p.stdout[-4000:])
+
+
+@pytest.mark.parametrize("n,cin,cout,p,q", [(4, 64, 128, 14, 14), (2, 256, 512, 28, 28), (3, 72, 40, 5, 9), (8, 1024, 2048, 7, 7)])
+def test_conv1x1_stride2_dgrad_scatter_epilogue(n, cin, cout, p, q):
+    """dX of a 1x1 / stride-2 convolution: GEMM + scattering st.global epilogue (row -> pixel (2p, 2q), zeros for the skipped pixels)
+    against autograd in fp32; the output buffer is pre-filled with NaN-free garbage to prove every element is written exactly once."""
+    from batch_shipyard_b200.ops import gemm
+    torch.manual_seed(n + cin)
+    dy = (torch.randn(n, cout, p, q, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 1, 1, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x = torch.zeros(n, cin, 2 * p, 2 * q, device="cuda", requires_grad=True)
+    torch.nn.functional.conv2d(x, w.float(), stride=2).backward(dy.float())
+    for max_ctas in (0, 3):
+        torch.full((n * 4 * p * q * cin,), 7.0, device="cuda", dtype=torch.bfloat16)       # dirty the allocator's next block
+        dx = gemm.conv1x1_s2_dgrad(dy, w, max_ctas=max_ctas)
+        assert dx.shape == x.shape
+        torch.testing.assert_close(dx.float(), x.grad, atol=3e-2, rtol=2e-2)
+        assert float(dx[:, :, 1::2, :].abs().max()) == 0.0 and float(dx[:, :, :, 1::2].abs().max()) == 0.0
