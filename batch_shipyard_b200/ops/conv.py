@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import gemm as _gemm
+from .fused import zeros as _fused_zeros
 
 _MODE = os.environ.get("SHIPYARD_CONV_IMPL", "auto").lower()
 _PLANS: dict = {}
@@ -386,12 +387,13 @@ def plan_for(x: torch.Tensor, w: torch.Tensor, stride: int) -> ConvPlan:
 class _Conv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, plan: ConvPlan):
+        ctx.set_materialize_grads(False)          # the statistics output has no gradient: do not let autograd build a zeros tensor for it
         k = w.shape[2]
         pad = k // 2
         stats = None
         if plan.fprop != "cudnn":
             if plan.stats:
-                stats = torch.zeros(2 * w.shape[0], dtype=torch.float32, device=x.device)
+                stats = _fused_zeros(2 * w.shape[0], x.device)          # slice of the step's zero pool (one memset per step)
             y = _fprop_tc(x, w, stride, pad, stats, plan.fprop == "tc2", impl=plan.fprop)
         else:
             y = F.conv2d(x, w, None, stride, pad)

@@ -71,6 +71,7 @@ def _bind_bn(lib):
     lib.sy_ops_bn_apply_only.argtypes = [vp, vp, vp, vp, vp, fp, fp, fp, fp, fp, C.c_long, C.c_int, C.c_float,
                                          C.c_float, C.c_int, vp, vp]
     lib.sy_ops_bn_bwd.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.sy_ops_set_ws_prezeroed.argtypes = [C.c_int]
     lib.sy_ops_bn_bwd_dual.argtypes = [vp, vp, vp, fp, fp, vp, vp, vp, vp, vp, fp, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.sy_ops_maxpool3x3s2_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.sy_ops_maxpool3x3s2_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
@@ -91,6 +92,53 @@ def bn_shape_supported(c: int) -> bool:
     return c % 8 == 0 and 1 <= g <= 256 and (g & (g - 1)) == 0
 
 
+# ---- zero pool: ONE memset per training step instead of one per layer -------------------------------------------------------------
+# Every fused BN layer needs a zeroed float[2C] scratch in forward (statistics) and in backward (reductions), and every GEMM with fused
+# statistics a zeroed float[2C] output: ~100 torch.zeros / cudaMemsetAsync nodes of a few hundred bytes each per ResNet-50 step
+# (0.24 ms of launch-bound work in the captured graph, gpurun_out/c6_kernel_census.txt).  The trainer opens a pool at the start of the
+# step (one memset of the whole arena); zeros(n) then hands out consecutive slices.  Outside a pool everything behaves as before.
+_ZPOOL: dict = {"buf": None, "off": 0, "active": False}
+
+
+def zero_pool_begin(device, nfloats: int = 1 << 18) -> None:
+    if not (isinstance(device, torch.device) and device.type == "cuda"):
+        return
+    buf = _ZPOOL["buf"]
+    if buf is None or buf.device != device or buf.numel() < nfloats:
+        buf = _ZPOOL["buf"] = torch.empty(nfloats, dtype=torch.float32, device=device)
+    buf.zero_()
+    _ZPOOL.update(off=0, active=True)
+    lib = load(); _bind_bn(lib)
+    lib.sy_ops_set_ws_prezeroed(1)
+
+
+def zero_pool_end() -> None:
+    _ZPOOL["active"] = False
+    if _LIB is not None:
+        _LIB.sy_ops_set_ws_prezeroed(0)
+
+
+def zeros(n: int, device) -> torch.Tensor:
+    """float32 zeros: a slice of the step's zero pool when one is open (and has room), else a fresh torch.zeros."""
+    buf = _ZPOOL["buf"]
+    n_al = (n + 31) // 32 * 32                            # 128-byte aligned slices
+    if _ZPOOL["active"] and buf is not None and buf.device == device and _ZPOOL["off"] + n_al <= buf.numel():
+        o = _ZPOOL["off"]
+        _ZPOOL["off"] = o + n_al
+        return buf[o:o + n]
+    if _ZPOOL["active"]:
+        z = torch.zeros(n, dtype=torch.float32, device=device)      # pool exhausted: correct, just not free
+        return z
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def _scratch(n: int, device) -> torch.Tensor:
+    """float[n] scratch the BN kernels expect zeroed: pool slice inside a step (kernels skip their memset), plain empty otherwise."""
+    if _ZPOOL["active"]:
+        return zeros(n, device)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
 class _FusedBNAct(torch.autograd.Function):
     """y = act(BN_train(x) [+ residual]) with saved (x, y, mean, invstd) for the fused backward."""
 
@@ -109,7 +157,7 @@ class _FusedBNAct(torch.autograd.Function):
         # ReLU sign bits (1 bit / element) saved for backward instead of re-reading the activation
         mask = torch.empty(m * (c // 8), dtype=torch.uint8, device=x.device) if relu else None
         if stats is None:
-            ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            ws = _scratch(2 * c, x.device)
             rc = lib.sy_ops_bn_fwd(_ptr(x), _ptr(residual), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(running_mean),
                                    _ptr(running_var), _ptr(save_mean), _ptr(save_invstd), _ptr(ws), m, c, eps,
                                    momentum, 1 if relu else 0, _ptr(mask), _stream(x))
@@ -160,7 +208,7 @@ class _FusedBNAct(torch.autograd.Function):
         else:
             dgamma = torch.empty(c, dtype=torch.bfloat16, device=x.device)
             dbeta = torch.empty(c, dtype=torch.bfloat16, device=x.device)
-        ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+        ws = _scratch(2 * c, x.device)
         if dout2 is not None:
             rc = lib.sy_ops_bn_bwd_dual(_ptr(dout), _ptr(dout2), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx),
                                         _ptr(dres), _ptr(dgamma), _ptr(dbeta), _ptr(ws), m, c, 1 if ctx.relu else 0,

@@ -66,6 +66,11 @@ def load() -> C.CDLL:
     return _LIB
 
 
+def _pool_zeros(n: int, device) -> torch.Tensor:
+    from .fused import zeros            # slice of the training step's zero pool when one is open, else torch.zeros
+    return zeros(n, device)
+
+
 def launch_count() -> int:
     return int(load().sy_gemm_launch_count())
 
@@ -264,11 +269,12 @@ class _Conv1x1NHWC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, want_stats):
+        ctx.set_materialize_grads(False)          # the statistics output has no gradient: do not let autograd build a zeros tensor for it
         n, cin, h, wd = x.shape
         cout = w.shape[0]
         x2 = x.permute(0, 2, 3, 1).reshape(n * h * wd, cin)            # view: NHWC storage
         w2 = w.permute(0, 2, 3, 1).reshape(cout, cin)
-        stats = torch.zeros(2 * cout, dtype=torch.float32, device=x.device) if want_stats else None
+        stats = _pool_zeros(2 * cout, x.device) if want_stats else None
         y2 = gemm_tn(x2, w2, stats=stats)
         ctx.save_for_backward(x, w)
         ctx.w_ref = w
@@ -539,8 +545,9 @@ class _ConvNHWC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, stride, pad, want_stats):
+        ctx.set_materialize_grads(False)          # the statistics output has no gradient: do not let autograd build a zeros tensor for it
         cout = w.shape[0]
-        stats = torch.zeros(2 * cout, dtype=torch.float32, device=x.device) if want_stats else None
+        stats = _pool_zeros(2 * cout, x.device) if want_stats else None
         y = conv_fprop_nhwc(x, w, stride, pad, stats=stats)
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.pad = stride, pad
@@ -625,7 +632,8 @@ class _StemS2D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w2, want_stats):
-        stats = torch.zeros(128, dtype=torch.float32, device=x.device) if want_stats else None
+        ctx.set_materialize_grads(False)          # the statistics output has no gradient: do not let autograd build a zeros tensor for it
+        stats = _pool_zeros(128, x.device) if want_stats else None
         y = stem_s2d_fprop(x, w2, stats=stats)
         ctx.save_for_backward(x)
         if stats is not None:

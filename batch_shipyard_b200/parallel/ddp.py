@@ -129,9 +129,15 @@ class FusedDataParallelTrainer:
 
     # -- one optimisation step on the static buffers ---------------------------
     def _step_body(self) -> None:
-        logits = self.model(self.static_x)
-        loss = self.loss_fn(logits, self.static_y)
-        loss.backward()
+        if self.is_cuda:
+            _fused.zero_pool_begin(self.dev)            # ONE memset for every layer's zeroed scratch / statistics buffer of this step
+        try:
+            logits = self.model(self.static_x)
+            loss = self.loss_fn(logits, self.static_y)
+            loss.backward()
+        finally:
+            if self.is_cuda:
+                _fused.zero_pool_end()
         self.comm.fused_allreduce_sgd(self.flat.grads, self.flat.params, self.flat.master, self.flat.momentum,
                                       self.hyper, zero_grads=True)
         self.static_loss.copy_(loss.detach())

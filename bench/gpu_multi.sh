@@ -9,7 +9,7 @@ mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 NG=$(nvidia-smi -L | wc -l)
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
 Q=""; [ "$NG" -ge 8 ] && Q=1
-SHIPYARD_TEST_QUICK=$Q timeout 900 python -m pytest tests/test_gpu_coll.py -q -m gpu -x ${Q:+-k "not trainer_equals and not p2p"} > gpurun_out/m_pytest_coll_n$NG.log 2>&1; tail -3 gpurun_out/m_pytest_coll_n$NG.log | cut -c1-300
+SHIPYARD_TEST_QUICK=$Q timeout 900 python -m pytest tests/test_gpu_coll.py -q -m gpu -x ${Q:+-k "multi_gpu_collectives and auto or preload or litmus"} > gpurun_out/m_pytest_coll_n$NG.log 2>&1; tail -3 gpurun_out/m_pytest_coll_n$NG.log | cut -c1-300
 export SHIPYARD_STATE_DIR=$PWD/gpurun_out/m_state
 run_recipe() {   # $1 = recipe config dir, $2 = tag, $3 = pool id
   rm -rf $SHIPYARD_STATE_DIR gpurun_out/m_cfg; mkdir -p gpurun_out/m_cfg; cp $1/*.yaml gpurun_out/m_cfg/
@@ -41,7 +41,7 @@ tail -3 gpurun_out/m_bench_n$NG.err | cut -c1-300
 B=$((256 / NG)); SHIPYARD_BENCH_BATCH=$B timeout 400 $TR --master-port 29585 bench.py --gpus $NG --steps 15 --warmup 5 --no-baseline --no-coll 2>/dev/null | tail -1 > gpurun_out/m_bench_strong_n$NG.json; python -c "
 import json; d=json.load(open('gpurun_out/m_bench_strong_n$NG.json')); print('strong scaling (global batch 256): N=$NG', d['value'], 'img/s', d['ms_per_step'], 'ms')" 2>&1 | tail -1
 timeout 300 $TR --master-port 29584 recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --size 256 --seconds 5 2>&1 | tail -2 | cut -c1-900 | tee gpurun_out/m_hpcg_n$NG.log
-timeout 200 $TR --master-port 29586 recipes/TensorFlow-Distributed/mnist_replica.py --train_steps 5000 --impl both 2>&1 | tail -1 | cut -c1-700 | tee gpurun_out/m_tfdist_n$NG.log
+timeout 200 $TR --master-port 29586 recipes/TensorFlow-Distributed/mnist_replica.py --train_steps 5000 --impl both 2>&1 | grep steps_per_sec | tail -1 | cut -c1-700 | tee gpurun_out/m_tfdist_n$NG.log
 S=k10m$$
 for r in $(seq 0 $((NG-1))); do timeout 200 python tests/_k10_worker.py --rank $r --world $NG --session $S --device $r --bench > gpurun_out/m_k10_r$r.log 2>&1 & done; wait
 tail -1 gpurun_out/m_k10_r0.log | cut -c1-400 | tee gpurun_out/m_k10_n$NG.log

@@ -248,9 +248,53 @@ def run_tuned(batch, steps, warmup, rank, world, local, sampler_factory=None):
     return out
 
 
+def run_compiled(batch, steps, warmup, rank, world, local, sampler_factory=None):
+    """stock-compiled (opt-in, SHIPYARD_BASELINE_COMPILE=1: inductor needs 1-3 minutes per process): the stock-tuned recipe with
+    torch.compile on the model, so the BatchNorm / ReLU / residual elementwise chains are fused by the tracing compiler."""
+    import time
+    import torchvision
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    torch.backends.cudnn.benchmark = True
+    model = torchvision.models.resnet50(weights=None).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4, foreach=True)
+    cnet = torch.compile(net)
+    x = torch.randn(batch, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (batch,), device=dev)
+
+    def step(_i=0):
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(cnet(x).float(), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    t0 = time.time()
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize()
+    compile_s = time.time() - t0
+    sampler = sampler_factory() if (sampler_factory and rank == 0) else None
+    if sampler:
+        sampler.start()
+    ms = _timed(step, steps, world, dev)
+    clocks = sampler.stop() if sampler else {}
+    out = {"flavour": "stock-compiled", "what": "stock-tuned recipe + torch.compile(model) (inductor), DDP/NCCL, foreach SGD",
+           "ms_per_step": round(ms, 3), "value": round(batch * world / (ms / 1e3), 2), "unit": "images/sec",
+           "compile_and_warmup_s": round(compile_s, 1), "clocks": clocks}
+    del cnet, net, model, opt
+    gc.collect(); torch.cuda.empty_cache()
+    return out
+
+
 def run_both(batch, steps, warmup, rank, world, local, sampler_factory=None) -> dict:
+    import os
     out = {}
-    for name, fn in (("stock_eager", run_eager), ("stock_tuned", run_tuned)):
+    arms = [("stock_eager", run_eager), ("stock_tuned", run_tuned)]
+    if os.environ.get("SHIPYARD_BASELINE_COMPILE"):
+        arms.append(("stock_compiled", run_compiled))
+    for name, fn in arms:
         try:
             out[name] = fn(batch, steps, warmup, rank, world, local, sampler_factory)
         except Exception as e:  # noqa: BLE001 - a failing baseline arm must not take the headline measurement down

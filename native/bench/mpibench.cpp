@@ -87,9 +87,9 @@ static int run_compare(size_t beg, size_t end, int factor, int iters, int warm, 
   // symmetric buffers (zero-copy path of the shipyard kernels) and plain cudaMalloc buffers (what an unmodified program passes)
   char* sym_in = (char*)MPIX_Sym_alloc(maxb + 256); char* sym_out = (char*)MPIX_Sym_alloc(maxb + 256);
   char *pl_in = nullptr, *pl_out = nullptr, *flush = nullptr; const size_t flush_bytes = 256ul << 20;
-  void *q8 = nullptr, *q8s = nullptr;
   cudaMalloc(&pl_in, maxb + 256); cudaMalloc(&pl_out, maxb + 256); cudaMalloc(&flush, flush_bytes);
-  cudaMalloc(&q8, maxb / 2 + 256); cudaMalloc(&q8s, maxb / 64 + 256);
+  // block-scaled fp8 output lives in the symmetric heap too (the kernel multicasts the quantised result): carved out of sym_out
+  void* q8 = sym_out; void* q8s = sym_out + ((maxb / 2 + 4095) & ~(size_t)4095);
   if (!sym_in || !sym_out || !pl_in || !pl_out || !flush) { fprintf(stderr, "mpibench: buffer allocation failed (raise SHIPYARD_COLL_HEAP for --compare up to %zu bytes)\n", maxb); return 2; }
   cudaMemsetAsync(sym_in, 0, maxb, st); cudaMemsetAsync(pl_in, 0, maxb, st); cudaStreamSynchronize(st);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -113,6 +113,7 @@ static int run_compare(size_t beg, size_t end, int factor, int iters, int warm, 
     MPI_Allreduce(&med, &mx, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
     return mx;
   };
+  bool fp8_warned = false;
   for (auto& op : ops) {
     for (size_t total = beg; total <= end; total *= (size_t)factor) {
       const size_t n = std::max<size_t>((size_t)world, total / 4 / world * world);     // fp32 elements of the per-rank buffer
@@ -125,7 +126,7 @@ static int run_compare(size_t beg, size_t end, int factor, int iters, int warm, 
         if (ncomm) f_nccl = [&] { nc.AllReduce(pl_in, pl_out, n, ncclFloat32, ncclSum, ncomm, st); };
       } else if (op == "allreduce_fp8") {
         // block-scaled fp8 output (e4m3 + one e8m0 scale per 32 elements) from bf16 input; NCCL comparator: the bf16 all-reduce it replaces
-        f_sym = [&] { sy_allreduce_fp8_blockscaled(sc, sym_in, SY_BF16, q8, q8s, n * 2, 1.0f, st); };
+        f_sym = [&] { if (sy_allreduce_fp8_blockscaled(sc, sym_in, SY_BF16, q8, q8s, n * 2, 1.0f, st) != SY_OK && rank == 0 && !fp8_warned) { fp8_warned = true; fprintf(stderr, "mpibench: allreduce_fp8: %s\n", sy_last_error()); } };
         if (ncomm) f_nccl = [&] { nc.AllReduce(pl_in, pl_out, n * 2, ncclBfloat16, ncclSum, ncomm, st); };
       } else if (op == "allgather") {
         f_sym = [&] { sy_allgather(sc, sym_in, sym_out, per * 4, SY_U8, st); };

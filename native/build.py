@@ -27,17 +27,6 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "--e
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-pthread"]
 
 
-def _site_cutlass() -> list[str]:
-    """CUTLASS/CuTe headers vendored inside flashinfer's wheel (header-only use)."""
-    import sysconfig
-    sp = sysconfig.get_paths()["purelib"]
-    for rel in ("flashinfer/data/cutlass/include", "tilelang/3rdparty/cutlass/include"):
-        p = os.path.join(sp, rel)
-        if os.path.isdir(p):
-            return ["-I", p]
-    return []
-
-
 TARGETS = {
     # name: (kind, output, sources, extra flags, link flags)
     "coll": ("nvcc-shared", "libshipyard_coll.so",
@@ -113,7 +102,7 @@ def build_target(name: str, force: bool = False) -> str:
         if not force and not _newer(o, [s] + hdrs + [os.path.abspath(__file__)]):
             continue
         if kind.startswith("nvcc"):
-            cmd = [NVCC] + GENCODE + NVCC_FLAGS + _site_cutlass() + flags + ["-c", s, "-o", o]
+            cmd = [NVCC] + GENCODE + NVCC_FLAGS + flags + ["-c", s, "-o", o]
             if not s.endswith(".cu"):
                 cmd = [NVCC] + GENCODE + ["-O3", "-std=c++17", "-x", "cu", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"] \
                     + flags + ["-c", s, "-o", o]

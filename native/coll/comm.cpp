@@ -43,7 +43,7 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->timeout_ms = (long)env_sz("SHIPYARD_COLL_TIMEOUT_MS", 20000);
   c->max_blocks = (long)env_sz("SHIPYARD_COLL_MAX_BLOCKS", 128);
   c->threads = (long)env_sz("SHIPYARD_COLL_THREADS", 512);
-  c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 4096);
+  c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 16384);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
   c->mailbox_max_bytes = (long)env_sz("SHIPYARD_COLL_MAILBOX_MAX", 1 << 20);
   c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);

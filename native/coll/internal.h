@@ -57,7 +57,7 @@ struct sy_comm {
   uint32_t* status_host = nullptr;
   // tuning
   long max_blocks = 128, threads = 512;
-  long ll_max_bytes = 4096, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;
+  long ll_max_bytes = 16384, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;   // LL up to its 16 KB payload: 10 us vs 18 us (one-shot) at 16 KB, N = 4 (round-2 sweep)
   long mailbox_max_bytes = 1 << 20;     // per-writer payload up to which all-gather / all-to-all / broadcast use the mailbox kernel
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)

@@ -374,13 +374,18 @@ static inline bool bn_shape_ok(int C) {
   return G >= 1 && G <= 256 && (G & (G - 1)) == 0;
 }
 
-// ws: float[2*C] scratch (zeroed here).  Returns 0 or a cuda error / -1 for bad shape.
+// Callers that hand over scratch from a buffer they zeroed themselves (one memset per training step for ALL layers, see
+// ops/fused.py zero pool) switch the per-call memsets off: ~85 memset nodes per ResNet-50 step otherwise.
+static int g_ws_prezeroed = 0;
+extern "C" void sy_ops_set_ws_prezeroed(int on) { g_ws_prezeroed = on ? 1 : 0; }
+
+// ws: float[2*C] scratch (zeroed here unless sy_ops_set_ws_prezeroed(1)).  Returns 0 or a cuda error / -1 for bad shape.
 extern "C" int sy_ops_bn_fwd(const void* x, const void* res, void* out, const void* gamma, const void* beta,
                              float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                              float* ws, long M, int C, float eps, float momentum, int relu, void* mask, void* stream) {
   if (!bn_shape_ok(C)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
+  if (!g_ws_prezeroed) cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
   const int g = bn_grid(M, C, 1);
   k_bn_stats<<<bn_grid(M, C, 0), 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, C);
   COUNT_LAUNCH();
@@ -410,7 +415,7 @@ static int bn_bwd_launch(const void* dout, const void* dout2, const void* out, c
   if (!bn_shape_ok(C)) return -1;
   if (dout2 && relu && !mask) return -2;          // the two-gradient variant gates with the saved bit mask only
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
+  if (!g_ws_prezeroed) cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s);
   const int g = bn_grid(M, C, 2);
   auto D = [](const void* p) { return (const __nv_bfloat16*)p; };
   if (dout2) {

@@ -222,6 +222,12 @@ def main():
             out["vs_best_nccl_flavour"] = round(out["steps_per_sec"] / best, 3)
         print(json.dumps(out), flush=True)
     comm.close()
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 if __name__ == "__main__":
