@@ -127,6 +127,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "timeout_ms")) c->timeout_ms = v;
   else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
   else if (!strcmp(k, "bcast_sag_min_bytes")) c->bcast_sag_min_bytes = v;
+  else if (!strcmp(k, "ag_p2p_min_bytes")) c->ag_p2p_min_bytes = v;
   else if (!strcmp(k, "nvls_min_world")) c->nvls_min_world = v;
   else return SY_ERR_ARG;
   return SY_OK;
@@ -141,6 +142,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "timeout_ms")) return c->timeout_ms;
   if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
   if (!strcmp(k, "bcast_sag_min_bytes")) return c->bcast_sag_min_bytes;
+  if (!strcmp(k, "ag_p2p_min_bytes")) return c->ag_p2p_min_bytes;
   if (!strcmp(k, "nvls_min_world")) return c->nvls_min_world;
   return -1;
 }
@@ -159,6 +161,7 @@ extern "C" size_t sy_shard_count(const sy_comm* c, size_t count, int rank) {
 static char* stage_half(sy_comm* c, int half) { return c->dev.heap[c->rank] + c->stage_off + (size_t)half * (c->stage_bytes / 2); }
 static size_t stage_half_off(sy_comm* c, int half) { return c->stage_off + (size_t)half * (c->stage_bytes / 2); }
 
+static bool mailbox_ok(const sy_comm* c, const void* in, const void* out, size_t bytes);
 static bool nvls_dtype_ok(int a, int b) {
   if (a == b) return a == SY_F32 || a == SY_BF16 || a == SY_F16;
   return (a == SY_BF16 && b == SY_F32) || (a == SY_F32 && b == SY_BF16);
@@ -228,6 +231,11 @@ extern "C" int sy_reduce_scatter(sy_comm* c, const void* in, void* out, size_t c
   if (c->world == 1) return k_local_cast(c, in, out, count, dt_in, dt_out, scale, stream);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t si = sy_dtype_size(dt_in);
+  // small / medium shards: one-shot through the mailboxes (push my block p into rank p's slot, one flag per block, the receiver sums
+  // its W slots in fp32 in rank order): no barriers, any device pointers.  NCCL was 1.4-1.6x faster than the barrier-based kernel
+  // below 1 MB (profiles/round2_multi_gpu.md, N = 4)
+  if (op == SY_SUM && dt_in == dt_out && (dt_in == SY_F32 || dt_in == SY_BF16) && mailbox_ok(c, in, out, count * si))
+    return k_mailbox(c, in, out, count * si, 3, dt_in, stream, scale);
   size_t in_off;
   const size_t total = count * si * c->world;
   if (!sym_off(c, in, &in_off)) {
@@ -295,7 +303,12 @@ extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count,
       return SY_OK;
   } }
   OutStage t; int rc = out_target(c, out, bytes * c->world, &t); if (rc) return rc;
-  rc = k_allgather(c, in, t.off, count, dt, c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)(c->nvls_min_bytes / c->world), stream);
+  // multimem.st replicates in the switch (egress bytes/rank instead of bytes x (world - 1)), which wins while the message is latency-
+  // bound; from ~16 MB of output on the same sweep shows plain peer stores (the all-to-all data path: 680 GB/s bus bandwidth at
+  // 1 GB) ahead of the multicast path (528-616 GB/s) — profiles/round2_multi_gpu.md, all-gather vs all-to-all rows at N = 4 / 8
+  const bool ag_nvls = c->has_mc && c->nvls_copy && c->world >= c->nvls_min_world && bytes >= (size_t)(c->nvls_min_bytes / c->world) &&
+                       bytes * c->world < (size_t)c->ag_p2p_min_bytes;
+  rc = k_allgather(c, in, t.off, count, dt, ag_nvls, stream);
   if (rc) return rc;
   if (t.staged) CUDA_TRY(cudaMemcpyAsync(out, stage_half(c, 1), bytes * c->world, cudaMemcpyDeviceToDevice, s));
   return SY_OK;

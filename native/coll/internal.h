@@ -62,6 +62,7 @@ struct sy_comm {
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
   long nvls_copy = 1;       // all-gather / broadcast through multimem.st when multicast exists
+  long ag_p2p_min_bytes = 16 << 20;     // all-gathers whose OUTPUT is at least this big use direct peer stores instead of multimem.st (see sy_allgather)
   long bcast_sag_min_bytes = 8 << 20;   // broadcasts from this size on run as pipelined scatter + all-gather (world >= 4, multicast)
   // VMM handles (opaque to other TUs)
   void* impl = nullptr;
@@ -114,7 +115,7 @@ int k_allreduce(sy_comm* c, const void* in, void* out, size_t in_off, size_t out
                 void* stream);
 int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_in, int dt_out,
                      float scale, int op, bool nvls, void* stream);
-int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream);
+int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream, float scale = 1.0f);
 int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt, bool nvls,
                 void* stream);
 int k_broadcast(sy_comm* c, const void* in, size_t out_off, size_t bytes, int root, bool nvls,

@@ -849,8 +849,11 @@ k_scatter_k(const __grid_constant__ CommDev c, size_t in_off, void* out, size_t 
 //   mode 0 all-gather : my `bytes` -> slot[me] on every rank; out[r*bytes ..] <- slot[r]
 //   mode 1 all-to-all : in[p*bytes ..] -> slot[me] on rank p;  out[r*bytes ..] <- slot[r]
 //   mode 2 broadcast  : root's `bytes` -> slot[root] on every rank; out <- slot[root]
+//   mode 3 reduce-scatter (sum, fp32 accumulate): in[p*bytes ..] -> slot[me] on rank p; out <- scale * sum_r slot[r], summed in rank
+//          order (bit-identical on every run); `root` carries the element type (SY_F32 / SY_BF16), `scale` the fused 1/N
 __global__ void __launch_bounds__(512)
-k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char* __restrict__ out, size_t bytes, int mode, int root) {
+k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char* __restrict__ out, size_t bytes, int mode, int root,
+            float scale = 1.0f) {
   const uint32_t seq = c.seq[0] + 1, parity = seq & 1;
   const size_t units = bytes / 16;
   const size_t per_block = (units + gridDim.x - 1) / gridDim.x;
@@ -858,12 +861,21 @@ k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char
   const bool writer = mode != 2 || c.rank == root;
   if (writer) {
     for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
-      if (mode == 1) {
+      if (mode == 1 || mode == 3) {
+        // all loads first, then all stores: ld16/st16 are volatile asm and keep their program order, so a load -> store -> load chain
+        // would pay one cold HBM latency per peer (world x ~0.7 us per unit)
+        V16 v[SY_MAXR];
 #pragma unroll
         for (int j = 0; j < SY_MAXR; ++j)
           if (j < c.world) {
             int p = c.rank + j; if (p >= c.world) p -= c.world;
-            st16(os_slot(c, p, parity, c.rank) + u * 16, ld16(in + (size_t)p * bytes + u * 16));
+            v[j] = ld16(in + (size_t)p * bytes + u * 16);
+          }
+#pragma unroll
+        for (int j = 0; j < SY_MAXR; ++j)
+          if (j < c.world) {
+            int p = c.rank + j; if (p >= c.world) p -= c.world;
+            st16(os_slot(c, p, parity, c.rank) + u * 16, v[j]);
           }
       } else {
         const V16 v = ld16(in + u * 16);
@@ -894,6 +906,35 @@ k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char
   __syncthreads();
   if (mode == 2) {
     for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) st16(out + u * 16, ld16(os_slot(c, c.rank, parity, root) + u * 16));
+  } else if (mode == 3) {
+    for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+      V16 v[SY_MAXR];
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) v[r] = ld16(os_slot(c, c.rank, parity, r) + u * 16);
+      V16 o;
+      if (root == SY_F32) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) {
+          a[0] += __uint_as_float(v[r].x); a[1] += __uint_as_float(v[r].y); a[2] += __uint_as_float(v[r].z); a[3] += __uint_as_float(v[r].w);
+        }
+        o.x = __float_as_uint(a[0] * scale); o.y = __float_as_uint(a[1] * scale); o.z = __float_as_uint(a[2] * scale); o.w = __float_as_uint(a[3] * scale);
+      } else {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) {
+          float t[8]; const uint32_t w4[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+          Codec<SY_BF16, 8>::unpack(w4, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] *= scale;
+        uint32_t w4[4]; Codec<SY_BF16, 8>::pack(a, w4);
+        o.x = w4[0]; o.y = w4[1]; o.z = w4[2]; o.w = w4[3];
+      }
+      st16(out + u * 16, o);
+    }
   } else {
     for (size_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
       V16 v[SY_MAXR];
@@ -1339,9 +1380,9 @@ int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_
 }
 
 // in/out: any device pointers (out is this rank's own buffer); bytes per writer, multiple of 16, <= SY_OS_SLOT
-int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream) {
+int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream, float scale) {
   int g = grid_for(c, bytes / 16 + 1, 256);
-  k_mailbox_k<<<g, 256, 0, (cudaStream_t)stream>>>(devof(c), (const char*)in, (char*)out, bytes, mode, root);
+  k_mailbox_k<<<g, 256, 0, (cudaStream_t)stream>>>(devof(c), (const char*)in, (char*)out, bytes, mode, root, scale);
   LAUNCH_CHECK(c);
   return SY_OK;
 }

@@ -198,6 +198,16 @@ def main():
     comm.all_gather(si, so); sync()
     assert torch.equal(so.cpu(), torch.cat([gen(r, cnt, torch.float32, "cpu", salt=19) for r in range(W)])), "sym all_gather"
     comm.barrier(); sync()
+    if dev.type == "cuda":
+        # output >= ag_p2p_min_bytes (16 MB): the direct-peer-store path that large all-gathers switch to
+        big = (4 << 20) // W
+        so2 = comm.alloc(big * W, torch.float32)
+        si2 = gen(R, big, torch.float32, dev, salt=21)
+        comm.all_gather(si2, so2); sync()
+        for r in range(W):
+            assert torch.equal(so2[r * big:(r + 1) * big].cpu(), gen(r, big, torch.float32, "cpu", salt=21)), f"large sym all_gather from {r}"
+        comm.barrier(); sync()
+        checks += 1
     a_in = gen(R, cnt * W, torch.float32, dev, salt=21)
     comm.all_to_all(a_in, so); sync()
     assert torch.equal(so.cpu(), torch.cat([gen(r, cnt * W, torch.float32, "cpu", salt=21)[R * cnt:(R + 1) * cnt] for r in range(W)])), "sym all_to_all"
