@@ -14,6 +14,8 @@ print({k:v for k,v in cd.items() if k not in ('race_us','halo')})
 print('staging', d['e2e'].get('input_staging'))
 PY
 tail -2 gpurun_out/f_bench.err | cut -c1-300
+timeout 200 python recipes/HPCG-Infiniband-IntelMPI/run_hpcg.py --size 256 --seconds 5 2>&1 | tail -1 | cut -c1-900 | tee gpurun_out/f_hpcg_n1.log
+timeout 150 python recipes/TensorFlow-Distributed/mnist_replica.py --train_steps 5000 --impl both 2>&1 | grep steps_per_sec | tail -1 | cut -c1-700 | tee gpurun_out/f_tfdist_n1.log
 [ -n "$SANITIZE" ] && bash bench/sanitize_timeboxed.sh
 [ -n "$COMPILE_BASELINE" ] && SHIPYARD_BASELINE_COMPILE=1 timeout 900 python - <<'PY'
 import json, sys

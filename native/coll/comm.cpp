@@ -46,6 +46,8 @@ extern "C" int sy_comm_init(sy_comm** out, int rank, int world, const char* sess
   c->ll_max_bytes = (long)env_sz("SHIPYARD_COLL_LL_MAX", 16384);
   c->oneshot_max_bytes = (long)env_sz("SHIPYARD_COLL_ONESHOT_MAX", 256 << 10);
   c->mailbox_max_bytes = (long)env_sz("SHIPYARD_COLL_MAILBOX_MAX", 1 << 20);
+  c->lm_max_bytes = (long)env_sz("SHIPYARD_COLL_LM_MAX", SY_LM_MAX_PAYLOAD);
+  if (c->lm_max_bytes > (long)SY_LM_MAX_PAYLOAD) c->lm_max_bytes = (long)SY_LM_MAX_PAYLOAD;
   c->nvls_copy = (long)env_sz("SHIPYARD_COLL_NVLS_COPY", 1);
   c->nvls_min_world = (long)env_sz("SHIPYARD_COLL_NVLS_MIN_WORLD", 4);
   if (heap_bytes == 0) heap_bytes = env_sz("SHIPYARD_COLL_HEAP", transport == SY_TRANSPORT_STUB ? (256ul << 20) : (1ul << 30));
@@ -128,6 +130,7 @@ extern "C" int sy_set_tuning(sy_comm* c, const char* k, long v) {
   else if (!strcmp(k, "nvls_copy")) c->nvls_copy = v;
   else if (!strcmp(k, "bcast_sag_min_bytes")) c->bcast_sag_min_bytes = v;
   else if (!strcmp(k, "ag_p2p_min_bytes")) c->ag_p2p_min_bytes = v;
+  else if (!strcmp(k, "lm_max_bytes")) c->lm_max_bytes = v > (long)SY_LM_MAX_PAYLOAD ? (long)SY_LM_MAX_PAYLOAD : v;
   else if (!strcmp(k, "nvls_min_world")) c->nvls_min_world = v;
   else return SY_ERR_ARG;
   return SY_OK;
@@ -143,6 +146,7 @@ extern "C" long sy_get_tuning(sy_comm* c, const char* k) {
   if (!strcmp(k, "nvls_copy")) return c->nvls_copy;
   if (!strcmp(k, "bcast_sag_min_bytes")) return c->bcast_sag_min_bytes;
   if (!strcmp(k, "ag_p2p_min_bytes")) return c->ag_p2p_min_bytes;
+  if (!strcmp(k, "lm_max_bytes")) return c->lm_max_bytes;
   if (!strcmp(k, "nvls_min_world")) return c->nvls_min_world;
   return -1;
 }
@@ -162,6 +166,7 @@ static char* stage_half(sy_comm* c, int half) { return c->dev.heap[c->rank] + c-
 static size_t stage_half_off(sy_comm* c, int half) { return c->stage_off + (size_t)half * (c->stage_bytes / 2); }
 
 static bool mailbox_ok(const sy_comm* c, const void* in, const void* out, size_t bytes);
+static bool lm_ok(const sy_comm* c, const void* in, const void* out, size_t bytes);
 static bool nvls_dtype_ok(int a, int b) {
   if (a == b) return a == SY_F32 || a == SY_BF16 || a == SY_F16;
   return (a == SY_BF16 && b == SY_F32) || (a == SY_F32 && b == SY_BF16);
@@ -182,11 +187,15 @@ extern "C" int sy_allreduce(sy_comm* c, const void* in, void* out, size_t count,
   size_t in_off = 0, out_off = 0;
   const bool in_sym = sym_off(c, in, &in_off), out_sym = sym_off(c, out, &out_off);
   const size_t bytes = count * si;
+  const bool auto_algo = algo == SY_ALGO_AUTO;
   if (algo == SY_ALGO_AUTO) {
     if (bytes <= (size_t)c->ll_max_bytes) algo = SY_ALGO_LL;
     else if (bytes <= (size_t)c->oneshot_max_bytes) algo = SY_ALGO_ONESHOT;
     else algo = (c->has_mc && c->world >= c->nvls_min_world && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out)) ? SY_ALGO_TWOSHOT_NVLS : SY_ALGO_TWOSHOT_P2P;
   }
+  // 16 KB .. 256 KB sums: the multi-block LL kernel instead of the one-shot mailboxes (no fence + flag round trip)
+  if (algo == SY_ALGO_ONESHOT && auto_algo && op == SY_SUM && dt_in == dt_out && (dt_in == SY_F32 || dt_in == SY_BF16) && lm_ok(c, in, out, bytes))
+    return k_lm(c, in, out, bytes, 4, dt_in, stream, scale);
   if (algo == SY_ALGO_TWOSHOT_NVLS && !(c->has_mc && op == SY_SUM && nvls_dtype_ok(dt_in, dt_out))) {
     sy_set_error("allreduce: NVLS path unavailable for this call"); return SY_ERR_UNSUPPORTED;
   }
@@ -234,6 +243,8 @@ extern "C" int sy_reduce_scatter(sy_comm* c, const void* in, void* out, size_t c
   // small / medium shards: one-shot through the mailboxes (push my block p into rank p's slot, one flag per block, the receiver sums
   // its W slots in fp32 in rank order): no barriers, any device pointers.  NCCL was 1.4-1.6x faster than the barrier-based kernel
   // below 1 MB (profiles/round2_multi_gpu.md, N = 4)
+  if (op == SY_SUM && dt_in == dt_out && (dt_in == SY_F32 || dt_in == SY_BF16) && lm_ok(c, in, out, count * si))
+    return k_lm(c, in, out, count * si, 3, dt_in, stream, scale);
   if (op == SY_SUM && dt_in == dt_out && (dt_in == SY_F32 || dt_in == SY_BF16) && mailbox_ok(c, in, out, count * si))
     return k_mailbox(c, in, out, count * si, 3, dt_in, stream, scale);
   size_t in_off;
@@ -284,12 +295,19 @@ static bool mailbox_ok(const sy_comm* c, const void* in, const void* out, size_t
          ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0 && !getenv("SHIPYARD_COLL_NO_MAILBOX");
 }
 
+// latency-bound range: the multi-block LL kernel (payload and flag in one 8-byte atom; see k_lm_k).  `span` = bytes of in / out touched
+static bool lm_ok(const sy_comm* c, const void* in, const void* out, size_t bytes) {
+  return bytes <= (size_t)c->lm_max_bytes && bytes <= SY_LM_MAX_PAYLOAD && bytes % 4 == 0 && c->heap_bytes >= SY_USER_OFF &&
+         ((((uintptr_t)in) | ((uintptr_t)out)) & 3) == 0;
+}
+
 extern "C" int sy_allgather(sy_comm* c, const void* in, void* out, size_t count, int dt, sy_stream_t stream) {
   if (count == 0) return SY_OK;
   if (is_stub(c)) return stub_allgather(c, in, out, count, dt);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (lm_ok(c, in, out, bytes)) return k_lm(c, in, out, bytes, 0, 0, stream);
   if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 0, 0, stream);
   { size_t o_; if (!sym_off(c, out, &o_) && bytes * c->world > c->stage_bytes / 2) {
       // plain (non-symmetric) output larger than the staging half: gather it in column chunks through the staging buffer
@@ -346,6 +364,7 @@ extern "C" int sy_alltoall(sy_comm* c, const void* in, void* out, size_t count, 
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (lm_ok(c, in, out, bytes)) return k_lm(c, in, out, bytes, 1, 0, stream);
   if (mailbox_ok(c, in, out, bytes)) return k_mailbox(c, in, out, bytes, 1, 0, stream);
   { size_t o_; if (!sym_off(c, out, &o_) && bytes * c->world > c->stage_bytes / 2) {
       // column chunks: stage [world x n] of the input, exchange, scatter the [world x n] result back with a strided copy

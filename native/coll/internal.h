@@ -27,6 +27,11 @@
 #define SY_OS_OFF (SY_LL_OFF + SY_LL_TOT)
 #define SY_OS_SLOT (1ul << 20)                       // 1 MB payload per rank
 #define SY_OS_TOT (2ul * SY_MAXR * SY_OS_SLOT)       // 16 MB
+// [17M,  17M+LMTOT )  multi-block LL mailboxes 2 parity x SY_MAXR x SY_LM_SLOT bytes (only ever written in LL line format)
+#define SY_LM_OFF (17ul << 20)
+#define SY_LM_MAX_PAYLOAD (256ul << 10)              // bytes of payload per writer
+#define SY_LM_SLOT (2 * SY_LM_MAX_PAYLOAD)           // 16 B line = two 8-byte atoms {word, flag}
+#define SY_LM_TOT (2ul * SY_MAXR * SY_LM_SLOT)       // 8 MB
 #define SY_USER_OFF (32ul << 20)                     // 32 MB, 2 MB aligned
 
 struct CommDev {
@@ -58,6 +63,7 @@ struct sy_comm {
   // tuning
   long max_blocks = 128, threads = 512;
   long ll_max_bytes = 16384, oneshot_max_bytes = 256 << 10, nvls_min_bytes = 256 << 10;   // LL up to its 16 KB payload: 10 us vs 18 us (one-shot) at 16 KB, N = 4 (round-2 sweep)
+  long lm_max_bytes = 256 << 10;        // per-writer payload up to which gathers / exchanges / sum-reductions use the multi-block LL kernel (k_lm_k)
   long mailbox_max_bytes = 1 << 20;     // per-writer payload up to which all-gather / all-to-all / broadcast use the mailbox kernel
   long timeout_ms = 20000;
   long nvls_min_world = 4;  // below this world size the P2P paths win (measured at N=2)
@@ -116,6 +122,7 @@ int k_allreduce(sy_comm* c, const void* in, void* out, size_t in_off, size_t out
 int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_in, int dt_out,
                      float scale, int op, bool nvls, void* stream);
 int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream, float scale = 1.0f);
+int k_lm(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int dt, void* stream, float scale = 1.0f);
 int k_allgather(sy_comm* c, const void* in, size_t out_off, size_t count, int dt, bool nvls,
                 void* stream);
 int k_broadcast(sy_comm* c, const void* in, size_t out_off, size_t bytes, int root, bool nvls,

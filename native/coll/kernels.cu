@@ -947,6 +947,93 @@ k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char
   seq_finish(c, 0);
 }
 
+// ---------------------------------------------------------------------------
+// Multi-block LL ("LM") kernel for the latency-bound range (<= 256 KB per writer): k_ll's line format — 16-byte lines of two 8-byte
+// atoms {payload word, flag} — on a grid of blocks and for every all-hear-all collective.  Data and flag share one 8-byte store, so
+// there is no fence, no separate flag store and no barrier: the receiver polls the lines themselves.  One NVLink store latency end
+// to end where the mailbox kernel (k_mailbox_k) pays payload flight + fence + flag flight + a second pass over its own HBM.
+// Lines live in a region that is only ever written in this format (SY_LM_OFF), double-buffered by the parity of the LL sequence
+// (c.seq[1], shared with k_ll): a rank can enter operation k + 2 only after it has heard from every peer in operation k + 1, i.e.
+// after every peer has finished reading operation k.
+//   mode 0 all-gather      : in[l] -> slot[me] on every rank;        out[r * bytes + l] <- slot[r]
+//   mode 1 all-to-all      : in[p * bytes + l] -> slot[me] on rank p; out[r * bytes + l] <- slot[r]
+//   mode 3 reduce-scatter  : in[p * bytes + l] -> slot[me] on rank p; out[l] <- scale * sum_r slot[r]   (fp32 accumulate, rank order)
+//   mode 4 all-reduce      : in[l] -> slot[me] on every rank;        out[l] <- scale * sum_r slot[r]
+// `bytes` (per writer) is a multiple of 4; in / out are 4-byte aligned; in == out is allowed (a thread reads every input word of its
+// line index before it writes any output word of that index, and no other thread touches that index).
+// ---------------------------------------------------------------------------
+DEVI char* lm_slot(const CommDev& c, int on_rank, uint32_t parity, int writer) {
+  return c.heap[on_rank] + SY_LM_OFF + ((size_t)parity * SY_MAXR + writer) * SY_LM_SLOT;
+}
+__global__ void __launch_bounds__(256)
+k_lm_k(const __grid_constant__ CommDev c, const uint32_t* in, uint32_t* out, size_t bytes, int mode, int dt,
+       float scale) {
+  const uint32_t seq = c.seq[1] + 1, parity = seq & 1, flag = seq;
+  const size_t words = bytes / 4, lines = (words + 1) / 2, wpr = words;      // wpr: words per rank block of in / out
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const bool exchange = mode == 1 || mode == 3;
+  for (size_t l = tid; l < lines; l += nth) {
+    const bool two = 2 * l + 1 < words;
+    // ---- send: all loads first (volatile asm keeps program order), then one 16-byte store per peer
+    uint32_t w0[SY_MAXR], w1[SY_MAXR];
+    if (exchange) {
+#pragma unroll
+      for (int j = 0; j < SY_MAXR; ++j)
+        if (j < c.world) {
+          int p = c.rank + j; if (p >= c.world) p -= c.world;
+          w0[j] = in[(size_t)p * wpr + 2 * l]; w1[j] = two ? in[(size_t)p * wpr + 2 * l + 1] : 0u;
+        }
+    } else {
+      w0[0] = in[2 * l]; w1[0] = two ? in[2 * l + 1] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SY_MAXR; ++j)
+      if (j < c.world) {
+        int p = c.rank + j; if (p >= c.world) p -= c.world;
+        const V16 line = {exchange ? w0[j] : w0[0], flag, exchange ? w1[j] : w1[0], flag};
+        st16_volatile(lm_slot(c, p, parity, c.rank) + l * 16, line);
+      }
+    // ---- receive: poll my own slots (local HBM / L2), every writer's line in flight at once
+    V16 v[SY_MAXR];
+    uint32_t pending = (1u << c.world) - 1u;
+    unsigned it = 0; unsigned long long t0 = 0;
+    while (pending) {
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r)
+        if (r < c.world && (pending >> r & 1u)) v[r] = ld16_volatile(lm_slot(c, c.rank, parity, r) + l * 16);
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r)
+        if (r < c.world && (pending >> r & 1u) && v[r].y == flag && v[r].w == flag) pending &= ~(1u << r);
+      if (pending && ((++it) & 0x3ff) == 0) {
+        unsigned long long t = globaltimer_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > c.timeout_ns) { *reinterpret_cast<volatile uint32_t*>(c.status) = SY_ERR_TIMEOUT; __threadfence_system(); break; }
+      }
+    }
+    if (mode == 0 || mode == 1) {
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r)
+        if (r < c.world) { out[(size_t)r * wpr + 2 * l] = v[r].x; if (two) out[(size_t)r * wpr + 2 * l + 1] = v[r].z; }
+    } else if (dt == SY_F32) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) { a0 += __uint_as_float(v[r].x); a1 += __uint_as_float(v[r].z); }
+      out[2 * l] = __float_as_uint(a0 * scale); if (two) out[2 * l + 1] = __float_as_uint(a1 * scale);
+    } else {                                    // bf16 pairs: low half = even element
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < SY_MAXR; ++r) if (r < c.world) {
+        a[0] += __uint_as_float(v[r].x << 16); a[1] += __uint_as_float(v[r].x & 0xffff0000u);
+        a[2] += __uint_as_float(v[r].z << 16); a[3] += __uint_as_float(v[r].z & 0xffff0000u);
+      }
+      uint32_t o[2]; float sc[4] = {a[0] * scale, a[1] * scale, a[2] * scale, a[3] * scale};
+      Codec<SY_BF16, 4>::pack(sc, o);
+      out[2 * l] = o[0]; if (two) out[2 * l + 1] = o[1];
+    }
+  }
+  seq_finish(c, 1);
+}
+
 __global__ void k_barrier_k(const __grid_constant__ CommDev c) {
   uint32_t ep = epoch_load(c);
   block_barrier(c, ep);
@@ -1383,6 +1470,13 @@ int k_reduce_scatter(sy_comm* c, size_t in_off, void* out, size_t count, int dt_
 int k_mailbox(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int root, void* stream, float scale) {
   int g = grid_for(c, bytes / 16 + 1, 256);
   k_mailbox_k<<<g, 256, 0, (cudaStream_t)stream>>>(devof(c), (const char*)in, (char*)out, bytes, mode, root, scale);
+  LAUNCH_CHECK(c);
+  return SY_OK;
+}
+// in/out: any device pointers, 4-byte aligned; bytes per writer: multiple of 4, <= SY_LM_MAX_PAYLOAD
+int k_lm(sy_comm* c, const void* in, void* out, size_t bytes, int mode, int dt, void* stream, float scale) {
+  int g = grid_for(c, (bytes / 4 + 1) / 2 + 1, 256);
+  k_lm_k<<<g, 256, 0, (cudaStream_t)stream>>>(devof(c), (const uint32_t*)in, (uint32_t*)out, bytes, mode, dt, scale);
   LAUNCH_CHECK(c);
   return SY_OK;
 }

@@ -79,7 +79,8 @@ def main():
             out.append("twoshot_nvls")
         return out
 
-    sizes = [1, 3, 8, 257, 4096, 65536 + 5] if a.quick else [1, 2, 3, 8, 31, 257, 1000, 4096, 65536 + 5, (1 << 20) + 24, 3 << 20]
+    # 20001 / 30000: 16 KB < bytes <= 256 KB = the multi-block LL kernel (odd and even 4-byte word counts)
+    sizes = [1, 3, 8, 257, 4096, 20001, 30000, 65536 + 5] if a.quick else [1, 2, 3, 8, 31, 257, 1000, 4096, 20001, 30000, 65536 + 5, (1 << 20) + 24, 3 << 20]
     dtypes = [torch.float32, torch.bfloat16, torch.float64, torch.int32] if a.quick else \
         [torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int32, torch.int64]
     # ---- all-reduce: plain (non-symmetric) buffers, every algorithm -----------
@@ -168,6 +169,29 @@ def main():
                 sync()
                 assert torch.equal(sc_out.cpu(), gen(root, cnt * W, dtype, "cpu", salt=17)[R * cnt:(R + 1) * cnt]), "scatter"
             checks += 6
+    # ---- ragged small sizes on the multi-block LL kernel (bytes % 4 == 0, odd word counts, in place on the GPU) ----
+    inplace = dev.type == "cuda"
+    for dtype, cnt in ((torch.float32, 7), (torch.bfloat16, 30), (torch.float32, 4099)):
+        x = gen(R, cnt * W, dtype, dev, salt=23)
+        out = torch.empty(cnt, dtype=dtype, device=dev)
+        comm.reduce_scatter(x, out, scale=0.5)
+        sync()
+        close(out, ref_sum(W, cnt * W, dtype, salt=23)[R * cnt:(R + 1) * cnt] * 0.5, dtype, W, f"ragged reduce_scatter {dtype} {cnt}")
+        g_out = torch.zeros(cnt * W, dtype=dtype, device=dev)
+        g_in = gen(R, cnt, dtype, dev, salt=25)
+        if inplace:
+            g_out[R * cnt:(R + 1) * cnt] = g_in
+            g_in = g_out[R * cnt:(R + 1) * cnt]
+        comm.all_gather(g_in, g_out)
+        sync()
+        assert torch.equal(g_out.cpu(), torch.cat([gen(r, cnt, dtype, "cpu", salt=25) for r in range(W)])), f"ragged all_gather {dtype} {cnt}"
+        a_in = gen(R, cnt * W, dtype, dev, salt=27)
+        a_out = a_in if inplace else torch.empty_like(a_in)
+        comm.all_to_all(a_in, a_out)
+        sync()
+        ref = torch.cat([gen(r, cnt * W, dtype, "cpu", salt=27)[R * cnt:(R + 1) * cnt] for r in range(W)])
+        assert torch.equal(a_out.cpu(), ref), f"ragged all_to_all {dtype} {cnt}"
+        checks += 3
     # ---- plain (non-symmetric) buffers larger than the staging half: chunked through staging with strided copies ----
     if 1 < W <= 4 and dev.type == "cuda":
         big = 20 * (1 << 20) + 64                     # fp32 elements per rank: 80 MB -> W * 80 MB of output
