@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 GPU call 4 (1 GPU): new stem kernels (tests, bench, ncu), re-calibrated parity tests, bench with same-run baselines
+# 1-GPU call: new stem kernels (tests, bench, ncu), re-calibrated parity tests, bench with same-run baselines
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 timeout 300 python -m pytest tests/test_gpu_stem.py -q -m gpu -x > gpurun_out/c4_stem_tests.log 2>&1; tail -15 gpurun_out/c4_stem_tests.log | cut -c1-300
 timeout 120 python bench/stem_bench.py > gpurun_out/c4_stem_bench.json 2> gpurun_out/c4_stem_bench.err; cat gpurun_out/c4_stem_bench.json; tail -3 gpurun_out/c4_stem_bench.err

@@ -339,6 +339,7 @@ extern "C" int sy_broadcast(sy_comm* c, const void* in, void* out, size_t count,
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = count * sy_dtype_size(dt);
   if (c->world == 1) { if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s)); return SY_OK; }
+  if (lm_ok(c, c->rank == root ? in : out, out, bytes)) return k_lm(c, c->rank == root ? in : out, out, bytes, 2, root, stream);
   if (mailbox_ok(c, c->rank == root ? in : out, out, bytes)) return k_mailbox(c, c->rank == root ? in : out, out, bytes, 2, root, stream);
   { size_t o_; if (!sym_off(c, out, &o_) && bytes > c->stage_bytes / 2) {
       const size_t piece = (c->stage_bytes / 2) & ~(size_t)255;

@@ -31,7 +31,7 @@
 #define SY_LM_OFF (17ul << 20)
 #define SY_LM_MAX_PAYLOAD (256ul << 10)              // bytes of payload per writer
 #define SY_LM_SLOT (2 * SY_LM_MAX_PAYLOAD)           // 16 B line = two 8-byte atoms {word, flag}
-#define SY_LM_TOT (2ul * SY_MAXR * SY_LM_SLOT)       // 8 MB
+#define SY_LM_TOT (2ul * SY_MAXR * SY_LM_SLOT)       // 8 MB; followed by 2 x SY_MAXR 16-byte token lines (broadcast)
 #define SY_USER_OFF (32ul << 20)                     // 32 MB, 2 MB aligned
 
 struct CommDev {

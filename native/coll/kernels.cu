@@ -891,14 +891,15 @@ k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char
   __syncthreads();
   if ((int)threadIdx.x < c.world) {
     const int p = threadIdx.x;
-    // flags: writers tell every receiver "my block-b payload has landed".  In a broadcast the non-root ranks also flag the
-    // root (no payload): the root may not run two mailbox generations ahead of a receiver that is still copying out.
-    if (writer || p == root) {
+    // flags: writers tell every receiver "my block-b payload has landed".  In a broadcast EVERY rank flags every rank (the non-roots
+    // without payload) and waits for all of them: the parity double-buffering of the mailboxes is only safe if finishing operation
+    // k + 1 implies having heard from every peer in k + 1, i.e. that every peer has finished copying out of operation k.  (With
+    // root-only flags a non-root could finish a broadcast, enter the next all-gather and overwrite a slot that a slower non-root
+    // was still copying from.)
+    {
       uint32_t* remote = reinterpret_cast<uint32_t*>(c.heap[p] + SY_OSFLAGS_OFF) + ((parity * SY_MAX_BLOCKS + blockIdx.x) * SY_MAXR + c.rank);
       __threadfence_system();
       st_release_sys(remote, seq);
-    }
-    if (mode != 2 || p == root || c.rank == root) {
       const uint32_t* local = reinterpret_cast<const uint32_t*>(c.heap[c.rank] + SY_OSFLAGS_OFF) + ((parity * SY_MAX_BLOCKS + blockIdx.x) * SY_MAXR + p);
       spin_until_ge(local, seq, c);
     }
@@ -959,11 +960,30 @@ k_mailbox_k(const __grid_constant__ CommDev c, const char* __restrict__ in, char
 //   mode 1 all-to-all      : in[p * bytes + l] -> slot[me] on rank p; out[r * bytes + l] <- slot[r]
 //   mode 3 reduce-scatter  : in[p * bytes + l] -> slot[me] on rank p; out[l] <- scale * sum_r slot[r]   (fp32 accumulate, rank order)
 //   mode 4 all-reduce      : in[l] -> slot[me] on every rank;        out[l] <- scale * sum_r slot[r]
+//   mode 2 broadcast       : root's in[l] -> slot[root] on every rank; out[l] <- slot[root]  (`dt` carries the root).  To stay
+//          all-hear-all every rank also sends one token line to every rank when it enters the kernel and waits for all tokens
+//          before it leaves.
 // `bytes` (per writer) is a multiple of 4; in / out are 4-byte aligned; in == out is allowed (a thread reads every input word of its
 // line index before it writes any output word of that index, and no other thread touches that index).
 // ---------------------------------------------------------------------------
 DEVI char* lm_slot(const CommDev& c, int on_rank, uint32_t parity, int writer) {
   return c.heap[on_rank] + SY_LM_OFF + ((size_t)parity * SY_MAXR + writer) * SY_LM_SLOT;
+}
+DEVI char* lm_token(const CommDev& c, int on_rank, uint32_t parity, int writer) {
+  return c.heap[on_rank] + SY_LM_OFF + SY_LM_TOT + ((size_t)parity * SY_MAXR + writer) * 16;
+}
+DEVI V16 lm_poll(const CommDev& c, const char* src, uint32_t flag) {
+  V16 v; unsigned it = 0; unsigned long long t0 = 0;
+  for (;;) {
+    v = ld16_volatile(src);
+    if (v.y == flag && v.w == flag) break;
+    if (((++it) & 0x3ff) == 0) {
+      unsigned long long t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > c.timeout_ns) { *reinterpret_cast<volatile uint32_t*>(c.status) = SY_ERR_TIMEOUT; __threadfence_system(); break; }
+    }
+  }
+  return v;
 }
 __global__ void __launch_bounds__(256)
 k_lm_k(const __grid_constant__ CommDev c, const uint32_t* in, uint32_t* out, size_t bytes, int mode, int dt,
@@ -972,6 +992,30 @@ k_lm_k(const __grid_constant__ CommDev c, const uint32_t* in, uint32_t* out, siz
   const size_t words = bytes / 4, lines = (words + 1) / 2, wpr = words;      // wpr: words per rank block of in / out
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   const bool exchange = mode == 1 || mode == 3;
+  if (mode == 2) {
+    const int root = dt;
+    if (blockIdx.x == 0 && (int)threadIdx.x < c.world) {
+      const V16 token = {0u, flag, 0u, flag};
+      st16_volatile(lm_token(c, (int)threadIdx.x, parity, c.rank), token);
+    }
+    for (size_t l = tid; l < lines; l += nth) {
+      const bool two = 2 * l + 1 < words;
+      if (c.rank == root) {
+        const V16 line = {in[2 * l], flag, two ? in[2 * l + 1] : 0u, flag};
+#pragma unroll
+        for (int j = 0; j < SY_MAXR; ++j)
+          if (j < c.world) {
+            int p = c.rank + j; if (p >= c.world) p -= c.world;
+            st16_volatile(lm_slot(c, p, parity, root) + l * 16, line);
+          }
+      }
+      const V16 v = lm_poll(c, lm_slot(c, c.rank, parity, root) + l * 16, flag);
+      out[2 * l] = v.x; if (two) out[2 * l + 1] = v.z;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < c.world) lm_poll(c, lm_token(c, c.rank, parity, (int)threadIdx.x), flag);
+    seq_finish(c, 1);
+    return;
+  }
   for (size_t l = tid; l < lines; l += nth) {
     const bool two = 2 * l + 1 < words;
     // ---- send: all loads first (volatile asm keeps program order), then one 16-byte store per peer

@@ -191,7 +191,12 @@ def main():
         sync()
         ref = torch.cat([gen(r, cnt * W, dtype, "cpu", salt=27)[R * cnt:(R + 1) * cnt] for r in range(W)])
         assert torch.equal(a_out.cpu(), ref), f"ragged all_to_all {dtype} {cnt}"
-        checks += 3
+        for root in {0, W - 1}:
+            b = gen(R, cnt, dtype, dev, salt=29)
+            comm.broadcast(b, root=root)
+            sync()
+            assert torch.equal(b.cpu(), gen(root, cnt, dtype, "cpu", salt=29)), f"ragged broadcast {dtype} {cnt} root={root}"
+        checks += 4
     # ---- plain (non-symmetric) buffers larger than the staging half: chunked through staging with strided copies ----
     if 1 < W <= 4 and dev.type == "cuda":
         big = 20 * (1 << 20) + 64                     # fp32 elements per rank: 80 MB -> W * 80 MB of output

@@ -1,5 +1,4 @@
 """libshipyard_stage on a GPU: file -> pinned arena -> HBM and pinned -> HBM tickets, event chaining, against plain byte comparison."""
-import os
 
 import pytest
 import torch
