@@ -93,7 +93,7 @@ def timing(mode: int) -> None:
             cands["dgrad_th2"] = lambda: gemm.conv3x3_halo(dy, wt, dgrad=True, pair=True, base_mode=mode)
         cands["wgrad_cudnn"] = lambda: torch.ops.aten.convolution_backward(dy, x, wt, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
         cands["wgrad_tc"] = lambda: gemm.conv_wgrad_nhwc(x, dy, wt.shape, 1, 1)
-        if os.environ.get("SHIPYARD_TEST_UNVERIFIED"):          # round-2 candidates (not yet validated on hardware)
+        if not os.environ.get("SHIPYARD_HALO_CHECK_BASIC"):      # every variant (all validated on hardware in round 2)
             cands["wgrad_th"] = lambda: gemm.conv3x3_wgrad_halo(x, dy)
             if cout == 64:
                 cands["fprop_th_alt"] = lambda: gemm.conv3x3_halo(x, wt, stats=st, base_mode=mode, epi_alt=True)

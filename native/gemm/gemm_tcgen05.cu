@@ -235,9 +235,10 @@ template <int BN> struct Cfg {
 // epilogue chunk costs 1.7-2 us although TMEM -> registers -> smem is ~0.3 us of work: the group's single staging buffer may
 // only be rewritten once the previous TMA store has READ it (`cp.async.bulk.wait_group.read 0`), and that store queues in the
 // SM's TMA unit behind the producer's loads for the next 4-6 stages.  Plain stores have no such dependency.
-// [written after the last GPU run of round 1: compiled and reviewed, selected only with SHIPYARD_GEMM_DIRECT_STORE=1]
+// [round 2, gpurun_out/r2_bench_direct.json: as a global switch the step gets slower (21.10 vs 20.81 ms), so it is selected only with
+// SHIPYARD_GEMM_DIRECT_STORE=1 and by the 1x1 / stride-2 dgrad, whose scattering epilogue needs plain stores]
 // kEpiAlt (BN = 64, with kDirect): a 64-column tile has one epilogue chunk, so warpgroup g drains accumulator stage g (alternate
-// tiles) instead of group 1 idling — same schedule as conv3x3_halo_kernel's kEpiAlt.  [round 1: compiled, not yet run; selected with
+// tiles) instead of group 1 idling — same schedule as conv3x3_halo_kernel's kEpiAlt.  [numerics verified on hardware in round 2; selected with
 // SHIPYARD_GEMM_DIRECT_STORE=1 SHIPYARD_GEMM_EPI_ALT=1]
 template <int BN, bool kStats, bool kBias, bool kBMN = false, bool kConv = false, bool kDirect = false, bool kEpiAlt = false>
 __global__ void __launch_bounds__(kThreadsTN, 1)
@@ -1344,7 +1345,7 @@ bool load_encode() {
 }
 
 // SHIPYARD_GEMM_DIRECT_STORE=1 selects the kDirect epilogue (st.global instead of TMA stores) in the TN / CTA-pair GEMM and
-// im2col convolution launches; off by default until it has been measured (round 2).
+// im2col convolution launches; off by default (measured in round 2: no gain on the whole step).
 bool direct_store() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SHIPYARD_GEMM_DIRECT_STORE"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }

@@ -523,7 +523,8 @@ k_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ 
 // four pooling windows (oy in {a, a+1}, ox in {b, b+1}), so each window's gradient vector and arg-max codes are loaded once per
 // thread instead of once per pixel (96 B of loads per 64 B stored instead of 216 B) and every thread has four independent 16-byte
 // stores in flight.  ncu (profiles/step_breakdown.md) has the per-pixel kernel at 494 us for the 411 MB stem gradient, 5x the HBM time.
-// [written after the last GPU run of round 1: selected with SHIPYARD_MAXPOOL_BWD2=1, even H and W only]
+// Default since round 2 for even H and W (bit-compared against the per-pixel kernel on hardware, tests/test_zz_gpu_bn_dual.py; step 20.81 ->
+// 20.57 ms in the same call, gpurun_out/r2_bench_pool2.json); SHIPYARD_MAXPOOL_BWD2=0 selects the per-pixel kernel.
 __global__ void __launch_bounds__(256)
 k_maxpool_bwd2(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
                int N, int H, int W, int C, int OH, int OW) {
@@ -591,7 +592,7 @@ extern "C" int sy_ops_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx
   if (C % 8) return -1;
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   static int bwd2 = -1;
-  if (bwd2 < 0) { const char* e = getenv("SHIPYARD_MAXPOOL_BWD2"); bwd2 = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  if (bwd2 < 0) { const char* e = getenv("SHIPYARD_MAXPOOL_BWD2"); bwd2 = (e && e[0] == '0') ? 0 : 1; }
   if (bwd2 && H % 2 == 0 && W % 2 == 0) {
     const long total2 = (long)N * (H / 2) * (W / 2) * (C / 8);
     const int blocks2 = (int)((total2 + 255) / 256 < 148 * 16 ? (total2 + 255) / 256 : 148 * 16);

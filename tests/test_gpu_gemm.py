@@ -278,7 +278,6 @@ def test_direct_store_epilogue_variants_in_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for extra in ({}, {"SHIPYARD_GEMM_EPI_ALT": "1"}):              # second pass: alternate-tile epilogue on the 64-column GEMM tiles
         env = dict(os.environ, SHIPYARD_GEMM_DIRECT_STORE="1", **extra)
-        env.pop("SHIPYARD_TEST_UNVERIFIED", None)
         p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu", "-k",
                             "matches_fp32 or bias_stats or two_cta or conv_implicit or nn_mn_major or conv1x1_and_linear"],
                            env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)

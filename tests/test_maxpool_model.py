@@ -1,5 +1,5 @@
 """CPU model of the 2x2-block max-pool backward (k_maxpool_bwd2 in native/ops/fused_ops.cu): same window / tap arithmetic, checked
-against autograd.  The CUDA kernel itself is selected with SHIPYARD_MAXPOOL_BWD2=1 and has not run on hardware yet."""
+against autograd.  The CUDA kernel is the default for even H and W (SHIPYARD_MAXPOOL_BWD2=0 selects the per-pixel kernel); tests/test_zz_gpu_bn_dual.py compares the two on hardware."""
 import pytest
 import torch
 import torch.nn.functional as F

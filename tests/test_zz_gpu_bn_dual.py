@@ -79,7 +79,8 @@ def test_resnet_residual_gradient_fusion_matches_unfused():
 
 
 def test_maxpool_bwd2_variant_in_subprocess():
-    """SHIPYARD_MAXPOOL_BWD2=1 (read once per process by the library) must reproduce the per-pixel kernel's gradient exactly."""
+    """Both max-pool backward kernels (2x2-block = default, per-pixel = SHIPYARD_MAXPOOL_BWD2=0; read once per process by the library) must
+    reproduce autograd's gradient."""
     import os
     import subprocess
     import sys
@@ -96,6 +97,7 @@ def test_maxpool_bwd2_variant_in_subprocess():
         "    assert torch.equal(y.float(), yr)\n"
         "    torch.testing.assert_close(x.grad.float(), xr.grad, atol=2e-2, rtol=2e-2)\n"
         "print('bwd2 ok')\n") % root
-    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SHIPYARD_MAXPOOL_BWD2="1"), stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True, timeout=300)
-    assert p.returncode == 0 and "bwd2 ok" in p.stdout, p.stdout[-3000:]
+    for flag in ("1", "0"):
+        p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SHIPYARD_MAXPOOL_BWD2=flag), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0 and "bwd2 ok" in p.stdout, (flag, p.stdout[-3000:])
