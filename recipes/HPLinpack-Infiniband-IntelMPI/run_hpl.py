@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""HPLinpack recipe body (retarget): HPL-MxP — bf16 tensor-core LU + fp64 iterative refinement, one rank per GPU.
+
+The reference recipe runs Intel's MKL mp_linpack binary ``runme_intel64_prv -p $P -q $Q -b $B $PSIZE`` over InfiniBand
+(/root/reference/recipes/HPLinpack-Infiniband-IntelMPI/config/docker/jobs.yaml:22-28; problem size from ``setup_hplinpack.sh -n 50000``).
+Same knobs here: ``-n`` problem size, ``-b`` block size, ``-p`` / ``-q`` process grid (1 x world: 1-D block-cyclic columns).
+The task runner (or torchrun) starts the ranks; rank 0 prints one JSON line in HPL's terms (N, NB, P, Q, time, GFLOP/s, scaled residual).
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.environ.get("SHIPYARD_HOME") or os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+import torch  # noqa: E402
+
+from batch_shipyard_b200.models import hpl  # noqa: E402
+from batch_shipyard_b200.ops.coll import Communicator  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-n", "--psize", dest="n", type=int, default=32768, help="problem size N (rounded down to a multiple of the block size)")
+    ap.add_argument("-b", "--nb", dest="nb", type=int, default=2048, help="block size NB")
+    ap.add_argument("-p", type=int, default=1)
+    ap.add_argument("-q", type=int, default=0, help="process columns (default: world size)")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--runs", type=int, default=1, help="repeat the solve (first run pays cuBLAS / cuSOLVER handle creation)")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if a.p != 1 or a.q not in (0, world):
+        if rank == 0:
+            print(json.dumps({"error": f"process grid {a.p} x {a.q}: this body distributes 1 x {world} (block-cyclic columns)"}), flush=True)
+        sys.exit(2)
+    gpu = os.environ.get("SHIPYARD_GPU", os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available() and gpu not in ("", "-1")
+    dev_index = int(gpu) % max(1, torch.cuda.device_count()) if use_cuda else None
+    if use_cuda:
+        torch.cuda.set_device(dev_index)
+    n = a.n // a.nb * a.nb
+    session = (os.environ.get("SHIPYARD_COLL_SESSION") or os.environ.get("TORCHELASTIC_RUN_ID") or f"hpl-{os.getppid()}") + "-hpl"
+    comm = Communicator(rank, world, session, dev_index, heap_bytes=hpl.heap_bytes_for(n, a.nb))
+    best = None
+    try:
+        for _ in range(max(1, a.runs)):
+            out = hpl.run(comm, n, a.nb, seed=a.seed)
+            if best is None or out["gflops"] > best["gflops"]:
+                best = out
+    except hpl.HPLError as e:
+        if rank == 0:
+            print(json.dumps({"passed": False, "error": str(e), "n": n, "nb": a.nb, "world": world}), flush=True)
+        comm.close()
+        sys.exit(1)
+    if rank == 0:
+        best = {k: (round(v, 6) if isinstance(v, float) else v) for k, v in best.items() if k != "residual_history"}
+        best.update({"N": n, "NB": a.nb, "P": 1, "Q": world, "transport": comm.transport})
+        print(json.dumps(best), flush=True)
+    comm.close()
+
+
+if __name__ == "__main__":
+    main()
