@@ -235,8 +235,10 @@ class HPLMxP:
 
 
 def heap_bytes_for(n: int, nb: int) -> int:
-    """Symmetric heap needed by :class:`HPLMxP`: control region + panel (bf16) + vector (fp32) + slack."""
-    return (64 << 20) + n * nb * 2 + n * 4 + (32 << 20)
+    """Symmetric heap needed by :class:`HPLMxP`: the 32 MB control region, the staging carve-out (min(128 MB, half of the rest), see
+    native/coll/comm.cpp) and the user part: panel (bf16) + right-hand side (fp32) + slack."""
+    need = n * nb * 2 + n * 4 + (16 << 20)
+    return (32 << 20) + max(2 * need, need + (128 << 20))
 
 
 def run(comm, n: int, nb: int = 2048, seed: int = 42, max_refine: int = 50) -> dict:

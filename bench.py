@@ -234,7 +234,7 @@ def run_shipyard(args, rank, world, local):
         out["vs_baseline"] = round(out["value"] / base, 4)
     if baselines is not None:
         out["baseline_same_run"] = baselines
-        for key, name in (("vs_stock_eager", "stock_eager"), ("vs_stock_tuned", "stock_tuned")):
+        for key, name in (("vs_stock_eager", "stock_eager"), ("vs_stock_tuned", "stock_tuned"), ("vs_stock_compiled", "stock_compiled")):
             b = baselines.get(name) or {}
             if b.get("value"):
                 out[key] = {"device_timed": round(out["value"] / b["value"], 4),

@@ -1333,6 +1333,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+// cuTensorMapEncode* is a driver entry point and needs a context current on the CALLING thread.  A thread that has made no runtime call
+// yet has none — e.g. PyTorch's autograd thread when the first thing a backward does is one of our GEMMs with its output served from the
+// caching allocator (seen as error 201 in tests/test_gpu_gemm.py when that file runs alone).  On that error: make the device that owns the
+// operand current (the runtime then binds its primary context to this thread) and encode again.
+bool bind_context_of(const void* ptr) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess || a.type != cudaMemoryTypeDevice) { cudaGetLastError(); return false; }
+  return cudaSetDevice(a.device) == cudaSuccess && cudaFree(nullptr) == cudaSuccess;
+}
+#define ENC_RETRY(call, ptr) ({ CUresult _r = (call); if (_r == CUDA_ERROR_INVALID_CONTEXT && bind_context_of(ptr)) _r = (call); _r; })
 std::atomic<unsigned long long> g_launches{0};
 thread_local char g_err[256];
 
@@ -1364,9 +1374,9 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = ENC_RETRY(g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE), ptr);
   if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
   return true;
 }
@@ -1389,9 +1399,9 @@ bool make_im2col_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C
   int lower[2] = {-pad, -pad};
   int upper[2] = {pad - (S - 1), pad - (R - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, pixels, estr,
+  CUresult r = ENC_RETRY(g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, pixels, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE), ptr);
   if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeIm2col failed (%d)", (int)r); return false; }
   return true;
 }
@@ -1401,9 +1411,9 @@ bool make_w3d_map(CUtensorMap* m, const void* ptr, int Cout, int taps, int Cin) 
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)taps * Cin * 2};
   cuuint32_t box[3] = {64, 1, 64};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = ENC_RETRY(g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE), ptr);
   if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(3D) failed (%d)", (int)r); return false; }
   return true;
 }
