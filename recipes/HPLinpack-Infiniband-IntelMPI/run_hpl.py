@@ -44,6 +44,7 @@ def main():
     best = None
     try:
         for _ in range(max(1, a.runs)):
+            comm.reset_heap()                      # the panel / right-hand-side buffers of the previous run
             out = hpl.run(comm, n, a.nb, seed=a.seed)
             if best is None or out["gflops"] > best["gflops"]:
                 best = out
