@@ -293,7 +293,9 @@ def run_both(batch, steps, warmup, rank, world, local, sampler_factory=None) -> 
     import os
     out = {}
     arms = [("stock_eager", run_eager), ("stock_tuned", run_tuned)]
-    if os.environ.get("SHIPYARD_BASELINE_COMPILE", "1") not in ("0", "", "off", "false"):
+    # torch.compile arm: on by default on one GPU; at N > 1 every rank would run inductor at the same time (minutes of host time on a
+    # shared box), so there it is opt-in (SHIPYARD_BASELINE_COMPILE=1) and bench/baseline_measured.json carries the scaled 1-GPU number
+    if os.environ.get("SHIPYARD_BASELINE_COMPILE", "1" if world == 1 else "0") not in ("0", "", "off", "false"):
         arms.append(("stock_compiled", run_compiled))
     for name, fn in arms:
         try:
