@@ -28,3 +28,22 @@ for f in re.split(r"\n\s*Function : ", txt)[1:]:
     short = re.sub(r"Ev14CUtensorMap.*", "", re.sub(r"^_Z\d+", "", name))
     print(f"{short:60s} " + " ".join(f"{k}={v}" for k, v in cnt.items() if v))
 PY
+
+# round-2 kernels: stem (32-byte-swizzle tcgen05 operands), scatter-epilogue dgrad, multi-block LL / broadcast scatter+all-gather collectives
+python3 - >> $out <<'PY'
+import re, subprocess
+def funcs(lib):
+    txt = subprocess.run(["cuobjdump", "-sass", f"batch_shipyard_b200/_native/{lib}"], stdout=subprocess.PIPE, text=True).stdout
+    for f in re.split(r"\n\s*Function : ", txt)[1:]:
+        yield f.split("\n", 1)[0].strip(), f
+print("\n-- round-2 kernels: mnemonics per function")
+for name, f in funcs("libshipyard_gemm.so"):
+    if "stem_s2d" in name:
+        cnt = {m: len(re.findall(r"\b" + re.escape(m), f)) for m in ("UTCHMMA", "UTMALDG.4D", "UTMASTG.4D", "UTCBAR", "LDTM", "REDG", "SYNCS.PHASECHK", "UTCATOMSWS")}
+        print(f"{re.sub(r'^_Z[0-9]+', '', name)[:48]:50s} " + " ".join(f"{k}={v}" for k, v in cnt.items() if v))
+for name, f in funcs("libshipyard_coll.so"):
+    if any(k in name for k in ("k_lm_k", "k_broadcast_sag_k", "k_mailbox_k", "k_twoshot_nvls", "k_fused_sgd_k")):
+        cnt = {m: len(re.findall(r"\b" + re.escape(m), f)) for m in ("LDGMC", "STG.E.128.STRONG.SYS", "STG.E.STRONG.SYS", "LDG.E.128.STRONG.SYS", "LDG.E.STRONG.SYS", "REDG", "ST.E.128", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "ATOMG")}
+        mc = len(re.findall(r"\bST[G]?\.E[A-Z0-9.]*MC|MULTIMEM|\.MC\b", f))
+        print(f"{re.sub(r'^_Z[0-9]+', '', name)[:48]:50s} " + " ".join(f"{k}={v}" for k, v in cnt.items() if v) + (f" multicast-stores={mc}" if mc else ""))
+PY
