@@ -167,7 +167,92 @@ static int run_compare(size_t beg, size_t end, int factor, int iters, int warm, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// --osu <benchmark> [OSU flags]: the OSU micro-benchmark front end for the collective latency tests the reference recipe launches
+// (`collective/osu_allreduce -f`, /root/reference/recipes/OSUMicroBenchmarks-Infiniband-MVAPICH/config/jobs.yaml:5-16): same flags
+// (-f full statistics, -m [min:]max message sizes in bytes, -i iterations, -x warm-up iterations, -d cuda = device buffers), same
+// columns (size in bytes, average / minimum / maximum latency over the ranks in microseconds, iterations), host-timed with MPI_Wtime
+// around each call like the original.
+// ---------------------------------------------------------------------------------------------------------------------------------
+static int run_osu(int argc, char** argv, const char* bench) {
+  std::string name = bench;
+  const size_t slash = name.rfind('/');
+  if (slash != std::string::npos) name = name.substr(slash + 1);
+  struct { const char* osu; const char* title; } known[] = {
+    {"osu_allreduce", "Allreduce"}, {"osu_reduce", "Reduce"}, {"osu_bcast", "Broadcast"}, {"osu_allgather", "Allgather"},
+    {"osu_alltoall", "All-to-All Personalized Exchange"}, {"osu_gather", "Gather"}, {"osu_scatter", "Scatter"}, {"osu_barrier", "Barrier"}};
+  const char* title = nullptr;
+  for (auto& k : known) if (name == k.osu) title = k.title;
+  bool full = false, device = false; size_t mn = 4, mx = 1 << 20; int iters = 1000, warm = 200; bool iters_set = false;
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "-f")) full = true;
+    else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = !strcmp(argv[++i], "cuda") || !strcmp(argv[i], "managed");
+    else if (!strcmp(argv[i], "-i") && i + 1 < argc) { iters = atoi(argv[++i]); iters_set = true; }
+    else if (!strcmp(argv[i], "-x") && i + 1 < argc) warm = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-m") && i + 1 < argc) {
+      std::string m = argv[++i]; const size_t c = m.find(':');
+      if (c == std::string::npos) mx = parse_size(m.c_str()); else { if (c > 0) mn = parse_size(m.substr(0, c).c_str()); mx = parse_size(m.substr(c + 1).c_str()); }
+    }
+  }
+  MPI_Init(&argc, &argv);
+  int rank, world;
+  MPI_Comm_rank(MPI_COMM_WORLD, &rank); MPI_Comm_size(MPI_COMM_WORLD, &world);
+  if (!title) { if (rank == 0) fprintf(stderr, "mpibench --osu: unknown benchmark %s (collective latency tests only)\n", name.c_str()); MPI_Finalize(); return 2; }
+  if (device) {
+    const char* g = getenv("SHIPYARD_GPU"); int ndev = 0; cudaGetDeviceCount(&ndev);
+    if (ndev == 0) { if (rank == 0) fprintf(stderr, "mpibench --osu: -d cuda requested but no GPU visible\n"); MPI_Finalize(); return 3; }
+    cudaSetDevice(g ? atoi(g) % ndev : rank % ndev);
+  }
+  if (mn < 4) mn = 4;
+  const size_t maxb = mx * (size_t)world;
+  void *sbuf = nullptr, *rbuf = nullptr;
+  if (device) { cudaMalloc(&sbuf, maxb + 64); cudaMalloc(&rbuf, maxb + 64); cudaMemset(sbuf, 0, maxb + 64); cudaMemset(rbuf, 0, maxb + 64); }
+  else { sbuf = calloc(1, maxb + 64); rbuf = calloc(1, maxb + 64); }
+  char tr[16]; MPIX_Query_shipyard_transport(tr, sizeof tr);
+  if (rank == 0) {
+    printf("# OSU MPI%s %s Latency Test (shipyard-mpibench over libshipyard_mpi, %d ranks, transport %s)\n", device ? "-CUDA" : "", title, world, device ? tr : "host");
+    if (full) printf("# %-8s %18s %18s %18s %12s\n", "Size", "Avg Latency(us)", "Min Latency(us)", "Max Latency(us)", "Iterations");
+    else printf("# %-8s %18s\n", "Size", "Avg Latency(us)");
+  }
+  const bool barrier = name == "osu_barrier";
+  for (size_t bytes = mn; bytes <= mx; bytes *= 2) {
+    const int count = (int)(bytes / 4);
+    int it_n = iters, wm_n = warm;
+    if (!iters_set && bytes > 8192) { it_n = 100; wm_n = warm < 10 ? warm : 10; }           // OSU's large-message defaults
+    auto once = [&]() {
+      if (barrier) MPI_Barrier(MPI_COMM_WORLD);
+      else if (name == "osu_allreduce") MPI_Allreduce(sbuf, rbuf, count, MPI_FLOAT, MPI_SUM, MPI_COMM_WORLD);
+      else if (name == "osu_reduce") MPI_Reduce(sbuf, rbuf, count, MPI_FLOAT, MPI_SUM, 0, MPI_COMM_WORLD);
+      else if (name == "osu_bcast") MPI_Bcast(sbuf, count, MPI_FLOAT, 0, MPI_COMM_WORLD);
+      else if (name == "osu_allgather") MPI_Allgather(sbuf, count, MPI_FLOAT, rbuf, count, MPI_FLOAT, MPI_COMM_WORLD);
+      else if (name == "osu_alltoall") MPI_Alltoall(sbuf, count, MPI_FLOAT, rbuf, count, MPI_FLOAT, MPI_COMM_WORLD);
+      else if (name == "osu_gather") MPI_Gather(sbuf, count, MPI_FLOAT, rbuf, count, MPI_FLOAT, 0, MPI_COMM_WORLD);
+      else if (name == "osu_scatter") MPI_Scatter(sbuf, count, MPI_FLOAT, rbuf, count, MPI_FLOAT, 0, MPI_COMM_WORLD);
+    };
+    for (int w = 0; w < wm_n; ++w) once();
+    MPI_Barrier(MPI_COMM_WORLD);
+    double total = 0;
+    for (int it = 0; it < it_n; ++it) { const double t0 = MPI_Wtime(); once(); total += MPI_Wtime() - t0; }
+    double us = total * 1e6 / it_n, lo, hi, sum;
+    MPI_Allreduce(&us, &lo, 1, MPI_DOUBLE, MPI_MIN, MPI_COMM_WORLD);
+    MPI_Allreduce(&us, &hi, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+    MPI_Allreduce(&us, &sum, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+    if (rank == 0) {
+      if (barrier) { if (full) printf("%-10s %18.2f %18.2f %18.2f %12d\n", "", sum / world, lo, hi, it_n); else printf("%-10s %18.2f\n", "", sum / world); }
+      else if (full) printf("%-10zu %18.2f %18.2f %18.2f %12d\n", bytes, sum / world, lo, hi, it_n);
+      else printf("%-10zu %18.2f\n", bytes, sum / world);
+      fflush(stdout);
+    }
+    if (barrier) break;
+  }
+  if (device) { cudaFree(sbuf); cudaFree(rbuf); } else { free(sbuf); free(rbuf); }
+  MPI_Finalize();
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  for (int i = 1; i + 1 < argc; ++i)
+    if (!strcmp(argv[i], "--osu")) return run_osu(argc, argv, argv[i + 1]);
   size_t beg = 8, end = 1024; int iters = 100; bool device = false; bool check = false;
   bool compare = false; int factor = 2, warm = 20;
   std::vector<std::string> ops;

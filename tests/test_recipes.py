@@ -26,8 +26,13 @@ def test_recipe_config_validates(recipe):
     cfg = loader.load_configs(configdir=os.path.join(ROOT, "recipes", recipe, "config"))
     if "pool_specification" in cfg:
         assert S.pool_id(cfg)
+    gr = cfg.get("global_resources") or {}
+    images = set(gr.get("docker_images") or []) | set(gr.get("singularity_images") or [])
     for job in cfg.get("job_specifications") or []:
         for task in job["tasks"]:
+            # `jobs add` refuses a task whose image is not a global resource (unless the job opts out): the dry-run does not check this
+            image = task.get("docker_image") or task.get("singularity_image")
+            assert job.get("allow_run_on_missing_image") or image is None or image in images, (image, sorted(images))
             mi = task.get("multi_instance")
             if mi is not None:
                 assert mi["num_instances"] == "pool_current_dedicated" and mi["mpi"]["runtime"] in ("openmpi", "mpich", "mvapich", "intelmpi", "intelmpi-ofa")
@@ -74,3 +79,23 @@ def test_quantised_gradient_recipe_world2():
 def test_tensorflow_distributed_recipe_world2():
     r = _run_world("recipes/TensorFlow-Distributed/mnist_replica.py", ["--train_steps", "60"])
     assert r["world"] == 2 and r["final_loss"] < 1.0 and r["transport"] == "stub"
+
+
+def test_osu_recipe_runs_through_the_cli_with_osu_output(tmp_path):
+    """The OSU recipe end to end on a 2-slot CPU pool: pool add, jobs add, and the task's stdout is an OSU latency table (-f columns)."""
+    env = dict(os.environ, SHIPYARD_STATE_DIR=str(tmp_path / "state"), SHIPYARD_FAKE_GPUS="2")
+    cfg = os.path.join(ROOT, "recipes", "OSUMicroBenchmarks-Infiniband-MVAPICH", "config")
+    sh = os.path.join(ROOT, "shipyard")
+    try:
+        p = subprocess.run([sh, "pool", "add", "--configdir", cfg, "-y", "--raw"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:]
+        p = subprocess.run([sh, "jobs", "add", "--configdir", cfg, "--tail", "stdout.txt"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-3000:]
+        out = p.stdout
+        assert "# OSU MPI Allreduce Latency Test" in out and "Avg Latency(us)" in out and "Iterations" in out, out[-3000:]
+        rows = [ln.split() for ln in out.splitlines() if ln[:1].isdigit()]
+        sizes = [int(r[0]) for r in rows if len(r) == 5]
+        assert sizes[0] == 4 and sizes[-1] == 1 << 20 and sizes == [4 << i for i in range(len(sizes))], sizes
+        assert all(float(r[2]) <= float(r[1]) <= float(r[3]) for r in rows if len(r) == 5)
+    finally:
+        subprocess.run([sh, "pool", "del", "--configdir", cfg, "-y"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
