@@ -197,7 +197,54 @@ static int run_osu(int argc, char** argv, const char* bench) {
   MPI_Init(&argc, &argv);
   int rank, world;
   MPI_Comm_rank(MPI_COMM_WORLD, &rank); MPI_Comm_size(MPI_COMM_WORLD, &world);
-  if (!title) { if (rank == 0) fprintf(stderr, "mpibench --osu: unknown benchmark %s (collective latency tests only)\n", name.c_str()); MPI_Finalize(); return 2; }
+  if (name == "osu_latency" || name == "osu_bw") {
+    // point-to-point tests between ranks 0 and 1 (host buffers: the MPI face's Send / Recv path): ping-pong latency (half round trip) and
+    // windowed bandwidth (64 non-blocking sends per iteration, then a 4-byte acknowledgement), as in the OSU originals
+    if (world < 2) { if (rank == 0) fprintf(stderr, "mpibench --osu %s needs 2 ranks\n", name.c_str()); MPI_Finalize(); return 3; }
+    if (device) { if (rank == 0) fprintf(stderr, "mpibench --osu %s: host buffers only\n", name.c_str()); MPI_Finalize(); return 3; }
+    const bool bw = name == "osu_bw";
+    if (mx == (size_t)(1 << 20) && bw) mx = 4 << 20;
+    if (mn <= 4) mn = 1;                                  // OSU's point-to-point tests start at one byte
+    const int window = 64;
+    char* sb = (char*)calloc(1, mx + 64); char* rb = (char*)calloc(1, mx + 64);
+    if (rank == 0) printf("# OSU MPI %s Test (shipyard-mpibench over libshipyard_mpi, ranks 0 <-> 1, host buffers)\n# %-8s %18s\n",
+                          bw ? "Bandwidth" : "Latency", "Size", bw ? "Bandwidth (MB/s)" : "Latency (us)");
+    for (size_t bytes = mn; bytes <= mx; bytes *= 2) {
+      int it_n = iters_set ? iters : (bytes > 8192 ? (bw ? 20 : 100) : (bw ? 100 : 1000));
+      int wm_n = bytes > 8192 ? 2 : (warm < 10 ? warm : 10);
+      MPI_Barrier(MPI_COMM_WORLD);
+      double t0 = 0;
+      if (rank < 2) {
+        std::vector<MPI_Request> reqs(window);
+        for (int it = -wm_n; it < it_n; ++it) {
+          if (it == 0) t0 = MPI_Wtime();
+          if (!bw) {
+            if (rank == 0) { MPI_Send(sb, (int)bytes, MPI_CHAR, 1, 1, MPI_COMM_WORLD); MPI_Recv(rb, (int)bytes, MPI_CHAR, 1, 1, MPI_COMM_WORLD, MPI_STATUS_IGNORE); }
+            else { MPI_Recv(rb, (int)bytes, MPI_CHAR, 0, 1, MPI_COMM_WORLD, MPI_STATUS_IGNORE); MPI_Send(sb, (int)bytes, MPI_CHAR, 0, 1, MPI_COMM_WORLD); }
+          } else if (rank == 0) {
+            for (int w = 0; w < window; ++w) MPI_Isend(sb, (int)bytes, MPI_CHAR, 1, 100, MPI_COMM_WORLD, &reqs[w]);
+            MPI_Waitall(window, reqs.data(), MPI_STATUSES_IGNORE);
+            MPI_Recv(rb, 4, MPI_CHAR, 1, 101, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+          } else {
+            for (int w = 0; w < window; ++w) MPI_Irecv(rb, (int)bytes, MPI_CHAR, 0, 100, MPI_COMM_WORLD, &reqs[w]);
+            MPI_Waitall(window, reqs.data(), MPI_STATUSES_IGNORE);
+            MPI_Send(sb, 4, MPI_CHAR, 0, 101, MPI_COMM_WORLD);
+          }
+        }
+        const double el = MPI_Wtime() - t0;
+        if (rank == 0) {
+          if (bw) printf("%-10zu %18.2f\n", bytes, (double)bytes * window * it_n / el / 1e6);
+          else printf("%-10zu %18.2f\n", bytes, el * 1e6 / (2.0 * it_n));
+          fflush(stdout);
+        }
+      }
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    free(sb); free(rb);
+    MPI_Finalize();
+    return 0;
+  }
+  if (!title) { if (rank == 0) fprintf(stderr, "mpibench --osu: unknown benchmark %s (collective latency tests, osu_latency, osu_bw)\n", name.c_str()); MPI_Finalize(); return 2; }
   if (device) {
     const char* g = getenv("SHIPYARD_GPU"); int ndev = 0; cudaGetDeviceCount(&ndev);
     if (ndev == 0) { if (rank == 0) fprintf(stderr, "mpibench --osu: -d cuda requested but no GPU visible\n"); MPI_Finalize(); return 3; }

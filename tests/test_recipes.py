@@ -99,3 +99,17 @@ def test_osu_recipe_runs_through_the_cli_with_osu_output(tmp_path):
         assert all(float(r[2]) <= float(r[1]) <= float(r[3]) for r in rows if len(r) == 5)
     finally:
         subprocess.run([sh, "pool", "del", "--configdir", cfg, "-y"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
+
+
+@pytest.mark.parametrize("bench,header", [("pt2pt/osu_latency", "Latency (us)"), ("pt2pt/osu_bw", "Bandwidth (MB/s)"), ("collective/osu_alltoall", "Avg Latency(us)")])
+def test_osu_front_end_point_to_point_and_collectives(bench, header):
+    """The OSU front end on two host ranks (shared-memory transport): benchmark names with their directory prefix, -m ranges, OSU tables."""
+    exe = os.path.join(ROOT, "batch_shipyard_b200", "_native", "shipyard-mpibench")
+    session = "osu" + uuid.uuid4().hex[:10]
+    procs = [subprocess.Popen([exe, "--osu", bench, "-m", "8:4096", "-i", "50", "-x", "5"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", SHIPYARD_COLL_SESSION=session, SHIPYARD_GPU="-1")) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    rows = [ln.split() for ln in outs[0].splitlines() if ln[:1].isdigit()]
+    assert header in outs[0] and [int(r[0]) for r in rows] == [8 << i for i in range(10)], outs[0]
+    assert all(float(r[1]) > 0 for r in rows)
