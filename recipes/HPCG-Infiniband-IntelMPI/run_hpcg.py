@@ -30,6 +30,11 @@ def main():
     dev_index = int(gpu) % max(1, torch.cuda.device_count()) if use_cuda else None
     if use_cuda:
         torch.cuda.set_device(dev_index)
+    downscaled = None
+    if not use_cuda and not os.environ.get("SHIPYARD_CPU_FULL_SIZE") and (a.n > 32 or a.t > 5):
+        # virtual (CPU) slots are a functional mode: the GPU-sized problem of the recipe would run for hours on CPU threads
+        downscaled = {"requested_n": a.n, "requested_t": a.t}
+        a.n, a.t, a.levels = min(a.n, 32), min(a.t, 5.0), min(a.levels, 3)
     session = (os.environ.get("SHIPYARD_COLL_SESSION") or os.environ.get("TORCHELASTIC_RUN_ID") or f"hpcg-{os.getppid()}") + "-hpcg"
     comm = Communicator(rank, world, session, dev_index, heap_bytes=256 << 20)
     try:
@@ -41,6 +46,8 @@ def main():
         comm.close()
         sys.exit(1)
     if rank == 0:
+        if downscaled:
+            res["downscaled_for_cpu"] = downscaled
         print(json.dumps({k: (round(v, 6) if isinstance(v, float) and k != "residual_reduction" else v) for k, v in res.items()}), flush=True)
     comm.close()
 

@@ -38,6 +38,11 @@ def main():
     dev_index = int(gpu) % max(1, torch.cuda.device_count()) if use_cuda else None
     if use_cuda:
         torch.cuda.set_device(dev_index)
+    downscaled = None
+    if not use_cuda and not os.environ.get("SHIPYARD_CPU_FULL_SIZE") and a.n > 2048:
+        # virtual (CPU) slots are a functional mode: emulated bf16 GEMMs at the recipe's GPU problem size would run for hours
+        downscaled = {"requested_n": a.n, "requested_nb": a.nb}
+        a.n, a.nb, a.runs = 1024, min(a.nb, 128), 1
     n = a.n // a.nb * a.nb
     session = (os.environ.get("SHIPYARD_COLL_SESSION") or os.environ.get("TORCHELASTIC_RUN_ID") or f"hpl-{os.getppid()}") + "-hpl"
     comm = Communicator(rank, world, session, dev_index, heap_bytes=hpl.heap_bytes_for(n, a.nb))
@@ -56,6 +61,8 @@ def main():
     if rank == 0:
         best = {k: (round(v, 6) if isinstance(v, float) else v) for k, v in best.items() if k != "residual_history"}
         best.update({"N": n, "NB": a.nb, "P": 1, "Q": world, "transport": comm.transport})
+        if downscaled:
+            best["downscaled_for_cpu"] = downscaled
         print(json.dumps(best), flush=True)
     comm.close()
 

@@ -36,9 +36,15 @@ def main():
     dev_index = int(gpu) % max(1, torch.cuda.device_count()) if use_cuda else None
     if use_cuda:
         torch.cuda.set_device(dev_index)
+    if not use_cuda and a.model == "resnet50" and not os.environ.get("SHIPYARD_ALLOW_CPU_RESNET50"):
+        # a GPU recipe scheduled on a pool without GPUs (virtual slots): ResNet-50 at this batch size would run for hours on CPU threads
+        if rank == 0:
+            print(json.dumps({"error": "no GPU visible to this task: use the -CPU recipe variant (--model tiny) or set SHIPYARD_ALLOW_CPU_RESNET50=1",
+                              "world": world, "model": a.model}), flush=True)
+        sys.exit(2)
     torch.manual_seed(1234)
     session = os.environ.get("SHIPYARD_COLL_SESSION", f"pytorch-gpu-{os.getppid()}") + "-train"
-    comm = Communicator(rank, world, session, dev_index, heap_bytes=(1 << 30) if use_cuda else (256 << 20))
+    comm = Communicator(rank, world, session, dev_index, heap_bytes=(1 << 30) if (use_cuda or a.model == "resnet50") else (256 << 20))
     nclass = 1000 if a.model == "resnet50" else 10
     model = resnet50() if a.model == "resnet50" else resnet_tiny(nclass)
     tr = FusedDataParallelTrainer(model, comm, (a.batch, 3, a.image, a.image), nclass, lr=a.lr)

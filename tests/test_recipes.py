@@ -113,3 +113,23 @@ def test_osu_front_end_point_to_point_and_collectives(bench, header):
     rows = [ln.split() for ln in outs[0].splitlines() if ln[:1].isdigit()]
     assert header in outs[0] and [int(r[0]) for r in rows] == [8 << i for i in range(10)], outs[0]
     assert all(float(r[1]) > 0 for r in rows)
+
+
+@pytest.mark.parametrize("recipe,key", [("HPLinpack-Infiniband-IntelMPI", "scaled_residual"), ("HPCG-Infiniband-IntelMPI", "validity")])
+def test_hpc_recipes_run_through_the_cli_on_a_cpu_pool(recipe, key, tmp_path):
+    """The GPU-sized HPC recipes on a 2-slot CPU pool: the bodies detect the virtual slots, downscale (and say so) and still pass their
+    validity checks; exit code 0 through pool add / jobs add."""
+    env = dict(os.environ, SHIPYARD_STATE_DIR=str(tmp_path / "state"), SHIPYARD_FAKE_GPUS="2")
+    cfg = os.path.join(ROOT, "recipes", recipe, "config")
+    sh = os.path.join(ROOT, "shipyard")
+    try:
+        p = subprocess.run([sh, "pool", "add", "--configdir", cfg, "-y", "--raw"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:]
+        p = subprocess.run([sh, "jobs", "add", "--configdir", cfg, "--tail", "stdout.txt"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert p.returncode == 0 and "task_state: completed" in p.stdout and "exit_code:" not in p.stdout, p.stdout[-3000:]
+        line = next(ln for ln in p.stdout.splitlines() if ln.startswith("{") and key in ln)
+        out = json.loads(line)
+        assert out["world"] == 2 and "downscaled_for_cpu" in out and out["transport"] == "stub", out
+        assert out.get("passed", True) and (out.get("validity") or {"passed": True})["passed"], out
+    finally:
+        subprocess.run([sh, "pool", "del", "--configdir", cfg, "-y"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
