@@ -29,29 +29,74 @@ def _match(rel: str, include: Iterable[str], exclude: Iterable[str]) -> bool:
     return not any(fnmatch.fnmatch(rel, p) for p in exclude)
 
 
+_NATIVE_MIN_BYTES = 1 << 20          # smaller files: the per-ticket overhead is not worth it, shutil.copy2 in this process
+
+
+class _Copier:
+    """Bounded-concurrency file copier: files of 1 MB and more go to the worker threads of the native staging library (copy_file_range
+    in the kernel, mode + mtime preserved: ``sy_stage_submit_copy``) and run in parallel; small files are copied inline.  The reference moves task
+    data with blobxfer's parallel transfers (/root/reference/convoy/data.py:219-291); ``SHIPYARD_NATIVE_COPY=0`` forces the inline path."""
+
+    def __init__(self):
+        self.stager, self.tickets = None, []
+        if os.environ.get("SHIPYARD_NATIVE_COPY", "1") not in ("0", "", "off", "false"):
+            try:
+                from ..ops.stage import Stager
+                self.stager = Stager(None, arena_bytes=64 << 20, concurrency=int(os.environ.get("SHIPYARD_COPY_THREADS", "4") or 4))
+            except Exception as e:  # noqa: BLE001 - the library is optional for the mover: say so once, then copy inline
+                _log("download", f"native copier unavailable ({type(e).__name__}: {e}); copying inline")
+
+    def copy(self, src: str, out: str) -> None:
+        if self.stager is not None and os.path.getsize(src) >= _NATIVE_MIN_BYTES:
+            self.tickets.append((self.stager.submit_copy(src, out), src))
+        else:
+            shutil.copy2(src, out)
+
+    def finish(self) -> None:
+        """Wait for every queued copy; the first failure is raised after all tickets have been collected."""
+        err = None
+        for t, src in self.tickets:
+            try:
+                self.stager.wait(t)
+            except Exception as e:  # noqa: BLE001
+                err = err or OSError(f"copy of {src} failed: {e}")
+            finally:
+                self.stager.release(t)
+        self.tickets = []
+        if self.stager is not None:
+            self.stager.close()
+            self.stager = None
+        if err:
+            raise err
+
+
 def copy_tree(src: str, dst: str, include=(), exclude=(), collect: Optional[list] = None) -> tuple[int, int]:
     """Copy files under `src` (or the single file `src`) to `dst`; returns (files, bytes); `collect` receives the written paths."""
     n = nb = 0
-    if os.path.isfile(src):
-        os.makedirs(dst, exist_ok=True)
-        out = os.path.join(dst, os.path.basename(src))
-        shutil.copy2(src, out)
-        if collect is not None:
-            collect.append(out)
-        return 1, os.path.getsize(src)
-    for d, _, fs in os.walk(src):
-        for fn in fs:
-            p = os.path.join(d, fn)
-            rel = os.path.relpath(p, src).replace(os.sep, "/")
-            if not _match(rel, include, exclude):
-                continue
-            out = os.path.join(dst, rel)
-            os.makedirs(os.path.dirname(out), exist_ok=True)
-            shutil.copy2(p, out)
+    cp = _Copier()
+    try:
+        if os.path.isfile(src):
+            os.makedirs(dst, exist_ok=True)
+            out = os.path.join(dst, os.path.basename(src))
+            cp.copy(src, out)
             if collect is not None:
                 collect.append(out)
-            n += 1; nb += os.path.getsize(p)
-    return n, nb
+            return 1, os.path.getsize(src)
+        for d, _, fs in os.walk(src):
+            for fn in fs:
+                p = os.path.join(d, fn)
+                rel = os.path.relpath(p, src).replace(os.sep, "/")
+                if not _match(rel, include, exclude):
+                    continue
+                out = os.path.join(dst, rel)
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                cp.copy(p, out)
+                if collect is not None:
+                    collect.append(out)
+                n += 1; nb += os.path.getsize(p)
+        return n, nb
+    finally:
+        cp.finish()
 
 
 def record_stage_manifest(paths: list, source: str) -> Optional[str]:

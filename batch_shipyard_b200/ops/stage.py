@@ -33,6 +33,7 @@ def load() -> C.CDLL:
         lib.sy_stage_destroy.argtypes = [vp]
         lib.sy_stage_submit_file.argtypes = [vp, C.c_char_p, vp, sz, sz]; lib.sy_stage_submit_file.restype = lg
         lib.sy_stage_submit_host.argtypes = [vp, vp, sz, vp]; lib.sy_stage_submit_host.restype = lg
+        lib.sy_stage_submit_copy.argtypes = [vp, C.c_char_p, C.c_char_p, sz, sz]; lib.sy_stage_submit_copy.restype = lg
         lib.sy_stage_submit_pinned.argtypes = [vp, vp, sz, vp, vp]; lib.sy_stage_submit_pinned.restype = lg
         lib.sy_stage_pinned_alloc.argtypes = [vp, sz]; lib.sy_stage_pinned_alloc.restype = vp
         lib.sy_stage_pinned_free.argtypes = [vp, vp]
@@ -86,6 +87,14 @@ class Stager:
 
     def submit_file(self, path: str, dptr: int = 0, offset: int = 0, nbytes: int = 0) -> int:
         t = self.lib.sy_stage_submit_file(self._h, path.encode(), C.c_void_p(dptr), offset, nbytes)
+        if t < 0:
+            raise StageError(self.lib.sy_stage_last_error().decode())
+        return int(t)
+
+    def submit_copy(self, src: str, dst: str, offset: int = 0, nbytes: int = 0) -> int:
+        """File -> file copy on a worker thread (copy_file_range, bounce through the arena where the kernel refuses): the task-side data
+        mover's primitive.  Mode and mtime are carried over like shutil.copy2."""
+        t = self.lib.sy_stage_submit_copy(self._h, os.fsencode(src), os.fsencode(dst), offset, nbytes)
         if t < 0:
             raise StageError(self.lib.sy_stage_last_error().decode())
         return int(t)

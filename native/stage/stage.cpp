@@ -38,6 +38,7 @@ enum TicketState { T_QUEUED = 0, T_RUNNING = 1, T_DONE = 2, T_FAILED = 3 };
 struct Ticket {
   long id = 0;
   std::string path;            // file source (empty => host memory source)
+  std::string dst_path;        // file -> file copy (the task-side data mover): no device involved
   const void* host_src = nullptr;
   bool pinned_src = false;     // host_src is page-locked: one cudaMemcpyAsync straight from it, no bounce through the arena
   cudaEvent_t wait_ev = nullptr;   // the copy stream waits for this event first (e.g. "the step that read dptr last is done")
@@ -104,6 +105,52 @@ static void worker_main(sy_stage* s, int wi) {
     }
     size_t done = 0; int ci = 0;
     std::vector<bool> chunk_busy(s->chunks_per_worker, false);
+    if (ok && !t->dst_path.empty()) {
+      // file -> file: copy_file_range keeps the bytes in the kernel (reflink / server-side copy where the file system can); when it is
+      // refused (EXDEV, EINVAL, ENOSYS, old kernels) the worker's arena slice is the bounce buffer.  Mode and mtime are carried over.
+      struct stat st{};
+      if (fstat(fd, &st) != 0) { ok = false; err = "fstat " + t->path + ": " + strerror(errno); }
+      int out = ok ? open(t->dst_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, st.st_mode & 07777) : -1;
+      if (ok && out < 0) { ok = false; err = "open " + t->dst_path + ": " + strerror(errno); }
+      if (ok) {
+        const size_t total = t->bytes ? t->bytes : (size_t)st.st_size;
+        t->bytes = total;
+        bool use_cfr = true;
+        off_t in_off = (off_t)t->offset, out_off = 0;
+        while (ok && done < total) {
+          if (use_cfr) {
+            ssize_t r = copy_file_range(fd, &in_off, out, &out_off, total - done, 0);
+            if (r > 0) { done += (size_t)r; { std::lock_guard<std::mutex> lk(s->mu); t->done_bytes = done; } continue; }
+            if (r == 0) { ok = false; err = "short read on " + t->path; break; }
+            if (errno == EINTR) continue;
+            use_cfr = false;                                  // fall through to the bounce path from the current offsets
+          }
+          const size_t n = total - done < s->chunk_bytes ? total - done : s->chunk_bytes;
+          size_t got = 0;
+          while (got < n) {
+            ssize_t r = pread(fd, slice + got, n - got, (off_t)(t->offset + done + got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) { ok = false; err = "short read on " + t->path; break; }
+            got += (size_t)r;
+          }
+          size_t put = 0;
+          while (ok && put < n) {
+            ssize_t w = pwrite(out, slice + put, n - put, (off_t)(done + put));
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) { ok = false; err = "write " + t->dst_path + ": " + strerror(errno); break; }
+            put += (size_t)w;
+          }
+          if (ok) { done += n; std::lock_guard<std::mutex> lk(s->mu); t->done_bytes = done; }
+        }
+        if (ok) {
+          fchmod(out, st.st_mode & 07777);
+          struct timespec ts[2] = {st.st_atim, st.st_mtim};
+          futimens(out, ts);
+        }
+      }
+      if (out >= 0 && close(out) != 0 && ok) { ok = false; err = "close " + t->dst_path + ": " + strerror(errno); }
+      done = t->bytes;                                        // skip the device loop below
+    }
     if (ok && gpu && t->wait_ev) {
       cudaError_t e = cudaStreamWaitEvent(stream, t->wait_ev, 0);
       if (e != cudaSuccess) { ok = false; err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e); }
@@ -207,7 +254,7 @@ extern "C" int sy_stage_destroy(sy_stage* s) {
 }
 
 static long submit(sy_stage* s, Ticket* t) {
-  if (!t->dptr) {
+  if (!t->dptr && t->dst_path.empty()) {
     if (s->device >= 0) {
       cudaSetDevice(s->device);
       cudaError_t e = cudaMalloc(&t->dptr, t->bytes ? t->bytes : 1);
@@ -234,6 +281,14 @@ extern "C" long sy_stage_submit_file(sy_stage* s, const char* path, void* dptr, 
   if (bytes == 0 || offset + bytes > (size_t)st.st_size) bytes = (size_t)st.st_size - offset;
   Ticket* t = new Ticket();
   t->path = path; t->offset = offset; t->bytes = bytes; t->dptr = dptr;
+  return submit(s, t);
+}
+
+// file -> file copy on a worker thread (bytes = 0: the whole file from `offset`); wait / query / release as for any ticket
+extern "C" long sy_stage_submit_copy(sy_stage* s, const char* src, const char* dst, size_t offset, size_t bytes) {
+  if (!src || !dst || !src[0] || !dst[0]) { g_err = "submit_copy: empty path"; return -1; }
+  Ticket* t = new Ticket();
+  t->path = src; t->dst_path = dst; t->offset = offset; t->bytes = bytes;
   return submit(s, t);
 }
 

@@ -194,3 +194,39 @@ def test_mover_refuses_remote_paths_that_leave_the_storage_root(tmp_path, capsys
     finally:
         os.environ.pop("SHIPYARD_TASK_RESULT", None)
     assert not os.path.exists(os.path.join(os.path.dirname(root), "outside"))
+
+
+def test_copy_tree_uses_the_native_parallel_copier_and_matches_shutil(tmp_path, monkeypatch):
+    """Files of 1 MB and more go through sy_stage_submit_copy on worker threads (content, mode and mtime as shutil.copy2), small ones inline;
+    include / exclude filters, the collected path list and the failure path (unwritable destination) behave the same with and without it."""
+    import os
+    from batch_shipyard_b200.data import mover
+    from batch_shipyard_b200.ops import stage as stage_mod
+    src = tmp_path / "src"; (src / "sub").mkdir(parents=True)
+    blobs = {"big0.bin": os.urandom((3 << 20) + 17), "sub/big1.bin": os.urandom(1 << 20), "small.txt": b"hello", "sub/skip.tmp": os.urandom(2 << 20)}
+    for rel, data in blobs.items():
+        p = src / rel; p.write_bytes(data); os.chmod(p, 0o640); os.utime(p, (1_600_000_000, 1_600_000_500))
+    calls = []
+    real = stage_mod.Stager.submit_copy
+    monkeypatch.setattr(stage_mod.Stager, "submit_copy", lambda self, a, b, *k: calls.append(a) or real(self, a, b, *k))
+    for native in ("1", "0"):
+        monkeypatch.setenv("SHIPYARD_NATIVE_COPY", native)
+        calls.clear()
+        dst = tmp_path / f"dst{native}"
+        got = []
+        n, nb = mover.copy_tree(str(src), str(dst), exclude=["*.tmp"], collect=got)
+        assert (n, nb) == (3, sum(len(v) for k, v in blobs.items() if not k.endswith(".tmp"))) and len(got) == 3
+        assert sorted(os.path.basename(c) for c in calls) == (["big0.bin", "big1.bin"] if native == "1" else [])
+        for rel, data in blobs.items():
+            q = dst / rel
+            if rel.endswith(".tmp"):
+                assert not q.exists()
+                continue
+            st = os.stat(q)
+            assert q.read_bytes() == data and (st.st_mode & 0o777) == 0o640 and int(st.st_mtime) == 1_600_000_500, rel
+    # a failing native copy surfaces as an error, not as a silently missing file
+    monkeypatch.setenv("SHIPYARD_NATIVE_COPY", "1")
+    ro = tmp_path / "ro"; ro.mkdir(); (ro / "big0.bin").mkdir()          # destination path is a directory: open(O_WRONLY) fails
+    import pytest as _pytest
+    with _pytest.raises(OSError):
+        mover.copy_tree(str(src / "big0.bin"), str(ro))
