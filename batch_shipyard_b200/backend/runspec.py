@@ -202,7 +202,15 @@ def build_task_spec(b, pool: dict, job: dict, t: dict, nodes: list[dict]) -> tup
     if epi:
         items.append(("system_epilogue", "; ".join(epi)))
     command = t.get("command") or ":"
-    session = f"{pid}-{jid}-{tid}-{t.get('retry_count', 0)}-{t.get('requeue_count', 0)}"
+    # the rendezvous name is global to the machine (abstract UNIX socket + POSIX shm): two shipyard installations with different state
+    # directories may run pools / jobs / tasks of the same names at the same time, so the state directory is part of it
+    inst = zlib.crc32(os.path.realpath(b.root).encode()) & 0xffffff
+    session = f"{pid}-{jid}-{tid}-{t.get('retry_count', 0)}-{t.get('requeue_count', 0)}-{inst:06x}"
+    if len(session) > 72:
+        # the socket name is cut at 106 characters by the transport (sockaddr_un) and programs append their own suffix: long ids are
+        # folded into a digest so that the distinguishing tail (attempt counters, installation) can never be truncated away
+        import hashlib
+        session = session[:40] + "-" + hashlib.sha1(session.encode()).hexdigest()[:28]
     # a stable, collision-resistant rendezvous port per task attempt
     port = 20000 + (zlib.crc32(session.encode()) % 20000)
     items += [("session", session), ("master_port", str(port))]

@@ -371,3 +371,23 @@ def test_node_fill_type_places_tasks_pack_or_spread(tmp_path, fill, expect):
     assert per_node == expect, per_node
     agent.run(until_idle=True, max_seconds=60)
     assert all(t["result"] == "success" for t in b.list_tasks("job1"))
+
+
+def test_rendezvous_session_is_unique_per_installation_and_survives_long_ids(tmp_path):
+    """Two state directories running identically named pool / job / task must not share a rendezvous name (abstract socket, POSIX shm are
+    machine-global), and 64-character ids must not push the distinguishing tail past the 106 characters the socket name keeps."""
+    import re
+    from batch_shipyard_b200.backend import runspec
+    from batch_shipyard_b200.backend.local import LocalBackend
+
+    def session_of(state, pid, jid, tid, retry=0):
+        b = LocalBackend(state_dir=str(state))
+        t = {"id": tid, "command": "true", "retry_count": retry}
+        spec, _ = runspec.build_task_spec(b, {"id": pid}, {"id": jid}, t, [{"id": "n0", "gpu_index": None}])
+        return re.search(r"^session\t(.*)$", open(spec).read(), re.M).group(1)
+
+    a = session_of(tmp_path / "a", "p", "j", "t")
+    assert a != session_of(tmp_path / "b", "p", "j", "t") and a == session_of(tmp_path / "a", "p", "j", "t")
+    long_ids = ("p" * 64, "j" * 64, "t" * 64)
+    s0, s1 = session_of(tmp_path / "a", *long_ids, retry=0), session_of(tmp_path / "a", *long_ids, retry=1)
+    assert s0 != s1 and len(s0) <= 72 and len(s1) <= 72 and s0[:40] == s1[:40]
