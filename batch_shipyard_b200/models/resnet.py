@@ -142,6 +142,63 @@ def resnet_tiny(num_classes: int = 10) -> ResNet:
     return ResNet((1, 1, 1, 1), num_classes, width=16)
 
 
+class BasicBlock(nn.Module):
+    """Two 3x3 ConvBN layers with an identity / 1x1 projection shortcut (the CIFAR ResNet block)."""
+
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.c1 = ConvBN(cin, cout, 3, stride)
+        self.c2 = ConvBN(cout, cout, 3, 1, relu=True, zero_gamma=True)
+        self.down = ConvBN(cin, cout, 1, stride, relu=False) if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        idt = x if self.down is None else self.down(x)
+        return self.c2(self.c1(x), residual=idt)
+
+
+class ResNetCifar(nn.Module):
+    """ResNet-6n+2 for 32x32 inputs (n = 3: ResNet-20): 3x3 stem, three stages of n BasicBlocks at 16 / 32 / 64 channels, global average
+    pool, linear classifier — the network behind the CIFAR-10 examples of the reference's MXNet and CNTK recipes
+    (/root/reference/recipes/MXNet-CPU/README.md:39-40 "cifar-10 examples run resnet")."""
+    s2d_stem = False
+
+    def __init__(self, n: int = 3, num_classes: int = 10, width: int = 16):
+        super().__init__()
+        self.stem = ConvBN(3, width, 3, 1)
+        blocks, cin = [], width
+        for i in range(3):
+            for j in range(n):
+                blocks.append(BasicBlock(cin, width * 2 ** i, 2 if (i > 0 and j == 0) else 1))
+                cin = width * 2 ** i
+        self.blocks = nn.Sequential(*blocks)
+        self.fc = nn.Linear(cin, num_classes)
+        for m in self.modules():                      # small channel counts: plain library convolutions, no dispatcher race
+            if hasattr(m, "use_tc_gemm"):
+                m.use_tc_gemm = False
+
+    def forward(self, x):
+        x = self.blocks(self.stem(x))
+        return self.fc(x.mean(dim=(2, 3)).to(self.fc.weight.dtype))
+
+
+def resnet20_cifar(num_classes: int = 10) -> ResNetCifar:
+    return ResNetCifar(3, num_classes)
+
+
+def synthetic_cifar(n: int, seed: int, num_classes: int = 10, size: int = 32):
+    """CIFAR-shaped synthetic data with a learnable signal: every class is a fixed low-frequency colour pattern (seed-independent) plus
+    per-sample shift, contrast jitter and pixel noise.  Returns uint8 NHWC images [n, size, size, 3] and int64 labels."""
+    g0 = torch.Generator().manual_seed(4321)
+    coarse = torch.rand(num_classes, 3, 4, 4, generator=g0)
+    templates = F.interpolate(coarse, size=(size, size), mode="bilinear", align_corners=False)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, num_classes, (n,), generator=g)
+    dx, dy = torch.randint(-3, 4, (n,), generator=g), torch.randint(-3, 4, (n,), generator=g)
+    x = torch.stack([torch.roll(templates[int(c)], (int(a), int(b)), (1, 2)) for c, a, b in zip(y, dy, dx)])
+    x = (x - 0.5) * (0.7 + 0.6 * torch.rand(n, 1, 1, 1, generator=g)) + 0.5 + 0.15 * (torch.rand(n, 3, size, size, generator=g) - 0.5)
+    return (x.clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous(), y
+
+
 def set_tc_gemm(m: nn.Module, flag: bool) -> None:
     for mod in m.modules():
         if hasattr(mod, "use_tc_gemm"):

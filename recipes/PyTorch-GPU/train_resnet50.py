@@ -27,8 +27,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--image", type=int, default=224)
-    ap.add_argument("--model", default="resnet50", choices=["resnet50", "tiny", "lenet"],
-                    help="resnet50 (the GPU recipes), tiny (a 4-block ResNet for smoke runs), lenet (the MNIST network of the single-framework CPU recipes, synthetic digits)")
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "tiny", "lenet", "resnet20"],
+                    help="resnet50 (the GPU recipes), tiny (a 4-block ResNet for smoke runs), lenet (the MNIST network of the single-framework CPU recipes, synthetic digits), resnet20 (the CIFAR-10 ResNet of the MXNet / CNTK examples, synthetic CIFAR-shaped images)")
     ap.add_argument("--lr", type=float, default=0.1)
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -56,6 +56,15 @@ def main():
         for slot in range(2):                                    # two alternating batches of learnable synthetic digits per rank
             xs, ys = synthetic_digits(a.batch, seed=1000 * rank + slot)
             st.host_x[slot].copy_(xs); st.host_y[slot].copy_(ys)
+    elif a.model == "resnet20":
+        from batch_shipyard_b200.models.resnet import resnet20_cifar, synthetic_cifar as synthetic_digits
+        a.image = 32
+        model = resnet20_cifar(nclass)
+        tr = FusedDataParallelTrainer(model, comm, (a.batch, 3, 32, 32), nclass, lr=a.lr)
+        st = tr.make_stager(depth=2)
+        for slot in range(2):
+            xs, ys = synthetic_digits(a.batch, seed=1000 * rank + slot)
+            st.host_x[slot].copy_(xs); st.host_y[slot].copy_(ys)
     else:
         model = resnet50() if a.model == "resnet50" else resnet_tiny(nclass)
         tr = FusedDataParallelTrainer(model, comm, (a.batch, 3, a.image, a.image), nclass, lr=a.lr)
@@ -68,7 +77,7 @@ def main():
     t0 = time.time()
     losses = []
     st.prefetch(0)
-    fresh = a.model == "lenet" and not use_cuda           # CPU pools: a new batch of synthetic digits every step (the host buffers are plain memory)
+    fresh = a.model in ("lenet", "resnet20") and not use_cuda           # CPU pools: a new batch of synthetic digits every step (the host buffers are plain memory)
     for i in range(a.steps):
         st.run_step(i % 2)
         if fresh:
@@ -79,7 +88,7 @@ def main():
     dt = time.time() - t0
     comm.check_status()
     extra = {}
-    if a.model == "lenet":
+    if a.model in ("lenet", "resnet20"):
         xs, ys = synthetic_digits(512, seed=987654)          # held-out digits, the same on every rank
         with torch.no_grad():
             model.eval()

@@ -135,16 +135,17 @@ def test_hpc_recipes_run_through_the_cli_on_a_cpu_pool(recipe, key, tmp_path):
         subprocess.run([sh, "pool", "del", "--configdir", cfg, "-y"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
 
 
-def test_lenet_recipe_body_learns():
-    """The MNIST-network body of the single-framework CPU recipes at world 2 (stub transport): the loss falls by an order of magnitude and
-    the held-out synthetic digits are classified."""
+@pytest.mark.parametrize("model,steps,lr", [("lenet", "120", "0.01"), ("resnet20", "50", "0.05")])
+def test_small_model_recipe_bodies_learn(model, steps, lr):
+    """The MNIST LeNet / CIFAR ResNet-20 bodies of the single-framework CPU recipes at world 2 (stub transport): the loss falls by a factor
+    of four at least and the held-out synthetic images are classified."""
     script = os.path.join(ROOT, "recipes", "PyTorch-GPU", "train_resnet50.py")
-    session = "lenet" + uuid.uuid4().hex[:10]
-    procs = [subprocess.Popen([sys.executable, script, "--model", "lenet", "--steps", "120", "--batch", "64", "--lr", "0.01"], stdout=subprocess.PIPE,
+    session = model + uuid.uuid4().hex[:10]
+    procs = [subprocess.Popen([sys.executable, script, "--model", model, "--steps", steps, "--batch", "64", "--lr", lr], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True,
                               env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", SHIPYARD_COLL_SESSION=session, SHIPYARD_GPU="-1", OMP_NUM_THREADS="2"))
              for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     out = json.loads(outs[0].strip().splitlines()[-1])
-    assert out["model"] == "lenet" and out["world"] == 2 and out["last_loss"] < 0.25 * out["first_loss"] and out["test_accuracy"] > 0.9, out
+    assert out["model"] == model and out["world"] == 2 and out["last_loss"] < 0.25 * out["first_loss"] and out["test_accuracy"] > 0.9, out
